@@ -1,0 +1,205 @@
+"""
+Generate golden fixtures from the UNMODIFIED reference (quantscious/finmlkit, imported from /root/reference).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    FMK_CONSOLE_LOGGER_LEVEL=ERROR PYTHONPATH=/root/reference python tests/golden/make_golden.py
+
+Writes tests/golden/*.npz.  Each file holds the inputs (``in_*``) and the reference outputs (``ref_*``) of one case.
+Footprint ragged lists are stored in CSR form (``ref_fp_off`` + flat arrays).  The script also cross-checks the C oracle
+against the reference on 1M-tick streams (not stored) and prints the result.
+"""
+import os
+import sys
+
+os.environ.setdefault("FMK_CONSOLE_LOGGER_LEVEL", "ERROR")
+sys.path.insert(0, "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+
+import numpy as np  # noqa: E402
+
+from finmlkit.bar.logic import (_time_bar_indexer, _tick_bar_indexer, _volume_bar_indexer, _dollar_bar_indexer,  # noqa: E402
+                                _cusum_bar_indexer)
+from finmlkit.bar.base import (comp_bar_ohlcv, comp_bar_directional_features, comp_bar_trade_size_features,  # noqa: E402
+                               comp_bar_footprints)
+from finmlkit.feature.core.utils import comp_lagged_returns  # noqa: E402
+from finmlkit.feature.core.volatility import ewmst  # noqa: E402
+from finmlkit.label.tbm import triple_barrier  # noqa: E402
+
+from finmlkit_b200.synth import synth_trades  # noqa: E402
+
+
+def csr(lists, dtype):
+    off = np.zeros(len(lists) + 1, np.int64)
+    for i, x in enumerate(lists):
+        off[i + 1] = off[i] + len(x)
+    flat = np.concatenate([np.asarray(x) for x in lists]).astype(dtype) if len(lists) else np.zeros(0, dtype)
+    return off, flat
+
+
+def ref_bundle(ts, px, qty, side, idx, prefix, out, tick=0.1, theta_val=0.05, footprints=True):
+    """All per-bar reductions of the reference for one set of close indices."""
+    o = comp_bar_ohlcv(px, qty, idx)
+    for k, name in enumerate(["open", "high", "low", "close", "volume", "vwap", "trades", "median"]):
+        out[f"ref_{prefix}_ohlcv_{name}"] = o[k]
+    d = comp_bar_directional_features(px, qty, idx, side)
+    for k in range(14):
+        out[f"ref_{prefix}_dir_{k}"] = d[k]
+    nb = len(idx) - 1
+    theta = np.full(nb, theta_val)
+    if nb > 3:
+        theta[3] = 0.0
+    out[f"in_{prefix}_theta"] = theta
+    t = comp_bar_trade_size_features(qty, theta, idx, 5.0)
+    for k in range(4):
+        out[f"ref_{prefix}_ts_{k}"] = t[k]
+    if footprints:
+        f = comp_bar_footprints(px, qty, idx, side, tick, o[2], o[1], 3.0)
+        dts = [np.int32, np.float32, np.float32, np.int32, np.int32, np.bool_, np.bool_]
+        for k in range(7):
+            off, flat = csr(list(f[k]), dts[k])
+            out[f"ref_{prefix}_fp_{k}"] = flat
+        out[f"ref_{prefix}_fp_off"] = off
+        for k in range(7, 13):
+            out[f"ref_{prefix}_fp_{k}"] = np.asarray(f[k])
+
+
+def case_stream(name, ts, px, qty, side, *, interval=60.0, tick_thr=100, vol_thr=5.0, dol_thr=1e5, tick=0.1,
+                ret_window=60.0, half_life=60.0, tbm=True):
+    out = {"in_ts": ts, "in_px": px, "in_qty": qty, "in_side": side,
+           "in_params": np.array([interval, tick_thr, vol_thr, dol_thr, tick, ret_window, half_life])}
+    clock, tidx = _time_bar_indexer(ts, interval)
+    out["ref_time_clock"], out["ref_time_idx"] = clock, tidx
+    out["ref_tick_idx"] = np.array(_tick_bar_indexer(ts, tick_thr), dtype=np.int64)
+    out["ref_volume_idx"] = np.array(_volume_bar_indexer(qty, vol_thr), dtype=np.int64)
+    out["ref_dollar_idx"] = np.array(_dollar_bar_indexer(px, qty, dol_thr), dtype=np.int64)
+    ret = comp_lagged_returns(ts, px, ret_window, True)
+    out["ref_lagret_log"] = ret
+    out["ref_lagret_simple"] = comp_lagged_returns(ts, px, ret_window, False)
+    sig = ewmst(ts, ret, half_life)
+    out["ref_ewmst"] = sig
+    sig_in = sig.copy()
+    out["in_cusum_sigma"] = sig.copy()
+    out["ref_cusum_idx"] = np.array(_cusum_bar_indexer(ts, px, sig_in, 5e-4, 2.0), dtype=np.int64)
+    out["ref_cusum_sigma_filled"] = sig_in
+    ref_bundle(ts, px, qty, side, tidx, "time", out, tick=tick)
+    ref_bundle(ts, px, qty, side, out["ref_dollar_idx"], "dollar", out, tick=tick)
+    ref_bundle(ts, px, qty, side, out["ref_volume_idx"], "volume", out, tick=tick)
+    ref_bundle(ts, px, qty, side, out["ref_tick_idx"], "tick", out, tick=tick, footprints=False)
+    if len(out["ref_cusum_idx"]) >= 2:
+        ref_bundle(ts, px, qty, side, out["ref_cusum_idx"], "cusum", out, tick=tick, footprints=False)
+    if tbm:
+        # events: dollar-bar closes with a finite sigma, excluding those too close to the end
+        ev = out["ref_dollar_idx"][1:]
+        ev = ev[np.isfinite(sig[ev])]
+        ev = ev[ts[ev] + int(interval * 5e9) <= ts[-1]]
+        if len(ev) > 0:
+            tg = sig[ev] * 1.0 + 1e-5
+            out["in_tbm_events"], out["in_tbm_targets"] = ev, tg
+            out["in_tbm_params"] = np.array([2.0, 2.0, interval * 5, 1.0, 0.0])
+            lab, tch, rets, rat = triple_barrier(ts, px, ev, tg, (2.0, 2.0), interval * 5, 1.0, None, 0.0)
+            out["ref_tbm_labels"], out["ref_tbm_touch"], out["ref_tbm_rets"], out["ref_tbm_ratios"] = lab, tch, rets, rat
+            sd = np.where(np.arange(len(ev)) % 3 == 0, -1, 1).astype(np.int8)
+            out["in_tbm_side"] = sd
+            lab, tch, rets, rat = triple_barrier(ts, px, ev, tg, (1.0, np.inf), interval * 2, 0.0, sd, 1e-4)
+            out["ref_tbm_meta_labels"], out["ref_tbm_meta_touch"] = lab, tch
+            out["ref_tbm_meta_rets"], out["ref_tbm_meta_ratios"] = rets, rat
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    nb = {k: len(out[f"ref_{k}_idx"]) - 1 for k in ["time", "tick", "volume", "dollar", "cusum"]}
+    print(f"{name}: n={len(ts)} bars={nb} events={len(out.get('in_tbm_events', []))}")
+
+
+def main():
+    # 1. plain synthetic stream (same generator the bench uses)
+    ts, px, qty, side = synth_trades(20000, seed=42)
+    case_stream("synth_20k", ts, px, qty, side)
+
+    # 2. adversarial: quantised equal-ish sizes -> exact-tie volume thresholds; hour-long gaps -> empty time bars;
+    #    first tick 100 ns before a minute boundary (H1); side == 0 ticks; duplicate timestamps
+    rng = np.random.default_rng(7)
+    n = 6000
+    gaps = rng.integers(1, 40, n).astype(np.int64) * 1_000_000
+    gaps[rng.random(n) < 0.3] = 0                      # duplicate timestamps
+    gaps[[1500, 3000]] = 3_600_000_000_000 + 17        # hour-long gaps
+    ts = 1_600_000_019_999_999_900 + np.cumsum(gaps)
+    ts[0] = 1_600_000_019_999_999_900
+    px = np.round(100.0 + np.cumsum(rng.choice([-0.5, 0.0, 0.0, 0.5], n)), 1)
+    qty = rng.choice([0.001, 0.002, 0.005, 0.01, 0.1, 0.25], n)
+    side = rng.choice(np.array([-1, 1, 1, -1, 0], dtype=np.int8), n)
+    case_stream("adversarial_6k", ts, px, qty, side, interval=60.0, tick_thr=7, vol_thr=1.0, dol_thr=250.0, tick=0.5,
+                ret_window=5.0, half_life=30.0)
+
+    # 3. giant trades: single ticks worth several dollar/volume thresholds, threshold-1 tick bars, tiny thresholds
+    rng = np.random.default_rng(11)
+    n = 4000
+    ts = 1_700_000_000_000_000_000 + np.cumsum(rng.integers(0, 3, n)).astype(np.int64) * 250_000_000
+    px = np.round(50.0 * np.exp(np.cumsum(rng.normal(0, 1e-3, n))), 2)
+    qty = np.round(rng.lognormal(0, 2.0, n), 3) + 0.001
+    side = rng.choice(np.array([-1, 1], dtype=np.int8), n)
+    case_stream("giant_4k", ts, px, qty, side, interval=1.0, tick_thr=1, vol_thr=3.0, dol_thr=150.0, tick=0.01,
+                ret_window=2.0, half_life=10.0)
+
+    # 4. sub-second clock (H12: numba arange evaluates int64(start + i*step) in float64)
+    ts, px, qty, side = synth_trades(3000, seed=5)
+    for iv in [0.001, 0.0005, 0.25]:
+        clock, idx = _time_bar_indexer(ts, iv)
+        np.savez_compressed(os.path.join(HERE, f"clock_{iv}.npz"), in_ts=ts, in_interval=np.array([iv]),
+                            ref_time_clock=clock, ref_time_idx=idx)
+
+    crosscheck()
+
+
+def crosscheck():
+    """C oracle vs reference on 1M ticks (not stored)."""
+    import oracle
+    ts, px, qty, side = synth_trades(1_000_000, seed=1)
+    ok = True
+
+    def chk(name, a, b, exact=True, atol=0):
+        nonlocal ok
+        a, b = np.asarray(a), np.asarray(b)
+        good = a.shape == b.shape and (np.array_equal(a, b, equal_nan=True) if exact else np.allclose(a, b, rtol=1e-12, atol=atol, equal_nan=True))
+        ok &= bool(good)
+        print(f"  {name:28s} {'OK' if good else 'MISMATCH'}")
+
+    c, i = _time_bar_indexer(ts, 60.0); oc, oi = oracle.time_bar_indexer(ts, 60.0)
+    chk("time clock", c, oc); chk("time idx", i, oi)
+    chk("tick", np.array(_tick_bar_indexer(ts, 1000)), oracle.tick_bar_indexer(ts, 1000))
+    chk("volume", np.array(_volume_bar_indexer(qty, 5.0)), oracle.volume_bar_indexer(qty, 5.0))
+    di = np.array(_dollar_bar_indexer(px, qty, 1e5), dtype=np.int64)
+    chk("dollar", di, oracle.dollar_bar_indexer(px, qty, 1e5))
+    r = comp_lagged_returns(ts, px, 60.0, True); chk("lagret", r, oracle.comp_lagged_returns(ts, px, 60.0, True))
+    s = ewmst(ts, r, 60.0); chk("ewmst", s, oracle.ewmst(ts, r, 60.0))
+    s1, s2 = s.copy(), s.copy()
+    chk("cusum", np.array(_cusum_bar_indexer(ts, px, s1, 5e-4, 2.0)), oracle.cusum_bar_indexer(ts, px, s2, 5e-4, 2.0))
+    for nm, idx in [("dollar", di), ("time", i)]:
+        a, b = comp_bar_ohlcv(px, qty, idx), oracle.comp_bar_ohlcv(px, qty, idx)
+        for k in range(8):
+            chk(f"ohlcv[{nm}][{k}]", a[k], b[k])
+        a, b = comp_bar_directional_features(px, qty, idx, side), oracle.comp_bar_directional_features(px, qty, idx, side)
+        for k in range(14):
+            chk(f"dir[{nm}][{k}]", a[k], b[k])
+        th = np.full(len(idx) - 1, 0.05)
+        a, b = comp_bar_trade_size_features(qty, th, idx, 5.0), oracle.comp_bar_trade_size_features(qty, th, idx, 5.0)
+        for k in range(4):
+            chk(f"tsize[{nm}][{k}]", a[k], b[k])
+        o = comp_bar_ohlcv(px, qty, idx)
+        a = comp_bar_footprints(px, qty, idx, side, 0.1, o[2], o[1], 3.0)
+        b = oracle.comp_bar_footprints_csr(px, qty, idx, side, 0.1, o[2], o[1], 3.0)
+        dts = [np.int32, np.float32, np.float32, np.int32, np.int32, np.bool_, np.bool_]
+        for k in range(7):
+            chk(f"fp[{nm}][{k}]", csr(list(a[k]), dts[k])[1], b[1 + k])
+        for k in range(7, 13):
+            chk(f"fp[{nm}][{k}]", a[k], b[1 + k], exact=(k != 11), atol=(1e-3 if k == 11 else 0))
+    ev = di[1:-50]; ev = ev[np.isfinite(s[ev])]
+    tg = s[ev] + 1e-5
+    a = triple_barrier(ts, px, ev, tg, (2.0, 2.0), 300.0, 1.0, None, 0.0)
+    b = oracle.triple_barrier(ts, px, ev, tg, (2.0, 2.0), 300.0, 1.0, None, 0.0)
+    for k in range(4):
+        chk(f"tbm[{k}]", a[k], b[k])
+    print("CROSSCHECK", "PASSED" if ok else "FAILED")
+
+
+if __name__ == "__main__":
+    main()
