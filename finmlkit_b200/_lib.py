@@ -1,0 +1,81 @@
+"""ctypes binding of libfmk.so (include/fmk.h).  There is no CPU fallback: if the library or a CUDA device is missing,
+every compute call raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libfmk.so")
+
+_lib = None
+
+P = C.c_void_p
+I64 = C.c_int64
+F64 = C.c_double
+INT = C.c_int
+
+# name -> (restype, argtypes); every symbol declared in include/fmk.h
+SIGNATURES = {
+    "fmk_version": (C.c_char_p, []),
+    "fmk_device_count": (INT, []),
+    "fmk_ctx_create": (INT, [INT, C.POINTER(P)]),
+    "fmk_ctx_destroy": (None, [P]),
+    "fmk_last_error": (C.c_char_p, [P]),
+    "fmk_ctx_sync": (INT, [P]),
+    "fmk_timer_start": (INT, [P]),
+    "fmk_timer_stop": (INT, [P, C.POINTER(C.c_float)]),
+    "fmk_launch_count": (I64, [P]),
+    "fmk_flush_l2": (INT, [P]),
+    "fmk_host_alloc": (INT, [C.POINTER(P), I64]),
+    "fmk_host_free": (None, [P]),
+    "fmk_trades_upload": (INT, [P, P, P, P, P, I64, C.POINTER(P)]),
+    "fmk_trades_synth": (INT, [P, I64, C.c_uint64, C.POINTER(P)]),
+    "fmk_trades_refill": (INT, [P, P, P, P, P, P, I64]),
+    "fmk_trades_download": (INT, [P, P, P, P, P, P]),
+    "fmk_trades_size": (I64, [P]),
+    "fmk_trades_free": (None, [P, P]),
+    "fmk_buf_upload": (INT, [P, P, I64, C.POINTER(P)]),
+    "fmk_buf_alloc": (INT, [P, I64, C.POINTER(P)]),
+    "fmk_buf_download": (INT, [P, P, P, I64]),
+    "fmk_buf_bytes": (I64, [P]),
+    "fmk_buf_devptr": (P, [P]),
+    "fmk_buf_free": (None, [P, P]),
+    "fmk_time_bar_index": (INT, [P, P, F64, C.POINTER(P)]),
+    "fmk_tick_bar_index": (INT, [P, P, I64, C.POINTER(P)]),
+    "fmk_volume_bar_index": (INT, [P, P, F64, C.POINTER(P)]),
+    "fmk_dollar_bar_index": (INT, [P, P, F64, C.POINTER(P)]),
+    "fmk_cusum_bar_index": (INT, [P, P, P, F64, F64, C.POINTER(P)]),
+    "fmk_index_from_host": (INT, [P, P, P, I64, C.POINTER(P)]),
+    "fmk_index_size": (I64, [P]),
+    "fmk_index_download": (INT, [P, P, P, P]),
+    "fmk_index_free": (None, [P, P]),
+    "fmk_index_stats": (INT, [P, P]),
+    "fmk_bar_ohlcv": (INT, [P, P, P] + [P] * 8),
+    "fmk_bar_ohlcv_device": (INT, [P, P, P, INT]),
+    "fmk_bar_directional": (INT, [P, P, P] + [P] * 14),
+    "fmk_bar_trade_size": (INT, [P, P, P, P, I64, F64, P, P, P, P]),
+    "fmk_bar_footprints": (INT, [P, P, P, F64, P, P, F64, C.POINTER(P)]),
+    "fmk_footprint_levels": (I64, [P]),
+    "fmk_footprint_download": (INT, [P, P] + [P] * 14),
+    "fmk_footprint_free": (None, [P, P]),
+    "fmk_lagged_returns": (INT, [P, P, P, I64, F64, INT, P]),
+    "fmk_ewmst": (INT, [P, P, P, I64, F64, F64, P]),
+    "fmk_lagged_returns_dev": (INT, [P, P, F64, INT, C.POINTER(P)]),
+    "fmk_ewmst_dev": (INT, [P, P, P, F64, F64, C.POINTER(P)]),
+    "fmk_triple_barrier": (INT, [P, P, P, P, I64, I64, F64, F64, F64, F64, P, I64, F64, P, P, P, P]),
+}
+
+
+def lib():
+    """Load libfmk.so (no build here: __graft_entry__.build() / finmlkit_b200.build.build() produce it)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(f"{SO_PATH} is missing: run `python -m finmlkit_b200.build` (nvcc, sm_100a). "
+                               "finmlkit_b200 has no CPU fallback.")
+        L = C.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib

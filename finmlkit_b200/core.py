@@ -1,0 +1,291 @@
+"""
+Thin object layer over the C ABI (include/fmk.h): Context, DeviceTrades, DeviceIndex and the array-level functions that
+mirror the reference's Numba "core functions" (same argument meaning, same return tuples, same ValueError messages).
+
+Everything here runs on the GPU through libfmk.so; nothing falls back to the CPU.
+"""
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from ._lib import lib
+
+_ERRORS = {-1: "CUDA", -2: "ARG", -3: "ALLOC", -4: "CAPACITY", -5: "LEVEL", -6: "INTERNAL"}
+
+
+class FmkError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+class Context:
+    """One CUDA device + stream (fmk_ctx). Single-threaded; create one per device."""
+
+    def __init__(self, device: int = 0):
+        self._L = lib()
+        if self._L.fmk_device_count() <= 0:
+            raise FmkError("no CUDA device: finmlkit_b200 has no CPU fallback")
+        h = C.c_void_p()
+        rc = self._L.fmk_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise FmkError(f"fmk_ctx_create(device={device}) failed: {_ERRORS.get(rc, rc)}")
+        self.h = h
+        self.device = device
+        self._fin = weakref.finalize(self, self._L.fmk_ctx_destroy, h)
+
+    def check(self, rc):
+        if rc == 0:
+            return
+        msg = self._L.fmk_last_error(self.h).decode()
+        if rc in (-2, -5):
+            raise ValueError(msg)          # the reference raises ValueError with the same text
+        raise FmkError(f"{_ERRORS.get(rc, rc)}: {msg}")
+
+    def sync(self):
+        self.check(self._L.fmk_ctx_sync(self.h))
+
+    def timer_start(self):
+        self.check(self._L.fmk_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self.check(self._L.fmk_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        return int(self._L.fmk_launch_count(self.h))
+
+    def flush_l2(self):
+        self.check(self._L.fmk_flush_l2(self.h))
+
+    def index_stats(self):
+        s = np.zeros(3, np.int64)
+        self._L.fmk_index_stats(self.h, _ptr(s))
+        return {"tasks": int(s[0]), "serial_repairs": int(s[1]), "chain_passes": int(s[2])}
+
+
+_default_ctx = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class DeviceBuf:
+    def __init__(self, ctx: Context, h):
+        self.ctx, self.h = ctx, h
+        self._fin = weakref.finalize(self, ctx._L.fmk_buf_free, ctx.h, h)
+
+    @classmethod
+    def upload(cls, ctx, arr):
+        arr = np.ascontiguousarray(arr)
+        h = C.c_void_p()
+        ctx.check(ctx._L.fmk_buf_upload(ctx.h, _ptr(arr), arr.nbytes, C.byref(h)))
+        ctx.sync()
+        return cls(ctx, h)
+
+    def download(self, dtype, count):
+        out = np.empty(count, dtype)
+        self.ctx.check(self.ctx._L.fmk_buf_download(self.ctx.h, self.h, _ptr(out), out.nbytes))
+        return out
+
+    @property
+    def devptr(self):
+        return self.ctx._L.fmk_buf_devptr(self.h)
+
+    @property
+    def nbytes(self):
+        return int(self.ctx._L.fmk_buf_bytes(self.h))
+
+
+class DeviceTrades:
+    """Trade columns as device SoA (fmk_trades): ts int64 ns, price f64, amount f64, side int8 (optional)."""
+
+    def __init__(self, ctx: Context, h, n):
+        self.ctx, self.h, self.n = ctx, h, n
+        self._fin = weakref.finalize(self, ctx._L.fmk_trades_free, ctx.h, h)
+
+    @classmethod
+    def upload(cls, ts, price, amount, side=None, ctx: Context = None):
+        ctx = ctx or default_context()
+        ts, price, amount = _c(ts, np.int64), _c(price, np.float64), _c(amount, np.float64)
+        if not (len(ts) == len(price) == len(amount)):
+            raise ValueError("Prices and volumes arrays must have the same length.")
+        sd = _c(side, np.int8) if side is not None else None
+        h = C.c_void_p()
+        ctx.check(ctx._L.fmk_trades_upload(ctx.h, _ptr(ts), _ptr(price), _ptr(amount), _ptr(sd), len(ts), C.byref(h)))
+        ctx.sync()
+        return cls(ctx, h, len(ts))
+
+    @classmethod
+    def synth(cls, n, seed=42, ctx: Context = None):
+        ctx = ctx or default_context()
+        h = C.c_void_p()
+        ctx.check(ctx._L.fmk_trades_synth(ctx.h, int(n), int(seed), C.byref(h)))
+        ctx.sync()
+        return cls(ctx, h, int(n))
+
+    def refill(self, ts, price, amount, side=None):
+        """Async H2D of new column contents into this handle (arrays must stay alive until the next sync)."""
+        self.ctx.check(self.ctx._L.fmk_trades_refill(self.ctx.h, self.h, _ptr(ts), _ptr(price), _ptr(amount), _ptr(side), self.n))
+
+    def download(self, out=None):
+        if out is None:
+            out = (np.empty(self.n, np.int64), np.empty(self.n, np.float64), np.empty(self.n, np.float64), np.empty(self.n, np.int8))
+        ts, px, qty, side = out
+        self.ctx.check(self.ctx._L.fmk_trades_download(self.ctx.h, self.h, _ptr(ts), _ptr(px), _ptr(qty), _ptr(side)))
+        return ts, px, qty, side
+
+
+class DeviceIndex:
+    """Bar close timestamps / indices on the device (fmk_index), m = n_bars + 1 elements."""
+
+    def __init__(self, ctx: Context, h):
+        self.ctx, self.h = ctx, h
+        self.m = int(ctx._L.fmk_index_size(h))
+        self._fin = weakref.finalize(self, ctx._L.fmk_index_free, ctx.h, h)
+
+    def download(self):
+        ts, idx = np.empty(self.m, np.int64), np.empty(self.m, np.int64)
+        self.ctx.check(self.ctx._L.fmk_index_download(self.ctx.h, self.h, _ptr(ts), _ptr(idx)))
+        return ts, idx
+
+    @classmethod
+    def from_host(cls, trades: DeviceTrades, close_idx):
+        ci = _c(close_idx, np.int64)
+        h = C.c_void_p()
+        ctx = trades.ctx
+        ctx.check(ctx._L.fmk_index_from_host(ctx.h, trades.h, _ptr(ci), len(ci), C.byref(h)))
+        ctx.sync()
+        return cls(ctx, h)
+
+
+def _mk_index(trades: DeviceTrades, fn, *args):
+    h = C.c_void_p()
+    trades.ctx.check(fn(trades.ctx.h, trades.h, *args, C.byref(h)))
+    return DeviceIndex(trades.ctx, h)
+
+
+def time_bar_index(trades: DeviceTrades, interval_seconds: float) -> DeviceIndex:
+    return _mk_index(trades, trades.ctx._L.fmk_time_bar_index, float(interval_seconds))
+
+
+def tick_bar_index(trades: DeviceTrades, threshold: int) -> DeviceIndex:
+    return _mk_index(trades, trades.ctx._L.fmk_tick_bar_index, int(threshold))
+
+
+def volume_bar_index(trades: DeviceTrades, threshold: float) -> DeviceIndex:
+    return _mk_index(trades, trades.ctx._L.fmk_volume_bar_index, float(threshold))
+
+
+def dollar_bar_index(trades: DeviceTrades, threshold: float) -> DeviceIndex:
+    return _mk_index(trades, trades.ctx._L.fmk_dollar_bar_index, float(threshold))
+
+
+def cusum_bar_index(trades: DeviceTrades, sigma: DeviceBuf, sigma_floor: float, sigma_mult: float) -> DeviceIndex:
+    return _mk_index(trades, trades.ctx._L.fmk_cusum_bar_index, sigma.h, float(sigma_floor), float(sigma_mult))
+
+
+# ---- per-bar reductions ---------------------------------------------------------------------------------------------
+def bar_ohlcv(trades: DeviceTrades, index: DeviceIndex, median=True):
+    """(open, high, low, close, volume f32, vwap, trades i64, median) -- tuple order of comp_bar_ohlcv (base.py:407)."""
+    nb = max(index.m - 1, 0)
+    o, h, l, c, vwap = (np.empty(nb) for _ in range(5))
+    vol = np.empty(nb, np.float32)
+    tr = np.empty(nb, np.int64)
+    med = np.empty(nb) if median else None
+    ctx = trades.ctx
+    ctx.check(ctx._L.fmk_bar_ohlcv(ctx.h, trades.h, index.h, _ptr(o), _ptr(h), _ptr(l), _ptr(c), _ptr(vol), _ptr(vwap), _ptr(tr), _ptr(med)))
+    return o, h, l, c, vol, vwap, tr, med
+
+
+def bar_directional(trades: DeviceTrades, index: DeviceIndex):
+    nb = max(index.m - 1, 0)
+    i64 = lambda: np.empty(nb, np.int64)   # noqa: E731
+    f32 = lambda: np.empty(nb, np.float32)  # noqa: E731
+    out = [i64(), i64(), f32(), f32(), f32(), f32(), f32(), f32(), i64(), i64(), f32(), f32(), f32(), f32()]
+    ctx = trades.ctx
+    ctx.check(ctx._L.fmk_bar_directional(ctx.h, trades.h, index.h, *[_ptr(a) for a in out]))
+    return tuple(out)
+
+
+def bar_trade_size(trades: DeviceTrades, index: DeviceIndex, theta, theta_mult):
+    nb = max(index.m - 1, 0)
+    th = _c(theta, np.float64)
+    out = [np.empty(nb, np.float32) for _ in range(4)]
+    ctx = trades.ctx
+    ctx.check(ctx._L.fmk_bar_trade_size(ctx.h, trades.h, index.h, _ptr(th), len(th), float(theta_mult), *[_ptr(a) for a in out]))
+    return tuple(out)
+
+
+def bar_footprints_csr(trades: DeviceTrades, index: DeviceIndex, price_tick_size, bar_lows, bar_highs, imbalance_factor):
+    """CSR footprint: (level_offsets, levels, buy_vol, sell_vol, buy_ticks, sell_ticks, buy_imb, sell_imb,
+    buy_imb_sum, sell_imb_sum, cot, run_signed, vp_skew, vp_gini)."""
+    nb = max(index.m - 1, 0)
+    lo, hi = _c(bar_lows, np.float64), _c(bar_highs, np.float64)
+    if len(lo) != nb or len(hi) != nb:
+        raise ValueError("bar_lows / bar_highs must have one element per bar")
+    ctx = trades.ctx
+    h = C.c_void_p()
+    ctx.check(ctx._L.fmk_bar_footprints(ctx.h, trades.h, index.h, float(price_tick_size), _ptr(lo), _ptr(hi), float(imbalance_factor), C.byref(h)))
+    try:
+        nl = int(ctx._L.fmk_footprint_levels(h))
+        off = np.empty(nb + 1, np.int64)
+        levels = np.empty(nl, np.int32)
+        bv, sv = np.empty(nl, np.float32), np.empty(nl, np.float32)
+        bt, st = np.empty(nl, np.int32), np.empty(nl, np.int32)
+        bi, si = np.empty(nl, np.bool_), np.empty(nl, np.bool_)
+        bis, sis = np.empty(nb, np.uint16), np.empty(nb, np.uint16)
+        cot = np.empty(nb, np.int32)
+        run = np.empty(nb, np.int16)
+        skew, gini = np.empty(nb), np.empty(nb)
+        ctx.check(ctx._L.fmk_footprint_download(ctx.h, h, _ptr(off), _ptr(levels), _ptr(bv), _ptr(sv), _ptr(bt), _ptr(st), _ptr(bi),
+                                                _ptr(si), _ptr(bis), _ptr(sis), _ptr(cot), _ptr(run), _ptr(skew), _ptr(gini)))
+    finally:
+        ctx._L.fmk_footprint_free(ctx.h, h)
+    return off, levels, bv, sv, bt, st, bi, si, bis, sis, cot, run, skew, gini
+
+
+# ---- tick-level series -----------------------------------------------------------------------------------------------
+def lagged_returns(timestamps, close, return_window_sec, is_log, ctx: Context = None):
+    ctx = ctx or default_context()
+    if return_window_sec <= 0:
+        raise ValueError("The return window must be greater than zero.")
+    ts, c = _c(timestamps, np.int64), _c(close, np.float64)
+    out = np.empty(len(c))
+    ctx.check(ctx._L.fmk_lagged_returns(ctx.h, _ptr(ts), _ptr(c), len(c), float(return_window_sec), int(bool(is_log)), _ptr(out)))
+    return out
+
+
+def ewmst_series(timestamps, y, half_life, sigma_floor=1e-12, ctx: Context = None):
+    ctx = ctx or default_context()
+    ts, yy = _c(timestamps, np.int64), _c(y, np.float64)
+    out = np.empty(len(yy))
+    ctx.check(ctx._L.fmk_ewmst(ctx.h, _ptr(ts), _ptr(yy), len(yy), float(half_life), float(sigma_floor), _ptr(out)))
+    return out
+
+
+def triple_barrier_dev(trades: DeviceTrades, event_idxs, targets, horizontal_barriers, vertical_barrier, min_close_time_sec, side, min_ret):
+    ev, tg = _c(event_idxs, np.int64), _c(targets, np.float64)
+    sd = _c(side, np.int8) if side is not None else None
+    ne = len(ev)
+    labels = np.zeros(ne, np.int8)
+    touch = np.zeros(ne, np.int64)
+    rets = np.full(ne, np.nan)
+    ratios = np.full(ne, np.nan)
+    bottom, top = horizontal_barriers
+    ctx = trades.ctx
+    ctx.check(ctx._L.fmk_triple_barrier(ctx.h, trades.h, _ptr(ev), _ptr(tg), ne, len(tg), float(bottom), float(top), float(vertical_barrier),
+                                        float(min_close_time_sec), _ptr(sd), len(sd) if sd is not None else 0, float(min_ret),
+                                        _ptr(labels), _ptr(touch), _ptr(rets), _ptr(ratios)))
+    return labels, touch, rets, ratios

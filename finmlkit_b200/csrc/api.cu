@@ -1,0 +1,435 @@
+// api.cu -- context / handle management, time & tick bar indexers, synthetic stream generator.
+#include <math.h>
+#include <new>
+#include "common.cuh"
+#include "scan.cuh"
+
+extern "C" {
+
+const char *fmk_version(void) { return "finmlkit_b200 0.1 (sm_100a)"; }
+
+int fmk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int fmk_ctx_create(int device, fmk_ctx **out) {
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device >= n) return FMK_ERR_CUDA;
+    fmk_ctx *ctx = new (std::nothrow) fmk_ctx();
+    if (!ctx) return FMK_ERR_ALLOC;
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return FMK_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FMK_ERR_CUDA; }
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    // keep freed blocks in the stream-ordered pool: scratch allocation inside a step must not hit the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = ctx;
+    return FMK_OK;
+}
+
+void fmk_ctx_destroy(fmk_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->res_cols) cudaFree(ctx->res_cols);
+    if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *fmk_last_error(fmk_ctx *ctx) { return ctx ? ctx->err : "no context (CUDA device missing?)"; }
+
+int fmk_ctx_sync(fmk_ctx *ctx) {
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMK_OK;
+}
+
+int fmk_timer_start(fmk_ctx *ctx) {
+    FMK_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    return FMK_OK;
+}
+
+int fmk_timer_stop(fmk_ctx *ctx, float *ms_out) {
+    FMK_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    FMK_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    FMK_CUDA(ctx, cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
+    return FMK_OK;
+}
+
+int64_t fmk_launch_count(fmk_ctx *ctx) { return ctx->launches; }
+
+int fmk_index_stats(fmk_ctx *ctx, int64_t *s) {
+    s[0] = ctx->stats[0]; s[1] = ctx->stats[1]; s[2] = ctx->stats[2];
+    return FMK_OK;
+}
+
+int fmk_host_alloc(void **out, int64_t bytes) {
+    return cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? FMK_OK : FMK_ERR_ALLOC;
+}
+void fmk_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"
+
+__global__ void k_flush(uint4 *buf, int64_t n16, unsigned v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x)
+        buf[i] = make_uint4(v, v, v, v);
+}
+
+extern "C" int fmk_flush_l2(fmk_ctx *ctx) {
+    const int64_t bytes = 512ll << 20;  // 4x the 126 MB L2
+    if (!ctx->flush_buf) {
+        FMK_CUDA(ctx, cudaMalloc(&ctx->flush_buf, (size_t)bytes));
+        ctx->flush_bytes = bytes;
+    }
+    static unsigned tick = 0;
+    FMK_LAUNCH(ctx, k_flush, ctx->sm_count * 8, 256, 0, (uint4 *)ctx->flush_buf, bytes / 16, ++tick);
+    return FMK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// buffers / trades
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int fmk_buf_alloc(fmk_ctx *ctx, int64_t bytes, fmk_buf **out) {
+    *out = nullptr;
+    fmk_buf *b = new (std::nothrow) fmk_buf();
+    if (!b) return FMK_ERR_ALLOC;
+    b->bytes = bytes;
+    char *p;
+    int rc = fmk_dalloc(ctx, &p, bytes);
+    if (rc) { delete b; return rc; }
+    b->ptr = p;
+    *out = b;
+    return FMK_OK;
+}
+
+int fmk_buf_upload(fmk_ctx *ctx, const void *host, int64_t bytes, fmk_buf **out) {
+    FMK_TRY(fmk_buf_alloc(ctx, bytes, out));
+    if (bytes > 0) FMK_CUDA(ctx, cudaMemcpyAsync((*out)->ptr, host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return FMK_OK;
+}
+
+int fmk_buf_download(fmk_ctx *ctx, const fmk_buf *b, void *host, int64_t bytes) {
+    if (bytes > b->bytes) return fmk_fail(ctx, FMK_ERR_CAPACITY, "download larger than buffer");
+    if (bytes > 0) FMK_CUDA(ctx, cudaMemcpyAsync(host, b->ptr, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMK_OK;
+}
+
+int64_t fmk_buf_bytes(const fmk_buf *b) { return b->bytes; }
+void *fmk_buf_devptr(const fmk_buf *b) { return b->ptr; }
+void fmk_buf_free(fmk_ctx *ctx, fmk_buf *b) {
+    if (!b) return;
+    fmk_dfree(ctx, b->ptr);
+    delete b;
+}
+
+static int trades_alloc(fmk_ctx *ctx, int64_t n, int with_side, fmk_trades **out) {
+    *out = nullptr;
+    fmk_trades *t = new (std::nothrow) fmk_trades();
+    if (!t) return FMK_ERR_ALLOC;
+    memset(t, 0, sizeof(*t));
+    t->n = n;
+    int rc = fmk_dalloc(ctx, &t->ts, n);
+    if (!rc) rc = fmk_dalloc(ctx, &t->price, n);
+    if (!rc) rc = fmk_dalloc(ctx, &t->amount, n);
+    if (!rc && with_side) rc = fmk_dalloc(ctx, &t->side, n);
+    if (rc) { fmk_trades_free(ctx, t); return rc; }
+    *out = t;
+    return FMK_OK;
+}
+
+int fmk_trades_refill(fmk_ctx *ctx, fmk_trades *t, const int64_t *ts, const double *price, const double *amount,
+                      const int8_t *side, int64_t n) {
+    if (n != t->n) return fmk_fail(ctx, FMK_ERR_ARG, "refill length differs from handle length");
+    if (n == 0) return FMK_OK;
+    FMK_CUDA(ctx, cudaMemcpyAsync(t->ts, ts, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FMK_CUDA(ctx, cudaMemcpyAsync(t->price, price, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FMK_CUDA(ctx, cudaMemcpyAsync(t->amount, amount, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (side && t->side) FMK_CUDA(ctx, cudaMemcpyAsync(t->side, side, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if (t->log_price) { fmk_dfree(ctx, t->log_price); t->log_price = nullptr; }
+    return FMK_OK;
+}
+
+int fmk_trades_upload(fmk_ctx *ctx, const int64_t *ts, const double *price, const double *amount, const int8_t *side,
+                      int64_t n, fmk_trades **out) {
+    if (n < 0) return fmk_fail(ctx, FMK_ERR_ARG, "negative length");
+    FMK_TRY(trades_alloc(ctx, n, side != nullptr, out));
+    int rc = fmk_trades_refill(ctx, *out, ts, price, amount, side, n);
+    if (rc) { fmk_trades_free(ctx, *out); *out = nullptr; return rc; }
+    // pageable host memory: the copies above are staged synchronously by the runtime, so the caller's arrays can be
+    // released on return; pinned memory callers must keep them alive until the next sync.
+    return FMK_OK;
+}
+
+int fmk_trades_download(fmk_ctx *ctx, const fmk_trades *t, int64_t *ts, double *price, double *amount, int8_t *side) {
+    const size_t n = (size_t)t->n;
+    if (ts) FMK_CUDA(ctx, cudaMemcpyAsync(ts, t->ts, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (price) FMK_CUDA(ctx, cudaMemcpyAsync(price, t->price, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (amount) FMK_CUDA(ctx, cudaMemcpyAsync(amount, t->amount, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (side && t->side) FMK_CUDA(ctx, cudaMemcpyAsync(side, t->side, n, cudaMemcpyDeviceToHost, ctx->stream));
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMK_OK;
+}
+
+int64_t fmk_trades_size(const fmk_trades *t) { return t->n; }
+
+void fmk_trades_free(fmk_ctx *ctx, fmk_trades *t) {
+    if (!t) return;
+    fmk_dfree(ctx, t->ts);
+    fmk_dfree(ctx, t->price);
+    fmk_dfree(ctx, t->amount);
+    fmk_dfree(ctx, t->side);
+    fmk_dfree(ctx, t->log_price);
+    delete t;
+}
+
+int64_t fmk_index_size(const fmk_index *ix) { return ix->m; }
+
+int fmk_index_download(fmk_ctx *ctx, const fmk_index *ix, int64_t *close_ts, int64_t *close_idx) {
+    if (close_ts && ix->close_ts)
+        FMK_CUDA(ctx, cudaMemcpyAsync(close_ts, ix->close_ts, (size_t)ix->m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (close_idx)
+        FMK_CUDA(ctx, cudaMemcpyAsync(close_idx, ix->close_idx, (size_t)ix->m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMK_OK;
+}
+
+void fmk_index_free(fmk_ctx *ctx, fmk_index *ix) {
+    if (!ix) return;
+    fmk_dfree(ctx, ix->close_ts);
+    fmk_dfree(ctx, ix->close_idx);
+    delete ix;
+}
+
+}  // extern "C"
+
+// close_ts[k] = ts[close_idx[k]]  (bar/kit.py:67,101,135,173: `close_ts = timestamps[close_indices]`)
+__global__ void k_gather_ts(const int64_t *ts, const int64_t *ci, int64_t m, int64_t n, int64_t *out) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < m) {
+        int64_t j = ci[k];
+        if (j < 0) j += n;
+        out[k] = (j >= 0 && j < n) ? ts[j] : 0;
+    }
+}
+
+int fmk_gather_close_ts(fmk_ctx *ctx, const fmk_trades *t, fmk_index *ix) {
+    if (!ix->close_ts) FMK_TRY(fmk_dalloc(ctx, &ix->close_ts, ix->m));
+    if (ix->m > 0)
+        FMK_LAUNCH(ctx, k_gather_ts, (unsigned)cdiv(ix->m, 256), 256, 0, t->ts, ix->close_idx, ix->m, t->n, ix->close_ts);
+    return FMK_OK;
+}
+
+extern "C" int fmk_index_from_host(fmk_ctx *ctx, const fmk_trades *t, const int64_t *close_idx, int64_t m, fmk_index **out) {
+    *out = nullptr;
+    fmk_index *ix = new (std::nothrow) fmk_index();
+    if (!ix) return FMK_ERR_ALLOC;
+    memset(ix, 0, sizeof(*ix));
+    ix->m = m;
+    ix->n_ticks = t->n;
+    int rc = fmk_dalloc(ctx, &ix->close_idx, m);
+    if (rc) { delete ix; return rc; }
+    if (m > 0) {
+        cudaError_t e = cudaMemcpyAsync(ix->close_idx, close_idx, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { fmk_index_free(ctx, ix); return fmk_fail(ctx, FMK_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+    rc = fmk_gather_close_ts(ctx, t, ix);
+    if (rc) { fmk_index_free(ctx, ix); return rc; }
+    *out = ix;
+    return FMK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a1: time bars (bar/logic.py:12-51)
+// ---------------------------------------------------------------------------------------------------------------
+// Python float floor division (numba lowers int64 // float64 to this).
+static double py_floordiv(double vx, double wx) {
+    double mod = fmod(vx, wx);
+    double div = (vx - mod) / wx;
+    if (mod != 0.0 && ((wx < 0) != (mod < 0))) div -= 1.0;
+    double fd;
+    if (div != 0.0) {
+        fd = floor(div);
+        if (div - fd > 0.5) fd += 1.0;
+    } else {
+        fd = copysign(0.0, vx / wx);
+    }
+    return fd;
+}
+
+// clock[i] = int64(start + i*step) evaluated in float64 exactly like Numba's np.arange;
+// idx[i] = searchsorted(ts, clock[i], 'right') - 1 with exact int64 compares.
+__global__ void k_time_bar(const int64_t *__restrict__ ts, int64_t n, double start, double step, int64_t m,
+                           int64_t *__restrict__ clock, int64_t *__restrict__ idx) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const double c = __dadd_rn(start, __dmul_rn((double)i, step));
+    const int64_t key = (int64_t)c;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(ts + mid) <= key) lo = mid + 1; else hi = mid;
+    }
+    clock[i] = key;
+    idx[i] = lo - 1;
+}
+
+extern "C" int fmk_time_bar_index(fmk_ctx *ctx, const fmk_trades *t, double interval_seconds, fmk_index **out) {
+    *out = nullptr;
+    if (t->n <= 0) return fmk_fail(ctx, FMK_ERR_ARG, "empty trades");
+    if (!(interval_seconds > 0)) return fmk_fail(ctx, FMK_ERR_ARG, "interval must be positive");
+    int64_t ends[2];
+    FMK_CUDA(ctx, cudaMemcpyAsync(&ends[0], t->ts, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FMK_CUDA(ctx, cudaMemcpyAsync(&ends[1], t->ts + (t->n - 1), 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // scalar clock set-up in float64, term by term as logic.py:30-39
+    const double iv = interval_seconds * 1e9;
+    const double start = py_floordiv((double)ends[0], iv) * iv;
+    const double last = ceil((double)ends[1] / iv) * iv;
+    const double stop = last + iv + 1.0;
+    int64_t m = (int64_t)ceil((stop - start) / iv);
+    if (m < 0) m = 0;
+    fmk_index *ix = new (std::nothrow) fmk_index();
+    if (!ix) return FMK_ERR_ALLOC;
+    memset(ix, 0, sizeof(*ix));
+    ix->m = m;
+    ix->n_ticks = t->n;
+    int rc = fmk_dalloc(ctx, &ix->close_ts, m);
+    if (!rc) rc = fmk_dalloc(ctx, &ix->close_idx, m);
+    if (rc) { fmk_index_free(ctx, ix); return rc; }
+    if (m > 0) {
+        k_time_bar<<<(unsigned)cdiv(m, 256), 256, 0, ctx->stream>>>(t->ts, t->n, start, iv, m, ix->close_ts, ix->close_idx);
+        ctx->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { fmk_index_free(ctx, ix); return fmk_fail(ctx, FMK_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+    *out = ix;
+    return FMK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a2: tick bars (bar/logic.py:54-84) -- closed form of the counter recurrence:
+//   threshold <= 1 : every index 0..n-1;   threshold >= 2 : {0} U {k*threshold - 1 : k >= 1}
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_tick_bar(int64_t m, int64_t thr, int64_t *idx) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    idx[k] = (thr <= 1) ? k : (k == 0 ? 0 : k * thr - 1);
+}
+
+extern "C" int fmk_tick_bar_index(fmk_ctx *ctx, const fmk_trades *t, int64_t threshold, fmk_index **out) {
+    *out = nullptr;
+    const int64_t n = t->n;
+    if (n <= 0) return fmk_fail(ctx, FMK_ERR_ARG, "empty trades");
+    const int64_t m = threshold <= 1 ? n : 1 + n / threshold;
+    fmk_index *ix = new (std::nothrow) fmk_index();
+    if (!ix) return FMK_ERR_ALLOC;
+    memset(ix, 0, sizeof(*ix));
+    ix->m = m;
+    ix->n_ticks = n;
+    int rc = fmk_dalloc(ctx, &ix->close_idx, m);
+    if (rc) { fmk_index_free(ctx, ix); return rc; }
+    k_tick_bar<<<(unsigned)cdiv(m, 256), 256, 0, ctx->stream>>>(m, threshold, ix->close_idx);
+    ctx->launches++;
+    rc = fmk_gather_close_ts(ctx, t, ix);
+    if (rc) { fmk_index_free(ctx, ix); return rc; }
+    *out = ix;
+    return FMK_OK;
+}
+
+extern "C" int fmk_volume_bar_index(fmk_ctx *ctx, const fmk_trades *t, double threshold, fmk_index **out) {
+    return fmk_volume_index_impl(ctx, t, threshold, out);
+}
+extern "C" int fmk_dollar_bar_index(fmk_ctx *ctx, const fmk_trades *t, double threshold, fmk_index **out) {
+    return fmk_dollar_index_impl(ctx, t, threshold, out);
+}
+extern "C" int fmk_cusum_bar_index(fmk_ctx *ctx, const fmk_trades *t, fmk_buf *sigma, double sigma_floor,
+                                   double sigma_mult, fmk_index **out) {
+    return fmk_cusum_index_impl(ctx, t, sigma, sigma_floor, sigma_mult, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// synthetic stream on the device (counter-based RNG; SURVEY 8d shape)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double u01(uint64_t seed, uint64_t i, uint64_t stream) {
+    uint64_t r = mix64(seed * 0x9e3779b97f4a7c15ull + mix64(i * 4 + stream + 0x632be59bd9b4e019ull));
+    return ((double)(r >> 11) + 0.5) * (1.0 / 9007199254740992.0);  // (0,1)
+}
+__device__ __forceinline__ double normal01(uint64_t seed, uint64_t i, uint64_t s0) {
+    double u1 = u01(seed, i, s0), u2 = u01(seed, i, s0 + 1);
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+struct GapIn {
+    uint64_t seed;
+    __device__ int64_t operator()(int64_t i) const {
+        return 1 + (int64_t)floor(-50e6 * log(u01(seed, (uint64_t)i, 0)));
+    }
+};
+struct TsOut {
+    int64_t *ts;
+    __device__ void operator()(int64_t i, int64_t cs) const {
+        int64_t t = 1700000000000000000ll + cs;
+        ts[i] = t / 1000000 * 1000000;  // floor to ms -> duplicate timestamps
+    }
+};
+struct RetIn {
+    uint64_t seed;
+    __device__ double operator()(int64_t i) const { return 2e-5 * normal01(seed, (uint64_t)i, 1); }
+};
+struct PxOut {
+    double *px;
+    __device__ void operator()(int64_t i, double cs) const { px[i] = rint(30000.0 * exp(cs) * 10.0) / 10.0; }
+};
+struct FlipIn {
+    uint64_t seed;
+    __device__ int64_t operator()(int64_t i) const { return u01(seed, (uint64_t)i, 3) < 0.3 ? 1 : 0; }
+};
+struct SideOut {
+    int8_t *side;
+    __device__ void operator()(int64_t i, int64_t cs) const { side[i] = (cs & 1) ? -1 : 1; }
+};
+
+__global__ void k_synth_amount(uint64_t seed, int64_t n, double *amt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // lognormal(-4, 1.2) + 0.001 rounded to 3 decimals; normal from an independent stream pair (4,5 -> use stream 2 base)
+    double u1 = u01(seed, (uint64_t)i, 2), u2 = u01(seed ^ 0xabcdef1234567ull, (uint64_t)i, 2);
+    double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    amt[i] = rint((exp(-4.0 + 1.2 * z) + 0.001) * 1000.0) / 1000.0;
+}
+
+extern "C" int fmk_trades_synth(fmk_ctx *ctx, int64_t n, uint64_t seed, fmk_trades **out) {
+    if (n <= 0) return fmk_fail(ctx, FMK_ERR_ARG, "n must be positive");
+    FMK_TRY(trades_alloc(ctx, n, 1, out));
+    fmk_trades *t = *out;
+    int rc = device_inclusive_scan<int64_t>(ctx, GapIn{seed}, TsOut{t->ts}, n, (int64_t *)nullptr);
+    if (!rc) rc = device_inclusive_scan<double>(ctx, RetIn{seed}, PxOut{t->price}, n, (double *)nullptr);
+    if (!rc) rc = device_inclusive_scan<int64_t>(ctx, FlipIn{seed}, SideOut{t->side}, n, (int64_t *)nullptr);
+    if (!rc) {
+        k_synth_amount<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(seed, n, t->amount);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = fmk_fail(ctx, FMK_ERR_CUDA, "synth launch failed");
+    }
+    if (rc) { fmk_trades_free(ctx, t); *out = nullptr; }
+    return rc;
+}

@@ -1,0 +1,340 @@
+// dollar_core.h -- bit-exact parallel dollar-bar indexer: host/device shared core (logic.py:118-149).
+//
+// Reference recurrence (strictly sequential, float64, no FMA):
+//     c = p0*v0 ; for i>=1: c = fl(c + fl(p_i*v_i)); if c >= T: emit i; c = fl(c - T)
+// The carried remainder makes every boundary depend on the rounding history of all earlier ticks, so a reassociated
+// (scan) sum cannot reproduce the reference's decisions at near-ties.  This file restates the recurrence as
+// independent TASKS whose results are provably identical to the sequential run, plus an exact integer carry chain:
+//
+//  * The stream is cut into chunks of CH ticks.  Task k starts right after the first (approximately located) bar
+//    boundary B_k inside chunk k and replays the *exact* recurrence until it emits a boundary at an index
+//    >= (k+1)*CH -- which is B_{k+1} if the guesses are consistent.
+//  * Right after a boundary the true carry r is a multiple of u = ulp(T).  The task does not know r, only an
+//    approximation g (from a double-double prefix sum).  Translation property: for states below 4*2^e(T), if the
+//    start state is shifted by D = 4*u*z, every float add rounds identically and the whole trajectory is shifted by
+//    exactly D, provided no value comes within |D| of a decision threshold (T) or a binade boundary (a power of two).
+//    Ties-to-even and the coarser ulp one binade above T depend on r mod 4u only, so the task replays FOUR chains
+//    (start = g0 + rho*u, rho = 0..3) and records for each: end state, and the smallest margin seen.
+//  * A sequential-in-bars but trivially cheap chain (dollar_chain_step, run as a parallel scan on the device) then
+//    propagates the TRUE start state: Delta = s_k - g0_k, rho = Delta mod 4, D = Delta - rho; the task is certified
+//    iff D == 0 or |D|*u < margin[rho] and chain rho emitted exactly where chain 0 did; s_{k+1} = end[rho] + D.
+//  * Certification failures (near-ties, giant trades, inconsistent guesses) are repaired by an exact serial replay
+//    from the last certified state (dollar_serial), after which the chain resumes.  Every emitted index is therefore
+//    either certified identical to the sequential run or produced by the sequential run itself.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#define DC_HD __host__ __device__ __forceinline__
+#else
+#define DC_HD static inline
+#endif
+
+DC_HD double dc_mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;  // host build uses -ffp-contract=off
+#endif
+}
+DC_HD double dc_add(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+DC_HD double dc_sub(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, -b);
+#else
+    return a - b;
+#endif
+}
+DC_HD uint64_t dc_bits(double x) {
+#ifdef __CUDA_ARCH__
+    return (uint64_t)__double_as_longlong(x);
+#else
+    uint64_t b; memcpy(&b, &x, 8); return b;
+#endif
+}
+DC_HD double dc_from_bits(uint64_t b) {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)b);
+#else
+    double x; memcpy(&x, &b, 8); return x;
+#endif
+}
+
+// ---- double-double helpers (approximate prefix sums for the guesses only) -------------------------------------
+struct dd_t { double hi, lo; };
+DC_HD dd_t dd_add_d(dd_t a, double b) {   // a + b (TwoSum)
+    double s = dc_add(a.hi, b);
+    double bb = dc_sub(s, a.hi);
+    double e = dc_add(dc_sub(a.hi, dc_sub(s, bb)), dc_sub(b, bb));
+    e = dc_add(e, a.lo);
+    double hi = dc_add(s, e);
+    double lo = dc_sub(e, dc_sub(hi, s));
+    dd_t r = {hi, lo};
+    return r;
+}
+DC_HD dd_t dd_add(dd_t a, dd_t b) {
+    dd_t r = dd_add_d(a, b.hi);
+    double e = dc_add(r.lo, b.lo);
+    double hi = dc_add(r.hi, e);
+    double lo = dc_sub(e, dc_sub(hi, r.hi));
+    dd_t q = {hi, lo};
+    return q;
+}
+
+// Guess of (number of emitted boundaries, carry) before a chunk whose exclusive prefix of dollars is P, in exact
+// arithmetic ignoring the one-emit-per-tick rule: K = floor(P/T), carry = P - K*T.  Only a guess.
+DC_HD void dollar_guess(dd_t P, double T, int64_t *K, double *carry) {
+    double q = floor(P.hi / T);
+    double ph = dc_mul(q, T);
+    double pl = fma(q, T, -ph);
+    double rem = dc_add(dc_sub(dc_sub(P.hi, ph), pl), P.lo);
+    int guard = 0;
+    while (rem < 0 && guard++ < 8) { rem = dc_add(rem, T); q -= 1.0; }
+    while (rem >= T && guard++ < 16) { rem = dc_sub(rem, T); q += 1.0; }
+    if (!(rem >= 0)) rem = 0;
+    *K = (int64_t)q;
+    *carry = rem;
+}
+
+constexpr int DC_NCH = 4;
+
+struct DollarTaskRec {
+    int64_t start_idx;        // B_k (boundary the task starts after); -1 = empty task (no boundary located in chunk)
+    int64_t k_start;          // ordinal of B_k in the output index array (out[k_start] == B_k)
+    int64_t end_idx;          // last boundary emitted by chain 0 (>= next chunk start); -2 = ran to the end of data
+    int64_t count;            // boundaries emitted by chain 0
+    int64_t start_units;      // chain-0 start state / u ; task 0: unused (exact start)
+    int64_t end_units[DC_NCH];
+    double margin[DC_NCH];    // smallest distance of any value to a decision/binade boundary
+    int32_t bad;              // bit r set: chain r left the regime where the translation property holds
+    int32_t nch;              // 1 for task 0 (exact start), DC_NCH otherwise
+};
+
+struct DollarParams {
+    double T, u, top_lim, sub_lim;  // u = ulp(T); top_lim = 4*2^e; sub_lim = 2*2^e
+    int64_t n, CH, cap;
+};
+
+DC_HD bool dollar_params_init(DollarParams *P, double T, int64_t n, int64_t CH, int64_t cap) {
+    P->T = T; P->n = n; P->CH = CH; P->cap = cap;
+    if (!(T > 0) || !(T < 1e300) || T < 1e-290) return false;
+    uint64_t b = dc_bits(T);
+    double pow2 = dc_from_bits(b & 0xFFF0000000000000ull);  // 2^e
+    P->u = pow2 * 2.220446049250313e-16;                    // 2^(e-52)
+    P->top_lim = pow2 * 4.0;
+    P->sub_lim = pow2 * 2.0;
+    return true;
+}
+
+// One exact step of the reference recurrence for one chain, with margin tracking.
+// Returns true when the chain emits at this tick.
+DC_HD bool dollar_chain_tick(double &c, double d, const DollarParams &P, uint64_t &mbits, bool &bad) {
+    const double r = dc_add(c, d);
+    const uint64_t rb = dc_bits(r);
+    const double lowb = dc_from_bits(rb & 0xFFF0000000000000ull);
+    const double dlo = dc_sub(r, lowb);
+    const double dhi = dc_sub(lowb, dlo);
+    const double am = fabs(dc_sub(r, P.T));
+    // positive doubles order like their bit patterns; negative/NaN values have the sign bit set -> never the minimum,
+    // they are caught by the explicit range test below
+    uint64_t m = mbits;
+    uint64_t x;
+    x = dc_bits(dlo); m = x < m ? x : m;
+    x = dc_bits(dhi); m = x < m ? x : m;
+    x = dc_bits(am);  m = x < m ? x : m;
+    mbits = m;
+    if (!(r >= 0.0) || !(r < P.top_lim)) bad = true;
+    if (r >= P.T) {
+        const double c2 = dc_sub(r, P.T);
+        if (!(c2 < P.sub_lim)) bad = true;
+        c = c2;
+        return true;
+    }
+    c = r;
+    return false;
+}
+
+// Task k.  carry_in / K_in: guess for the state before tick k*CH (ignored for k == 0).
+// out: global index array (out[0] = 0 is written by the caller), cap = its capacity.
+template <typename LoadP, typename LoadV>
+DC_HD void dollar_task(LoadP p, LoadV v, const DollarParams &P, int64_t k, double carry_in, int64_t K_in,
+                       int64_t *out, DollarTaskRec *rec) {
+    const int64_t n = P.n;
+    const int64_t lo = k * P.CH;
+    int64_t hi = lo + P.CH;
+    if (hi > n) hi = n;
+    const bool last_chunk = (hi >= n);
+    rec->start_idx = -1; rec->k_start = 0; rec->end_idx = -2; rec->count = 0; rec->start_units = 0;
+    rec->bad = 0; rec->nch = DC_NCH;
+    for (int r = 0; r < DC_NCH; r++) { rec->end_units[r] = 0; rec->margin[r] = 0.0; }
+
+    double c[DC_NCH];
+    uint64_t mb[DC_NCH];
+    bool bad[DC_NCH];
+    int64_t B, K;
+    int nch;
+    if (k == 0) {
+        B = 0; K = 0;
+        c[0] = dc_mul(p(0), v(0));      // exact start: cum = prices[0] * volumes[0]
+        nch = 1;
+    } else {
+        // phase 1: locate the first boundary inside this chunk with the approximate carry
+        double x = carry_in;
+        B = -1;
+        for (int64_t i = lo; i < hi; i++) {
+            x = dc_add(x, dc_mul(p(i), v(i)));
+            if (x >= P.T) { x = dc_sub(x, P.T); B = i; break; }
+        }
+        if (B < 0) return;              // empty task
+        K = K_in + 1;
+        double units = rint(x / P.u);
+        if (!(units >= 0)) units = 0;
+        rec->start_units = (int64_t)units;
+        nch = DC_NCH;
+        for (int r = 0; r < DC_NCH; r++) c[r] = dc_mul((double)(rec->start_units + r), P.u);
+    }
+    for (int r = 0; r < DC_NCH; r++) { mb[r] = 0x7FF0000000000000ull; bad[r] = false; }
+    rec->start_idx = B;
+    rec->k_start = K;
+    if (nch == DC_NCH) {
+        for (int r = 0; r < DC_NCH; r++) {
+            // the start must be exactly representable (it is unless units ~ 2^53)
+            double chk = c[r] / P.u;
+            if (chk != (double)(rec->start_units + r)) bad[r] = true;
+        }
+    }
+    // phase 2: exact replay
+    int64_t cnt = 0;
+    int64_t end_idx = -2;
+    for (int64_t i = B + 1; i < n; i++) {
+        const double d = dc_mul(p(i), v(i));
+        const bool e0 = dollar_chain_tick(c[0], d, P, mb[0], bad[0]);
+        for (int r = 1; r < nch; r++) {
+            const bool er = dollar_chain_tick(c[r], d, P, mb[r], bad[r]);
+            if (er != e0) bad[r] = true;
+        }
+        if (e0) {
+            cnt++;
+            if (K + cnt < P.cap) out[K + cnt] = i;   // speculative writes stay in bounds; cap bounds the true count
+            if (!last_chunk && i >= hi) { end_idx = i; break; }
+        }
+    }
+    rec->count = cnt;
+    rec->end_idx = end_idx;
+    rec->nch = nch;
+    if (end_idx >= 0) {
+        for (int r = 0; r < nch; r++) {
+            double eu = c[r] / P.u;          // exact when c is a multiple of u below 2^(e+1)
+            rec->end_units[r] = (int64_t)eu;
+            if ((double)rec->end_units[r] != eu || dc_mul(eu, P.u) != c[r]) bad[r] = true;
+        }
+    }
+    for (int r = 0; r < nch; r++) rec->margin[r] = dc_from_bits(mb[r]);
+    int32_t bm = 0;
+    for (int r = 0; r < nch; r++) if (bad[r]) bm |= (1 << r);
+    rec->bad = bm;
+}
+
+// ---- carry chain ---------------------------------------------------------------------------------------------
+// Transfer function of a task on Delta = s - start_units: f(Delta) = Delta + off[Delta & 3].
+struct DollarXfer { int64_t off[4]; };
+
+DC_HD DollarXfer dollar_xfer_identity() { DollarXfer f; for (int r = 0; r < 4; r++) f.off[r] = 0; return f; }
+// h = g after f
+DC_HD DollarXfer dollar_xfer_compose(const DollarXfer &f, const DollarXfer &g) {
+    DollarXfer h;
+    for (int r = 0; r < 4; r++) {
+        int64_t mid = r + f.off[r];
+        h.off[r] = f.off[r] + g.off[mid & 3];
+    }
+    return h;
+}
+
+// Exact serial replay from a known state (repair path / degenerate thresholds).  Starts after boundary `pos` with
+// carry c and `K` boundaries emitted so far; stops at the first emitted boundary i for which stop(i, K_after) is
+// true, or at the end of the data.  Returns the number emitted; *c_out / *pos_out describe the stop.
+template <typename LoadP, typename LoadV, typename Stop>
+DC_HD int64_t dollar_serial(LoadP p, LoadV v, int64_t n, double T, int64_t pos, double c, int64_t K, int64_t *out,
+                            int64_t cap, int *overflow, Stop stop, double *c_out, int64_t *pos_out) {
+    int64_t cnt = 0;
+    *pos_out = -2;
+    for (int64_t i = pos + 1; i < n; i++) {
+        c = dc_add(c, dc_mul(p(i), v(i)));
+        if (c >= T) {
+            c = dc_sub(c, T);
+            cnt++;
+            if (K + cnt < cap) out[K + cnt] = i; else *overflow = 1;
+            if (stop(i, K + cnt, c)) { *pos_out = i; break; }
+        }
+    }
+    *c_out = c;
+    return cnt;
+}
+
+// ---- chain walk over task records -----------------------------------------------------------------------------
+// Absolute-state transfer function of task k: F(s) = s + off[s & 3] (s = true start state in units of u).
+DC_HD DollarXfer dollar_task_xfer(const DollarTaskRec &t) {
+    DollarXfer f;
+    for (int a = 0; a < 4; a++) {
+        int rho = (int)((a - t.start_units) & 3);
+        f.off[a] = t.end_units[rho] - t.start_units - rho;
+    }
+    return f;
+}
+
+struct DollarWalk {
+    int64_t s;           // true state (units of u) right after boundary `pos`
+    int64_t pos;         // last certified boundary index
+    int64_t K;           // its ordinal in out[]
+    int64_t fail_task;   // first task that could not be certified (-1: none)
+    int64_t done;        // 1: a certified task ran to the end of the data; K_total valid
+    int64_t K_total;
+};
+
+// Certify task t given the walk state w (which describes the boundary the task must start from).
+// Returns 0 = certified & advanced, 1 = certified tail (done), 2 = failure (repair serially, resync after this task),
+// 3 = task is stale or empty (skip), 4 = failure before the task (repair serially, resync may happen at this task).
+// strict: a stale task (start behind the certified frontier) is reported as a failure instead of skipped -- the
+// parallel chain composes transfer functions assuming perfect linkage, so any deviation must go to the repair path.
+DC_HD int dollar_walk_step(const DollarTaskRec &t, double u, DollarWalk &w, bool strict) {
+    if (t.start_idx < 0) return 3;
+    if (t.start_idx < w.pos) return strict ? 4 : 3;
+    if (t.start_idx > w.pos) return 4;
+    if (t.k_start != w.K) return 2;
+    if (t.nch != DC_NCH) return 2;            // task 0 is consumed by the caller
+    const int64_t delta = w.s - t.start_units;
+    const int rho = (int)(delta & 3);
+    const int64_t D = delta - rho;
+    if ((t.bad >> rho) & 1) return 2;
+    if (D != 0) {
+        double ad = fabs((double)D) * u;
+        if (!(ad < t.margin[rho])) return 2;
+    }
+    if (t.end_idx == -2) { w.done = 1; w.K_total = t.k_start + t.count; return 1; }
+    w.s = t.end_units[rho] + D;
+    w.pos = t.end_idx;
+    w.K = t.k_start + t.count;
+    return 0;
+}
+
+// Sequential walk over tasks [k, k_end).  Returns 0 when the range is exhausted, 1 when done (tail certified),
+// 2/4 on failure with *k_fail = failing task.
+DC_HD int dollar_walk_range(const DollarTaskRec *recs, int64_t k, int64_t k_end, double u, DollarWalk &w,
+                            int64_t *k_fail, int64_t *n_certified, bool strict) {
+    for (; k < k_end; k++) {
+        int rc = dollar_walk_step(recs[k], u, w, strict);
+        if (rc == 3) continue;
+        if (rc == 0) { (*n_certified)++; continue; }
+        *k_fail = k;
+        return rc;
+    }
+    return 0;
+}

@@ -1,0 +1,317 @@
+// index_volume.cu -- bit-exact parallel volume-bar indexer (reference: finmlkit/bar/logic.py:87-115).
+//
+// Reference recurrence: cum = v0; for i>=1: cum = fl(cum + v_i); if cum >= T: emit i; cum = 0.0   (no carry-over).
+// The reset to exactly 0.0 means the state after a boundary b is known exactly, so the boundary that follows b is a
+// pure function next(b) = min{ j > b : seqsum(v[b+1..j]) >= T } of the data.  The boundaries are the orbit of the
+// first boundary under `next`, which is a pointer chase.  It is resolved in parallel with two levels of exit tables:
+//
+//   V1  prefix        P = inclusive scan of v                                     (scan.cuh; 8 B/tick in, 8 B/tick out)
+//   V2  k_volume_next next[i] for EVERY tick i: binary search of P for P[i]+T-guard, certain when the candidate
+//                     clears T+guard as well; otherwise (exact ties, 2.5 % of bars on quantised sizes -- SURVEY H5)
+//                     the reference's sequential float64 sum is replayed from i+1.  guard bounds |seqsum - (P[j]-P[i])|.
+//   V3  k_volume_exit0 per 2048-tick chunk, pointer jumping in shared memory: exit0[i] = first orbit element of i
+//                     beyond the chunk
+//       k_volume_exit1 per 1024-chunk superchunk, backward over chunks: exit1[i] = first orbit element beyond the
+//                     superchunk
+//       k_volume_chase2 / chase1: serial hops over superchunks, then (parallel over superchunks) over chunks
+//       k_volume_count / emit: per chunk, walk next[] from the chunk's entry and write the indices in order
+//
+// Requires v >= 0 and finite (P monotone); anything else falls back to the exact serial device kernel.
+#include <new>
+#include "common.cuh"
+#include "scan.cuh"
+
+constexpr int VC0 = 2048;            // ticks per chunk
+constexpr int VC1 = 1024;            // chunks per superchunk
+constexpr int64_t VSC = (int64_t)VC0 * VC1;
+constexpr int VN_THREADS = 256;
+
+struct VolIn {
+    const double *v;
+    __device__ double operator()(int64_t i) const { return v[i]; }
+};
+struct VolOut {
+    double *P;
+    int *bad;
+    const double *v;
+    __device__ void operator()(int64_t i, double cs) const {
+        P[i] = cs;
+        const double x = v[i];
+        if (!(x >= 0.0) || !(x < 1e300)) *bad = 1;
+    }
+};
+
+// first index in [lo, hi) with P[idx] >= key (hi if none)
+__device__ __forceinline__ int64_t lower_bound_f64(const double *__restrict__ P, int64_t lo, int64_t hi, double key) {
+    while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(P + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ int64_t volume_replay(const double *__restrict__ v, int64_t n, int64_t i, double T) {
+    double cum = 0.0;
+    for (int64_t t = i + 1; t < n; t++) {
+        cum = __dadd_rn(cum, v[t]);
+        if (cum >= T) return t;
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(VN_THREADS) k_volume_next(const double *__restrict__ P, const double *__restrict__ v,
+                                                            int64_t n, double T, double guard,
+                                                            int32_t *__restrict__ next, int64_t *replays) {
+    __shared__ int64_t bracket[2];
+    const int64_t i0 = (int64_t)blockIdx.x * VN_THREADS;
+    const int64_t i = i0 + threadIdx.x;
+    int64_t ilast = i0 + VN_THREADS - 1;
+    if (ilast > n - 1) ilast = n - 1;
+    const double tlo = __dadd_rn(T, -guard), thi = __dadd_rn(T, guard);
+    if (threadIdx.x == 0) bracket[0] = lower_bound_f64(P, i0 + 1, n, __dadd_rn(P[i0], tlo));
+    if (threadIdx.x == 32) bracket[1] = lower_bound_f64(P, ilast + 1, n, __dadd_rn(P[ilast], tlo));
+    __syncthreads();
+    if (i >= n) return;
+    const double base = P[i];
+    int64_t lo = bracket[0], hi = bracket[1];
+    if (lo < i + 1) lo = i + 1;
+    if (hi < lo) hi = lo;
+    // candidate: first j > i whose approximate bar volume reaches T - guard (monotone in i, bracketed by the block)
+    int64_t j = lower_bound_f64(P, lo, hi, __dadd_rn(base, tlo));
+    int64_t r;
+    if (j >= n) r = n;                                            // even T - guard is never reached: no boundary
+    else if (__ldg(P + j) >= __dadd_rn(base, thi)) r = j;        // clears T + guard: certain
+    else {                                                       // within the guard band: the reference's own sum decides
+        r = volume_replay(v, n, i, T);
+        atomicAdd((unsigned long long *)replays, 1ull);
+    }
+    next[i] = (int32_t)r;
+}
+
+// first boundary: cum = v[0]; for i >= 1: cum += v[i]; cum >= T -> i   (logic.py:106-111; tick 0 is never tested)
+__global__ void k_volume_first(const double *__restrict__ v, int64_t n, double T, int64_t *first) {
+    double cum = v[0];
+    int64_t r = n;
+    for (int64_t t = 1; t < n; t++) {
+        cum = __dadd_rn(cum, v[t]);
+        if (cum >= T) { r = t; break; }
+    }
+    *first = r;
+}
+
+// exit0[i] = first element of the orbit of i that lies beyond i's chunk (n if the orbit ends)
+__global__ void __launch_bounds__(256) k_volume_exit0(const int32_t *__restrict__ next, int64_t n,
+                                                      int32_t *__restrict__ exit0) {
+    __shared__ int32_t tgt[VC0];
+    __shared__ int changed;
+    const int64_t base = (int64_t)blockIdx.x * VC0;
+    const int64_t end = base + VC0 < n ? base + VC0 : n;
+    for (int k = threadIdx.x; k < VC0; k += 256) tgt[k] = base + k < n ? next[base + k] : (int32_t)n;
+    __syncthreads();
+    for (int round = 0; round < 12; round++) {
+        if (threadIdx.x == 0) changed = 0;
+        __syncthreads();
+        int32_t nv[VC0 / 256];
+        bool ch = false;
+#pragma unroll
+        for (int q = 0; q < VC0 / 256; q++) {
+            const int k = threadIdx.x + q * 256;
+            int32_t t = tgt[k];
+            if ((int64_t)t < end) { t = tgt[t - base]; ch = true; }
+            nv[q] = t;
+        }
+        if (ch) changed = 1;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < VC0 / 256; q++) tgt[threadIdx.x + q * 256] = nv[q];
+        __syncthreads();
+        if (!changed) break;
+    }
+    for (int k = threadIdx.x; k < VC0; k += 256)
+        if (base + k < n) exit0[base + k] = tgt[k];
+}
+
+// exit1[i] = first orbit element beyond i's superchunk; chunks are processed back to front so that the exit1 of
+// every later chunk in the superchunk is final when it is gathered.
+__global__ void __launch_bounds__(256) k_volume_exit1(const int32_t *__restrict__ exit0, int64_t n,
+                                                      int32_t *exit1) {
+    const int64_t sbase = (int64_t)blockIdx.x * VSC;
+    const int64_t send = sbase + VSC < n ? sbase + VSC : n;
+    const int64_t nchunks = (send - sbase + VC0 - 1) / VC0;
+    for (int64_t c = nchunks - 1; c >= 0; c--) {
+        const int64_t base = sbase + c * VC0;
+        for (int k = threadIdx.x; k < VC0; k += 256) {
+            const int64_t i = base + k;
+            if (i < send) {
+                int32_t e = exit0[i];
+                if ((int64_t)e < send) e = exit1[e];   // written in an earlier iteration (later chunk)
+                exit1[i] = e;
+            }
+        }
+        __threadfence_block();
+        __syncthreads();
+    }
+}
+
+// serial hops over superchunks: entryS[S] = first boundary inside superchunk S (-1 if none)
+__global__ void k_volume_chase2(const int32_t *__restrict__ exit1, const int64_t *first, int64_t n,
+                                int64_t *entryS) {
+    int64_t e = *first;
+    while (e < n) {
+        entryS[e / VSC] = e;
+        e = exit1[e];
+    }
+}
+
+// per superchunk: entryC[c] = first boundary inside chunk c (-1 if none)
+__global__ void k_volume_chase1(const int32_t *__restrict__ exit0, const int64_t *__restrict__ entryS, int64_t nS,
+                                int64_t n, int64_t *entryC) {
+    const int64_t S = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (S >= nS) return;
+    int64_t e = entryS[S];
+    if (e < 0) return;
+    const int64_t send = (S + 1) * VSC < n ? (S + 1) * VSC : n;
+    while (e < send) {
+        entryC[e / VC0] = e;
+        e = exit0[e];
+    }
+}
+
+__global__ void k_volume_count(const int32_t *__restrict__ next, const int64_t *__restrict__ entryC, int64_t nC,
+                               int64_t n, int64_t *counts) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    int64_t e = entryC[c], cnt = 0;
+    const int64_t cend = (c + 1) * VC0 < n ? (c + 1) * VC0 : n;
+    while (e >= 0 && e < cend) { cnt++; e = next[e]; }
+    counts[c] = cnt;
+}
+
+struct CntIn {
+    const int64_t *c;
+    __device__ int64_t operator()(int64_t i) const { return c[i]; }
+};
+struct CntOut {
+    int64_t *off;
+    __device__ void operator()(int64_t i, int64_t cs) const { off[i + 1] = cs; }
+};
+
+__global__ void k_volume_emit(const int32_t *__restrict__ next, const int64_t *__restrict__ entryC,
+                              const int64_t *__restrict__ off, int64_t nC, int64_t n, int64_t *out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    int64_t e = entryC[c];
+    int64_t w = 1 + off[c];            // out[0] = 0 is the open marker
+    const int64_t cend = (c + 1) * VC0 < n ? (c + 1) * VC0 : n;
+    while (e >= 0 && e < cend) { out[w++] = e; e = next[e]; }
+    if (c == 0) out[0] = 0;
+}
+
+// exact serial fallback (negative / non-finite volumes, NaN threshold ...): two passes, count then write
+__global__ void k_volume_serial(const double *__restrict__ v, int64_t n, double T, int64_t *out, int64_t cap,
+                                int64_t *count) {
+    int64_t m = 0;
+    if (out && m < cap) out[m] = 0;
+    m++;
+    double cum = v[0];
+    for (int64_t i = 1; i < n; i++) {
+        cum = __dadd_rn(cum, v[i]);
+        if (cum >= T) {
+            if (out && m < cap) out[m] = i;
+            m++;
+            cum = 0.0;
+        }
+    }
+    *count = m;
+}
+
+template <typename T>
+static int fetch(fmk_ctx *ctx, T *host, const T *dev) {
+    FMK_CUDA(ctx, cudaMemcpyAsync(host, dev, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMK_OK;
+}
+
+static int finish_index(fmk_ctx *ctx, const fmk_trades *t, int64_t *idx, int64_t m, fmk_index **out_ix) {
+    fmk_index *ix = new (std::nothrow) fmk_index();
+    if (!ix) { fmk_dfree(ctx, idx); return FMK_ERR_ALLOC; }
+    memset(ix, 0, sizeof(*ix));
+    ix->m = m;
+    ix->n_ticks = t->n;
+    ix->close_idx = idx;
+    int rc = fmk_gather_close_ts(ctx, t, ix);
+    if (rc) { fmk_index_free(ctx, ix); return rc; }
+    *out_ix = ix;
+    return FMK_OK;
+}
+
+static int volume_serial(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index **out_ix) {
+    Scratch<int64_t> cnt(ctx);
+    FMK_TRY(cnt.alloc(1));
+    FMK_LAUNCH(ctx, k_volume_serial, 1, 1, 0, t->amount, t->n, T, (int64_t *)nullptr, (int64_t)0, cnt.p);
+    int64_t m = 0;
+    FMK_TRY(fetch(ctx, &m, cnt.p));
+    int64_t *idx = nullptr;
+    FMK_TRY(fmk_dalloc(ctx, &idx, m));
+    FMK_LAUNCH(ctx, k_volume_serial, 1, 1, 0, t->amount, t->n, T, idx, m, cnt.p);
+    ctx->stats[1]++;
+    return finish_index(ctx, t, idx, m, out_ix);
+}
+
+int fmk_volume_index_impl(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index **out_ix) {
+    *out_ix = nullptr;
+    const int64_t n = t->n;
+    if (n <= 0) return fmk_fail(ctx, FMK_ERR_ARG, "empty trades");
+    ctx->stats[0] = ctx->stats[1] = ctx->stats[2] = 0;
+    if (!(T > 0) || !(T < 1e300) || n >= 2147483000ll) return volume_serial(ctx, t, T, out_ix);
+
+    Scratch<double> P(ctx), tot(ctx);
+    Scratch<int> bad(ctx);
+    FMK_TRY(P.alloc(n)); FMK_TRY(tot.alloc(1)); FMK_TRY(bad.alloc(1));
+    FMK_CUDA(ctx, cudaMemsetAsync(bad.p, 0, sizeof(int), ctx->stream));
+    FMK_TRY(device_inclusive_scan<double>(ctx, VolIn{t->amount}, VolOut{P.p, bad.p, t->amount}, n, tot.p));
+    double total = 0;
+    int hbad = 0;
+    FMK_CUDA(ctx, cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FMK_TRY(fetch(ctx, &total, tot.p));
+    if (hbad || !(total >= 0) || !(total < 1e300)) return volume_serial(ctx, t, T, out_ix);
+    // guard >= |seqsum(v[i+1..j]) - (P[j]-P[i])|: scan rounding (<= ~50 eps P_total, taken 4096x) + the sequential
+    // sum's own rounding (<= (j-i) eps T, taken with j-i = n) + the two key additions
+    const double eps = 1.1102230246251565e-16;
+    const double guard = eps * (4096.0 * total + 4.0 * (double)n * T + 16.0 * T);
+
+    Scratch<int32_t> next(ctx), exit0(ctx), exit1(ctx);
+    Scratch<int64_t> first(ctx), entryS(ctx), entryC(ctx), counts(ctx), off(ctx), replays(ctx);
+    const int64_t nC = cdiv(n, VC0), nS = cdiv(n, VSC);
+    FMK_TRY(next.alloc(n)); FMK_TRY(exit0.alloc(n)); FMK_TRY(exit1.alloc(n));
+    FMK_TRY(first.alloc(1)); FMK_TRY(entryS.alloc(nS)); FMK_TRY(entryC.alloc(nC)); FMK_TRY(counts.alloc(nC));
+    FMK_TRY(off.alloc(nC + 1)); FMK_TRY(replays.alloc(1));
+    FMK_CUDA(ctx, cudaMemsetAsync(replays.p, 0, 8, ctx->stream));
+    FMK_CUDA(ctx, cudaMemsetAsync(entryS.p, 0xff, (size_t)nS * 8, ctx->stream));
+    FMK_CUDA(ctx, cudaMemsetAsync(entryC.p, 0xff, (size_t)nC * 8, ctx->stream));
+    FMK_CUDA(ctx, cudaMemsetAsync(off.p, 0, 8, ctx->stream));
+    FMK_LAUNCH(ctx, k_volume_next, (unsigned)cdiv(n, VN_THREADS), VN_THREADS, 0, (const double *)P.p, t->amount, n, T, guard,
+               next.p, replays.p);
+    FMK_LAUNCH(ctx, k_volume_first, 1, 1, 0, t->amount, n, T, first.p);
+    FMK_LAUNCH(ctx, k_volume_exit0, (unsigned)nC, 256, 0, (const int32_t *)next.p, n, exit0.p);
+    FMK_LAUNCH(ctx, k_volume_exit1, (unsigned)nS, 256, 0, (const int32_t *)exit0.p, n, exit1.p);
+    FMK_LAUNCH(ctx, k_volume_chase2, 1, 1, 0, (const int32_t *)exit1.p, (const int64_t *)first.p, n, entryS.p);
+    FMK_LAUNCH(ctx, k_volume_chase1, (unsigned)cdiv(nS, 64), 64, 0, (const int32_t *)exit0.p, (const int64_t *)entryS.p, nS, n, entryC.p);
+    FMK_LAUNCH(ctx, k_volume_count, (unsigned)cdiv(nC, 128), 128, 0, (const int32_t *)next.p, (const int64_t *)entryC.p, nC, n, counts.p);
+    FMK_TRY(device_inclusive_scan<int64_t>(ctx, CntIn{counts.p}, CntOut{off.p}, nC, (int64_t *)nullptr));
+    int64_t nb = 0, hrep = 0;
+    FMK_CUDA(ctx, cudaMemcpyAsync(&hrep, replays.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FMK_TRY(fetch(ctx, &nb, off.p + nC));
+    ctx->stats[0] = nC; ctx->stats[1] = hrep; ctx->stats[2] = 1;
+    int64_t *idx = nullptr;
+    FMK_TRY(fmk_dalloc(ctx, &idx, nb + 1));
+    k_volume_emit<<<(unsigned)cdiv(nC, 128), 128, 0, ctx->stream>>>((const int32_t *)next.p, (const int64_t *)entryC.p,
+                                                                   (const int64_t *)off.p, nC, n, idx);
+    ctx->launches++;
+    return finish_index(ctx, t, idx, nb + 1, out_ix);
+}
+
+int fmk_cusum_index_impl(fmk_ctx *ctx, const fmk_trades *, fmk_buf *, double, double, fmk_index **out) {
+    *out = nullptr;
+    return fmk_fail(ctx, FMK_ERR_INTERNAL, "cusum bars: not built yet");
+}

@@ -1,0 +1,740 @@
+// reduce.cu -- per-bar reductions keyed on the close-index array (bar/base.py:303-850 of the reference).
+//
+// Layout: bar i covers ticks (ci[i], ci[i+1]] of the SoA trade columns.  One warp owns one bar: lanes stride the
+// bar's contiguous tick range with coalesced 8-byte loads (4 independent loads in flight per lane per column),
+// partial results are combined with warp shuffles.  Bars are independent, so there are no atomics and results are
+// deterministic.  When bars are very short (avg < 8 ticks) a thread-per-bar variant is used instead.
+// HBM traffic: price + amount read once (16 B/tick) for OHLCV; amount once more (8 B/tick) for the median.
+#include <math.h>
+#include <new>
+#include "common.cuh"
+#include "scan.cuh"
+
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+__device__ __forceinline__ double warp_max(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(FULL, x, o));
+    return x;
+}
+__device__ __forceinline__ double warp_min(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmin(x, __shfl_xor_sync(FULL, x, o));
+    return x;
+}
+__device__ __forceinline__ int64_t warp_sum_i64(int64_t x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+__device__ __forceinline__ int64_t wrap_idx(int64_t j, int64_t n) { return j < 0 ? j + n : j; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// a7: comp_bar_ohlcv (bar/base.py:306-407) without the median (see k_bar_order_stats)
+// ---------------------------------------------------------------------------------------------------------------
+struct OhlcvOut {
+    double *open, *high, *low, *close, *vwap;
+    float *volume;
+    int64_t *trades;
+};
+
+__device__ __forceinline__ void ohlcv_empty(const OhlcvOut &o, int64_t i, const double *p, int64_t e, int64_t n) {
+    const double pe = p[wrap_idx(e, n)];  // base.py:352-361: O=H=L=C=prices[end], rest 0
+    o.open[i] = pe; o.high[i] = pe; o.low[i] = pe; o.close[i] = pe;
+    o.volume[i] = 0.0f; o.vwap[i] = 0.0; o.trades[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_bar_ohlcv_warp(const double *__restrict__ p, const double *__restrict__ v,
+                                                        const int64_t *__restrict__ ci, int64_t nb, int64_t n,
+                                                        OhlcvOut o) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nb; i += nwarps) {
+        const int64_t s = ci[i], e = ci[i + 1];
+        if (s == e) {
+            if (lane == 0) ohlcv_empty(o, i, p, e, n);
+            continue;
+        }
+        const int64_t start = s + 1;
+        double hi = -INFINITY, lo = INFINITY, sv = 0.0, sd = 0.0;
+        int64_t j = start + lane;
+        // 4 independent (price, amount) pairs in flight per lane
+        for (; j + 96 <= e; j += 128) {
+            double p0 = __ldg(p + j), p1 = __ldg(p + j + 32), p2 = __ldg(p + j + 64), p3 = __ldg(p + j + 96);
+            double v0 = __ldg(v + j), v1 = __ldg(v + j + 32), v2 = __ldg(v + j + 64), v3 = __ldg(v + j + 96);
+            hi = fmax(fmax(hi, fmax(p0, p1)), fmax(p2, p3));
+            lo = fmin(fmin(lo, fmin(p0, p1)), fmin(p2, p3));
+            sv += (v0 + v1) + (v2 + v3);
+            sd += (p0 * v0 + p1 * v1) + (p2 * v2 + p3 * v3);
+        }
+        for (; j <= e; j += 32) {
+            double pj = __ldg(p + j), vj = __ldg(v + j);
+            hi = fmax(hi, pj); lo = fmin(lo, pj);
+            sv += vj; sd += pj * vj;
+        }
+        hi = warp_max(hi); lo = warp_min(lo); sv = warp_sum(sv); sd = warp_sum(sd);
+        if (lane == 0) {
+            o.open[i] = p[start]; o.close[i] = p[e]; o.high[i] = hi; o.low[i] = lo;
+            o.volume[i] = (float)sv;
+            o.vwap[i] = sv > 0 ? sd / sv : 0.0;
+            o.trades[i] = e - start + 1;
+        }
+    }
+}
+
+// thread-per-bar variant for very short bars (sequential sums: same order as the reference)
+__global__ void __launch_bounds__(256) k_bar_ohlcv_thread(const double *__restrict__ p, const double *__restrict__ v,
+                                                          const int64_t *__restrict__ ci, int64_t nb, int64_t n,
+                                                          OhlcvOut o) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const int64_t s = ci[i], e = ci[i + 1];
+    if (s == e) { ohlcv_empty(o, i, p, e, n); return; }
+    const int64_t start = s + 1;
+    double hi = p[start], lo = p[start], sv = 0.0, sd = 0.0;
+    for (int64_t j = start; j <= e; j++) {
+        double pj = p[j], vj = v[j];
+        if (pj > hi) hi = pj;
+        if (pj < lo) lo = pj;
+        sv += vj; sd += pj * vj;
+    }
+    o.open[i] = p[start]; o.close[i] = p[e]; o.high[i] = hi; o.low[i] = lo;
+    o.volume[i] = (float)sv;
+    o.vwap[i] = sv > 0 ? sd / sv : 0.0;
+    o.trades[i] = e - start + 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// order statistics per bar: np.median (base.py:401-405) and np.percentile(., 95) (base.py:593) with Numba's
+// definitions (numba/np/arraymath.py _median_inner / _collect_percentiles_inner).
+// One block per bar (grid-stride).  Bars that fit in shared memory are bitonic-sorted there; longer bars use an
+// 8-pass MSB radix select over the bar's global-memory segment.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int OS_THREADS = 128;
+constexpr int OS_CAP = 4096;  // doubles in shared memory (32 KB)
+
+__device__ __forceinline__ unsigned long long dkey(double x) {  // order-preserving map double -> uint64
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dunkey(unsigned long long k) {
+    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// k-th smallest (0-based) of a[0..cnt) in global memory, plus the (k+1)-th; block-cooperative.
+__device__ void radix_select_two(const double *__restrict__ a, int64_t cnt, int64_t k, double *r0, double *r1) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ long long s_k;
+    __shared__ unsigned long long s_next;
+    __shared__ long long s_le;
+    if (threadIdx.x == 0) { s_prefix = 0; s_k = k; }
+    __syncthreads();
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = 56 - 8 * pass;
+        for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        const unsigned long long mask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+        for (int64_t j = threadIdx.x; j < cnt; j += blockDim.x) {
+            unsigned long long key = dkey(a[j]);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long kk = s_k;
+            int b = 0;
+            for (; b < 256; b++) {
+                if (kk < (long long)hist[b]) break;
+                kk -= hist[b];
+            }
+            s_k = kk;
+            s_prefix = prefix | ((unsigned long long)b << shift);
+        }
+        __syncthreads();
+    }
+    const unsigned long long kth = s_prefix;
+    // count elements <= kth and the smallest element > kth
+    if (threadIdx.x == 0) { s_next = ~0ull; s_le = 0; }
+    __syncthreads();
+    unsigned long long mn = ~0ull;
+    long long le = 0;
+    for (int64_t j = threadIdx.x; j < cnt; j += blockDim.x) {
+        unsigned long long key = dkey(a[j]);
+        if (key <= kth) le++;
+        else if (key < mn) mn = key;
+    }
+    atomicMin(&s_next, mn);
+    atomicAdd((unsigned long long *)&s_le, (unsigned long long)le);
+    __syncthreads();
+    *r0 = dunkey(kth);
+    *r1 = (k + 1 < s_le) ? dunkey(kth) : (s_next == ~0ull ? dunkey(kth) : dunkey(s_next));
+    __syncthreads();
+}
+
+// mode bit 0: median -> median_out ; bit 1: 95th percentile -> p95_out
+__global__ void __launch_bounds__(OS_THREADS) k_bar_order_stats(const double *__restrict__ a,
+                                                                const int64_t *__restrict__ ci, int64_t nb, int mode,
+                                                                double *__restrict__ median_out,
+                                                                double *__restrict__ p95_out) {
+    __shared__ double buf[OS_CAP];
+    for (int64_t i = blockIdx.x; i < nb; i += gridDim.x) {
+        const int64_t start = ci[i] + 1, e = ci[i + 1];
+        const int64_t cnt = e - start + 1;
+        if (cnt <= 0) {  // empty bar: median 0.0 (base.py:360); percentile untouched (NaN path handled by caller)
+            if (threadIdx.x == 0 && (mode & 1)) median_out[i] = 0.0;
+            continue;
+        }
+        const double *seg = a + start;
+        // ranks needed
+        const int64_t mk = (cnt & 1) ? (cnt >> 1) : (cnt >> 1) - 1;  // median: a[mk] (odd) or (a[mk]+a[mk+1])/2
+        double rank = 1.0 + (double)(cnt - 1) * (95.0 / 100.0);       // numba: 1 + (n-1)*true_divide(q,100)
+        double f = floor(rank), mfrac = rank - f;
+        const int64_t pk = (int64_t)(f - 1.0);
+        if (cnt <= OS_CAP) {
+            int64_t m2 = 1;
+            while (m2 < cnt) m2 <<= 1;
+            for (int64_t j = threadIdx.x; j < m2; j += OS_THREADS) buf[j] = j < cnt ? seg[j] : INFINITY;
+            __syncthreads();
+            for (int64_t k = 2; k <= m2; k <<= 1) {
+                for (int64_t jj = k >> 1; jj > 0; jj >>= 1) {
+                    for (int64_t t = threadIdx.x; t < (m2 >> 1); t += OS_THREADS) {
+                        // t-th compare-exchange pair of this step
+                        int64_t lo = 2 * t - (t & (jj - 1));
+                        int64_t hi = lo + jj;
+                        bool up = ((lo & k) == 0);
+                        double x = buf[lo], y = buf[hi];
+                        if ((x > y) == up) { buf[lo] = y; buf[hi] = x; }
+                    }
+                    __syncthreads();
+                }
+            }
+            if (threadIdx.x == 0) {
+                if (mode & 1) median_out[i] = (cnt & 1) ? buf[mk] : (buf[mk] + buf[mk + 1]) / 2;
+                if (mode & 2) {
+                    if (cnt == 1) p95_out[i] = buf[0];
+                    else {
+                        double lower = buf[pk], upper = buf[pk + 1 < cnt ? pk + 1 : pk];
+                        p95_out[i] = lower * (1 - mfrac) + upper * mfrac;
+                    }
+                }
+            }
+            __syncthreads();
+        } else {
+            double r0, r1;
+            if (mode & 1) {
+                radix_select_two(seg, cnt, mk, &r0, &r1);
+                if (threadIdx.x == 0) median_out[i] = (cnt & 1) ? r0 : (r0 + r1) / 2;
+            }
+            if (mode & 2) {
+                radix_select_two(seg, cnt, pk, &r0, &r1);
+                if (threadIdx.x == 0) p95_out[i] = r0 * (1 - mfrac) + r1 * mfrac;
+            }
+        }
+    }
+}
+
+static int launch_order_stats(fmk_ctx *ctx, const double *a, const int64_t *ci, int64_t nb, int mode, double *med,
+                              double *p95) {
+    if (nb <= 0) return FMK_OK;
+    int64_t grid = nb < (int64_t)ctx->sm_count * 32 ? nb : (int64_t)ctx->sm_count * 32;
+    FMK_LAUNCH(ctx, k_bar_order_stats, (unsigned)grid, OS_THREADS, 0, a, ci, nb, mode, med, p95);
+    return FMK_OK;
+}
+
+static int check_index(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix) {
+    if (ix->m < 2) return fmk_fail(ctx, FMK_ERR_ARG, "Bar close indices must contain at least two elements.");
+    if (ix->n_ticks != t->n) return fmk_fail(ctx, FMK_ERR_ARG, "index was built for a different trades handle");
+    return FMK_OK;
+}
+
+static int run_ohlcv(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, OhlcvOut o, double *median) {
+    const int64_t nb = ix->m - 1;
+    if (t->n / nb >= 8) {
+        int64_t warps = nb;
+        int64_t blocks = cdiv(warps, 8);
+        int64_t maxb = (int64_t)ctx->sm_count * 64;
+        if (blocks > maxb) blocks = maxb;
+        FMK_LAUNCH(ctx, k_bar_ohlcv_warp, (unsigned)blocks, 256, 0, t->price, t->amount, ix->close_idx, nb, t->n, o);
+    } else {
+        FMK_LAUNCH(ctx, k_bar_ohlcv_thread, (unsigned)cdiv(nb, 256), 256, 0, t->price, t->amount, ix->close_idx, nb, t->n, o);
+    }
+    if (median) FMK_TRY(launch_order_stats(ctx, t->amount, ix->close_idx, nb, 1, median, nullptr));
+    return FMK_OK;
+}
+
+template <typename T>
+static int d2h(fmk_ctx *ctx, T *host, const T *dev, int64_t count) {
+    if (host && count > 0) FMK_CUDA(ctx, cudaMemcpyAsync(host, dev, (size_t)count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    return FMK_OK;
+}
+
+extern "C" int fmk_bar_ohlcv(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, double *open, double *high,
+                             double *low, double *close, float *volume, double *vwap, int64_t *trades, double *median) {
+    FMK_TRY(check_index(ctx, t, ix));
+    const int64_t nb = ix->m - 1;
+    Scratch<double> d(ctx);   // open, high, low, close, vwap, median
+    Scratch<float> f(ctx);
+    Scratch<int64_t> l(ctx);
+    FMK_TRY(d.alloc(6 * nb));
+    FMK_TRY(f.alloc(nb));
+    FMK_TRY(l.alloc(nb));
+    OhlcvOut o{d.p, d.p + nb, d.p + 2 * nb, d.p + 3 * nb, d.p + 4 * nb, f.p, l.p};
+    FMK_TRY(run_ohlcv(ctx, t, ix, o, median ? d.p + 5 * nb : nullptr));
+    FMK_TRY(d2h(ctx, open, o.open, nb));
+    FMK_TRY(d2h(ctx, high, o.high, nb));
+    FMK_TRY(d2h(ctx, low, o.low, nb));
+    FMK_TRY(d2h(ctx, close, o.close, nb));
+    FMK_TRY(d2h(ctx, vwap, o.vwap, nb));
+    FMK_TRY(d2h(ctx, median, d.p + 5 * nb, nb));
+    FMK_TRY(d2h(ctx, volume, o.volume, nb));
+    FMK_TRY(d2h(ctx, trades, o.trades, nb));
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMK_OK;
+}
+
+extern "C" int fmk_bar_ohlcv_device(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, int with_median) {
+    FMK_TRY(check_index(ctx, t, ix));
+    const int64_t nb = ix->m - 1;
+    const int64_t need = nb * (6 * 8 + 4 + 8);
+    if (ctx->res_cols_bytes < need) {
+        if (ctx->res_cols) cudaFree(ctx->res_cols);
+        ctx->res_cols = nullptr;
+        FMK_CUDA(ctx, cudaMalloc(&ctx->res_cols, (size_t)need));
+        ctx->res_cols_bytes = need;
+    }
+    double *d = (double *)ctx->res_cols;
+    int64_t *l = (int64_t *)(d + 6 * nb);
+    float *f = (float *)(l + nb);
+    OhlcvOut o{d, d + nb, d + 2 * nb, d + 3 * nb, d + 4 * nb, f, l};
+    return run_ohlcv(ctx, t, ix, o, with_median ? d + 5 * nb : nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a8: comp_bar_directional_features (bar/base.py:409-546)
+// Ordered warp pass: 32 ticks per step, inclusive warp scans of the signed tick/volume/dollar flows with a carry,
+// running min/max taken only at ticks whose side is +-1 (side 0 ticks are skipped exactly like the reference).
+// ---------------------------------------------------------------------------------------------------------------
+struct DirOut {
+    int64_t *ticks_buy, *ticks_sell;
+    float *volume_buy, *volume_sell, *dollars_buy, *dollars_sell, *mean_spread, *max_spread;
+    int64_t *cum_ticks_min, *cum_ticks_max;
+    float *cum_volume_min, *cum_volume_max, *cum_dollars_min, *cum_dollars_max;
+};
+
+__global__ void __launch_bounds__(256) k_bar_directional(const double *__restrict__ p, const double *__restrict__ v,
+                                                         const int8_t *__restrict__ side,
+                                                         const int64_t *__restrict__ ci, int64_t nb, int64_t n,
+                                                         DirOut o) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nb; i += nwarps) {
+        const int64_t start = ci[i] + 1, e = ci[i + 1];
+        int64_t tb = 0, tsell = 0;
+        double vb = 0, vs = 0, db = 0, ds = 0, maxsp = 0, cumsp = 0;
+        int64_t ctmin = 1000000000ll, ctmax = -1000000000ll;
+        double cvmin = INFINITY, cvmax = -INFINITY, cdmin = INFINITY, cdmax = -INFINITY;
+        int64_t carry_t = 0;
+        double carry_v = 0, carry_d = 0;
+        int prev_init = 0;
+        if (e > start) prev_init = side[wrap_idx(start - 1, n)];
+        for (int64_t base = start; base <= e; base += 32) {
+            const int64_t j = base + lane;
+            const bool act = j <= e;
+            int cur = 0, prv = 0;
+            double pj = 0, vj = 0, pprev = 0;
+            if (act) {
+                cur = side[j];
+                pj = p[j]; vj = v[j];
+                const int64_t q = wrap_idx(j - 1, n);
+                prv = (j == start) ? prev_init : (int)side[q];
+                if (cur != prv) pprev = p[q];
+            }
+            if (act && cur != prv) {
+                double sp = fabs(pj - pprev);
+                maxsp = fmax(maxsp, sp);
+                cumsp += sp;
+            }
+            const int st = (cur == 1) ? 1 : (cur == -1 ? -1 : 0);
+            const double dol = pj * vj;
+            if (st == 1) { tb++; vb += vj; db += dol; }
+            else if (st == -1) { tsell++; vs += vj; ds += dol; }
+            // inclusive scans of signed flows
+            int64_t it = st;
+            double iv = (double)st * vj, id = (double)st * dol;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                int64_t yt = __shfl_up_sync(FULL, it, off);
+                double yv = __shfl_up_sync(FULL, iv, off);
+                double yd = __shfl_up_sync(FULL, id, off);
+                if (lane >= off) { it += yt; iv += yv; id += yd; }
+            }
+            it += carry_t; iv += carry_v; id += carry_d;
+            if (st != 0) {
+                ctmax = it > ctmax ? it : ctmax; ctmin = it < ctmin ? it : ctmin;
+                cvmax = fmax(cvmax, iv); cvmin = fmin(cvmin, iv);
+                cdmax = fmax(cdmax, id); cdmin = fmin(cdmin, id);
+            }
+            carry_t = __shfl_sync(FULL, it, 31);
+            carry_v = __shfl_sync(FULL, iv, 31);
+            carry_d = __shfl_sync(FULL, id, 31);
+        }
+        tb = warp_sum_i64(tb); tsell = warp_sum_i64(tsell);
+        vb = warp_sum(vb); vs = warp_sum(vs); db = warp_sum(db); ds = warp_sum(ds);
+        maxsp = warp_max(maxsp); cumsp = warp_sum(cumsp);
+        cvmax = warp_max(cvmax); cvmin = warp_min(cvmin); cdmax = warp_max(cdmax); cdmin = warp_min(cdmin);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            int64_t a = __shfl_xor_sync(FULL, ctmax, off), b = __shfl_xor_sync(FULL, ctmin, off);
+            ctmax = a > ctmax ? a : ctmax; ctmin = b < ctmin ? b : ctmin;
+        }
+        if (lane == 0) {
+            o.ticks_buy[i] = tb; o.ticks_sell[i] = tsell;
+            o.volume_buy[i] = (float)vb; o.volume_sell[i] = (float)vs;
+            o.dollars_buy[i] = (float)db; o.dollars_sell[i] = (float)ds;
+            o.max_spread[i] = (float)maxsp;
+            o.mean_spread[i] = (float)(cumsp / (double)(tb + tsell));  // 0/0 -> NaN like the reference
+            o.cum_ticks_min[i] = ctmin; o.cum_ticks_max[i] = ctmax;
+            // float32(+-1e9) sentinels survive when no +-1 tick was seen (base.py:457-462)
+            o.cum_volume_min[i] = (tb + tsell) ? (float)fmin(cvmin, (double)1e9f) : 1e9f;
+            o.cum_volume_max[i] = (tb + tsell) ? (float)fmax(cvmax, (double)-1e9f) : -1e9f;
+            o.cum_dollars_min[i] = (tb + tsell) ? (float)fmin(cdmin, (double)1e9f) : 1e9f;
+            o.cum_dollars_max[i] = (tb + tsell) ? (float)fmax(cdmax, (double)-1e9f) : -1e9f;
+        }
+    }
+}
+
+extern "C" int fmk_bar_directional(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, int64_t *ticks_buy,
+                                   int64_t *ticks_sell, float *volume_buy, float *volume_sell, float *dollars_buy,
+                                   float *dollars_sell, float *mean_spread, float *max_spread, int64_t *cum_ticks_min,
+                                   int64_t *cum_ticks_max, float *cum_volume_min, float *cum_volume_max,
+                                   float *cum_dollars_min, float *cum_dollars_max) {
+    FMK_TRY(check_index(ctx, t, ix));
+    if (!t->side) return fmk_fail(ctx, FMK_ERR_ARG, "trades have no 'side' column");
+    const int64_t nb = ix->m - 1;
+    Scratch<int64_t> l(ctx);
+    Scratch<float> f(ctx);
+    FMK_TRY(l.alloc(4 * nb));
+    FMK_TRY(f.alloc(10 * nb));
+    DirOut o{l.p, l.p + nb, f.p, f.p + nb, f.p + 2 * nb, f.p + 3 * nb, f.p + 4 * nb, f.p + 5 * nb,
+             l.p + 2 * nb, l.p + 3 * nb, f.p + 6 * nb, f.p + 7 * nb, f.p + 8 * nb, f.p + 9 * nb};
+    int64_t blocks = cdiv(nb, 8);
+    int64_t maxb = (int64_t)ctx->sm_count * 64;
+    if (blocks > maxb) blocks = maxb;
+    FMK_LAUNCH(ctx, k_bar_directional, (unsigned)blocks, 256, 0, t->price, t->amount, t->side, ix->close_idx, nb, t->n, o);
+    FMK_TRY(d2h(ctx, ticks_buy, o.ticks_buy, nb)); FMK_TRY(d2h(ctx, ticks_sell, o.ticks_sell, nb));
+    FMK_TRY(d2h(ctx, volume_buy, o.volume_buy, nb)); FMK_TRY(d2h(ctx, volume_sell, o.volume_sell, nb));
+    FMK_TRY(d2h(ctx, dollars_buy, o.dollars_buy, nb)); FMK_TRY(d2h(ctx, dollars_sell, o.dollars_sell, nb));
+    FMK_TRY(d2h(ctx, mean_spread, o.mean_spread, nb)); FMK_TRY(d2h(ctx, max_spread, o.max_spread, nb));
+    FMK_TRY(d2h(ctx, cum_ticks_min, o.cum_ticks_min, nb)); FMK_TRY(d2h(ctx, cum_ticks_max, o.cum_ticks_max, nb));
+    FMK_TRY(d2h(ctx, cum_volume_min, o.cum_volume_min, nb)); FMK_TRY(d2h(ctx, cum_volume_max, o.cum_volume_max, nb));
+    FMK_TRY(d2h(ctx, cum_dollars_min, o.cum_dollars_min, nb)); FMK_TRY(d2h(ctx, cum_dollars_max, o.cum_dollars_max, nb));
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a9: comp_bar_trade_size_features (bar/base.py:549-612)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bar_trade_size(const double *__restrict__ a, const double *__restrict__ theta,
+                                                        const int64_t *__restrict__ ci, int64_t nb, double theta_mult,
+                                                        const double *__restrict__ p95, float *mean_size_rel,
+                                                        float *size_95_rel, float *pct_block, float *size_gini) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float fnan = __int_as_float(0x7fc00000);
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nb; i += nwarps) {
+        const int64_t start = ci[i] + 1, e = ci[i + 1];
+        float o0 = fnan, o1 = fnan, o2 = fnan, o3 = fnan;
+        const double th = theta[i];
+        if (start <= e && th != 0.0) {
+            const double thr = th * theta_mult;
+            const int64_t cnt = e - start + 1;
+            double s = 0.0, blk = 0.0;
+            for (int64_t j = start + lane; j <= e; j += 32) {
+                double x = __ldg(a + j);
+                s += x;
+                if (x > thr) blk += x;
+            }
+            s = warp_sum(s); blk = warp_sum(blk);
+            o0 = (float)log1p((s / (double)cnt) / thr);
+            o1 = (float)log1p(p95[i] / thr);
+            if (s != 0.0) {
+                o2 = (float)(blk / s);
+                if (cnt == 1) o3 = 0.0f;
+                else {
+                    double g = 0.0;
+                    for (int64_t j = start + lane; j <= e; j += 32) {
+                        double r = __ldg(a + j) / s;
+                        g += r * r;
+                    }
+                    g = warp_sum(g);
+                    o3 = (float)(1.0 - g);
+                }
+            }
+        }
+        if (lane == 0) { mean_size_rel[i] = o0; size_95_rel[i] = o1; pct_block[i] = o2; size_gini[i] = o3; }
+    }
+}
+
+extern "C" int fmk_bar_trade_size(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, const double *theta,
+                                  int64_t n_theta, double theta_mult, float *mean_size_rel, float *size_95_rel,
+                                  float *pct_block, float *size_gini) {
+    FMK_TRY(check_index(ctx, t, ix));
+    const int64_t nb = ix->m - 1;
+    if (n_theta != nb)
+        return fmk_fail(ctx, FMK_ERR_ARG, "Theta should match the the number of bars (len(bar_close_indices) - 1).");
+    Scratch<double> d(ctx);
+    Scratch<float> f(ctx);
+    FMK_TRY(d.alloc(2 * nb));
+    FMK_TRY(f.alloc(4 * nb));
+    FMK_CUDA(ctx, cudaMemcpyAsync(d.p, theta, (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FMK_TRY(launch_order_stats(ctx, t->amount, ix->close_idx, nb, 2, nullptr, d.p + nb));
+    int64_t blocks = cdiv(nb, 8);
+    int64_t maxb = (int64_t)ctx->sm_count * 64;
+    if (blocks > maxb) blocks = maxb;
+    FMK_LAUNCH(ctx, k_bar_trade_size, (unsigned)blocks, 256, 0, t->amount, d.p, ix->close_idx, nb, theta_mult, d.p + nb,
+               f.p, f.p + nb, f.p + 2 * nb, f.p + 3 * nb);
+    FMK_TRY(d2h(ctx, mean_size_rel, f.p, nb)); FMK_TRY(d2h(ctx, size_95_rel, f.p + nb, nb));
+    FMK_TRY(d2h(ctx, pct_block, f.p + 2 * nb, nb)); FMK_TRY(d2h(ctx, size_gini, f.p + 3 * nb, nb));
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a10/a11: comp_bar_footprints + comp_footprint_features (bar/base.py:615-850) -> CSR on the device
+// ---------------------------------------------------------------------------------------------------------------
+struct LevelsIn {
+    const double *lows, *highs;
+    double tick;
+    __device__ int64_t operator()(int64_t i) const {
+        // int(round(x / tick)): IEEE division then round-half-even
+        long long lo = __double2ll_rn(__ddiv_rn(lows[i], tick)), hi = __double2ll_rn(__ddiv_rn(highs[i], tick));
+        long long L = hi - lo + 1;
+        return L > 0 ? L : 0;
+    }
+};
+struct OffOut {
+    int64_t *off;
+    __device__ void operator()(int64_t i, int64_t cs) const { off[i + 1] = cs; }
+};
+
+// One warp per bar.  Level volumes are float32 accumulated in tick order (base.py:694-717): inside a 32-tick step,
+// lanes that hit the same (level, side) bin are serialised in lane (= tick) order by the lowest lane of the group,
+// so every bin sees exactly the reference's sequence of `float32(float64(bin) + amount)` updates.
+__global__ void __launch_bounds__(256) k_bar_footprint(const double *__restrict__ p, const double *__restrict__ a,
+                                                       const int8_t *__restrict__ side,
+                                                       const int64_t *__restrict__ ci, int64_t nb,
+                                                       const double *__restrict__ lows, double tick,
+                                                       const int64_t *__restrict__ off, int32_t *levels, float *bvol,
+                                                       float *svol, int32_t *bt, int32_t *st, int *err) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nb; i += nwarps) {
+        const int64_t start = ci[i] + 1, e = ci[i + 1];
+        const int64_t o = off[i], L = off[i + 1] - o;
+        const long long low = __double2ll_rn(__ddiv_rn(lows[i], tick));
+        for (int64_t k = lane; k < L; k += 32) {
+            levels[o + k] = (int32_t)(low + k);
+            bvol[o + k] = 0.0f; svol[o + k] = 0.0f; bt[o + k] = 0; st[o + k] = 0;
+        }
+        __syncwarp();
+        for (int64_t base = start; base <= e; base += 32) {
+            const int64_t j = base + lane;
+            long long bin = -1;  // 2*level + (sell ? 1 : 0); -1 = no update
+            double amt = 0.0;
+            if (j <= e) {
+                const int sd = side[j];
+                const long long lv = __double2ll_rn(__ddiv_rn(p[j], tick)) - low;
+                if (lv < 0 || lv >= L) atomicExch(err, 1);
+                else if (sd == 1) bin = 2 * lv;
+                else if (sd == -1) bin = 2 * lv + 1;
+                amt = a[j];
+            }
+            const unsigned grp = __match_any_sync(FULL, bin);
+            const int leader = __ffs(grp) - 1;
+            const bool lead = (lane == leader) && bin >= 0;
+            float acc = 0.0f;
+            int cntk = 0;
+            float *vp = nullptr;
+            int32_t *tp = nullptr;
+            if (lead) {
+                const int64_t lv = o + (bin >> 1);
+                vp = (bin & 1) ? svol + lv : bvol + lv;
+                tp = (bin & 1) ? st + lv : bt + lv;
+                acc = *vp;
+            }
+            // every lane walks the largest group size; shuffles are warp-wide
+            unsigned rem = grp;
+            const unsigned any_multi = __any_sync(FULL, bin >= 0);
+            if (any_multi) {
+                int maxg = __popc(grp);
+                for (int off2 = 16; off2 > 0; off2 >>= 1) maxg = max(maxg, __shfl_xor_sync(FULL, maxg, off2));
+                for (int r = 0; r < maxg; r++) {
+                    int src = rem ? (__ffs(rem) - 1) : lane;
+                    double x = __shfl_sync(FULL, amt, src);
+                    if (lead && rem) { acc = (float)((double)acc + x); cntk++; }
+                    if (rem) rem &= rem - 1;
+                }
+                if (lead) { *vp = acc; *tp += cntk; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// one thread per bar: comp_footprint_features (base.py:755-850) with Numba's float32 typing of every intermediate
+__global__ void k_footprint_features(const int64_t *__restrict__ off, int64_t nb, const int32_t *__restrict__ levels,
+                                     const float *__restrict__ bvol, const float *__restrict__ svol, double factor,
+                                     uint8_t *bimb, uint8_t *simb, uint16_t *bsum, uint16_t *ssum, int32_t *cot,
+                                     int16_t *run_signed, double *vp_skew, double *vp_gini) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const int64_t o = off[i], L = off[i + 1] - o;
+    const int32_t *lv = levels + o;
+    const float *b = bvol + o, *s = svol + o;
+    long long max_run = 0, max_sign = 0, run = 0, run_sign = 0;
+    unsigned bs = 0, ss = 0;
+    float sumtot = 0.0f, best = 0.0f;
+    int64_t arg = 0;
+    for (int64_t k = 0; k < L; k++) {
+        const bool si = (L > 1 && k + 1 < L) ? ((double)s[k] > __dmul_rn((double)b[k + 1], factor)) : false;
+        const bool bi = (L > 1 && k >= 1) ? ((double)b[k] > __dmul_rn((double)s[k - 1], factor)) : false;
+        bimb[o + k] = bi; simb[o + k] = si;
+        bs += bi; ss += si;
+        const int sign = bi ? 1 : (si ? -1 : 0);
+        if (sign != 0 && sign == run_sign) run += 1;
+        else if (sign != 0) { run = 1; run_sign = sign; }
+        else { run = 0; run_sign = 0; }
+        if (run > max_run) { max_run = run; max_sign = run_sign; }
+        const float t = __fadd_rn(b[k], s[k]);
+        sumtot = __fadd_rn(sumtot, t);
+        if (k == 0 || t > best) { best = t; arg = k; }
+    }
+    bsum[i] = (uint16_t)bs; ssum[i] = (uint16_t)ss;
+    run_signed[i] = (int16_t)(max_run * max_sign);
+    cot[i] = L > 0 ? lv[arg] : 0;
+    double skew = 0.0, gini = 0.0;
+    if (sumtot > 0 && L > 0) {
+        float num = 0.0f;
+        for (int64_t k = 0; k < L; k++) num = __fadd_rn(num, __fmul_rn((float)lv[k], __fadd_rn(b[k], s[k])));
+        const float vw = __fdiv_rn(num, sumtot);
+        float dot = 0.0f, g = 0.0f;
+        for (int64_t k = 0; k < L; k++) {
+            const float t = __fadd_rn(b[k], s[k]);
+            dot = __fadd_rn(dot, __fmul_rn(__fsub_rn((float)lv[k], vw), t));
+            const float r = __fdiv_rn(t, sumtot);
+            g = __fadd_rn(g, __fmul_rn(r, r));
+        }
+        skew = (double)__fdiv_rn(dot, sumtot);
+        gini = 1.0 - (double)g;
+    }
+    vp_skew[i] = skew; vp_gini[i] = gini;
+}
+
+extern "C" void fmk_footprint_free(fmk_ctx *ctx, fmk_footprint *fp) {
+    if (!fp) return;
+    fmk_dfree(ctx, fp->level_offsets); fmk_dfree(ctx, fp->price_levels);
+    fmk_dfree(ctx, fp->buy_vol); fmk_dfree(ctx, fp->sell_vol);
+    fmk_dfree(ctx, fp->buy_ticks); fmk_dfree(ctx, fp->sell_ticks);
+    fmk_dfree(ctx, fp->buy_imb); fmk_dfree(ctx, fp->sell_imb);
+    fmk_dfree(ctx, fp->buy_imb_sum); fmk_dfree(ctx, fp->sell_imb_sum);
+    fmk_dfree(ctx, fp->cot); fmk_dfree(ctx, fp->run_signed);
+    fmk_dfree(ctx, fp->vp_skew); fmk_dfree(ctx, fp->vp_gini);
+    delete fp;
+}
+
+extern "C" int64_t fmk_footprint_levels(const fmk_footprint *fp) { return fp->n_levels; }
+
+extern "C" int fmk_bar_footprints(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, double tick,
+                                  const double *bar_lows, const double *bar_highs, double factor, fmk_footprint **out) {
+    *out = nullptr;
+    FMK_TRY(check_index(ctx, t, ix));
+    if (!t->side) return fmk_fail(ctx, FMK_ERR_ARG, "trades have no 'side' column");
+    if (!(tick > 0)) return fmk_fail(ctx, FMK_ERR_ARG, "price_tick_size must be positive");
+    const int64_t nb = ix->m - 1;
+    Scratch<double> lh(ctx);
+    Scratch<int> err(ctx);
+    FMK_TRY(lh.alloc(2 * nb));
+    FMK_TRY(err.alloc(1));
+    FMK_CUDA(ctx, cudaMemcpyAsync(lh.p, bar_lows, (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FMK_CUDA(ctx, cudaMemcpyAsync(lh.p + nb, bar_highs, (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FMK_CUDA(ctx, cudaMemsetAsync(err.p, 0, sizeof(int), ctx->stream));
+    fmk_footprint *fp = new (std::nothrow) fmk_footprint();
+    if (!fp) return FMK_ERR_ALLOC;
+    memset(fp, 0, sizeof(*fp));
+    fp->n_bars = nb;
+    int rc = fmk_dalloc(ctx, &fp->level_offsets, nb + 1);
+    if (!rc) {
+        cudaMemsetAsync(fp->level_offsets, 0, 8, ctx->stream);
+        rc = device_inclusive_scan<int64_t>(ctx, LevelsIn{lh.p, lh.p + nb, tick}, OffOut{fp->level_offsets}, nb, (int64_t *)nullptr);
+    }
+    int64_t total = 0;
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(&total, fp->level_offsets + nb, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fmk_fail(ctx, FMK_ERR_CUDA, cudaGetErrorString(e));
+    }
+    fp->n_levels = total;
+    if (!rc) rc = fmk_dalloc(ctx, &fp->price_levels, total);
+    if (!rc) rc = fmk_dalloc(ctx, &fp->buy_vol, total);
+    if (!rc) rc = fmk_dalloc(ctx, &fp->sell_vol, total);
+    if (!rc) rc = fmk_dalloc(ctx, &fp->buy_ticks, total);
+    if (!rc) rc = fmk_dalloc(ctx, &fp->sell_ticks, total);
+    if (!rc) rc = fmk_dalloc(ctx, &fp->buy_imb, total);
+    if (!rc) rc = fmk_dalloc(ctx, &fp->sell_imb, total);
+    if (!rc) rc = fmk_dalloc(ctx, &fp->buy_imb_sum, nb);
+    if (!rc) rc = fmk_dalloc(ctx, &fp->sell_imb_sum, nb);
+    if (!rc) rc = fmk_dalloc(ctx, &fp->cot, nb);
+    if (!rc) rc = fmk_dalloc(ctx, &fp->run_signed, nb);
+    if (!rc) rc = fmk_dalloc(ctx, &fp->vp_skew, nb);
+    if (!rc) rc = fmk_dalloc(ctx, &fp->vp_gini, nb);
+    if (rc) { fmk_footprint_free(ctx, fp); return rc; }
+    int64_t blocks = cdiv(nb, 8);
+    int64_t maxb = (int64_t)ctx->sm_count * 64;
+    if (blocks > maxb) blocks = maxb;
+    k_bar_footprint<<<(unsigned)blocks, 256, 0, ctx->stream>>>(t->price, t->amount, t->side, ix->close_idx, nb, lh.p, tick,
+                                                              fp->level_offsets, fp->price_levels, fp->buy_vol,
+                                                              fp->sell_vol, fp->buy_ticks, fp->sell_ticks, err.p);
+    ctx->launches++;
+    k_footprint_features<<<(unsigned)cdiv(nb, 128), 128, 0, ctx->stream>>>(fp->level_offsets, nb, fp->price_levels, fp->buy_vol,
+                                                                          fp->sell_vol, factor, fp->buy_imb, fp->sell_imb,
+                                                                          fp->buy_imb_sum, fp->sell_imb_sum, fp->cot,
+                                                                          fp->run_signed, fp->vp_skew, fp->vp_gini);
+    ctx->launches++;
+    int herr = 0;
+    cudaError_t e = cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { fmk_footprint_free(ctx, fp); return fmk_fail(ctx, FMK_ERR_CUDA, cudaGetErrorString(e)); }
+    if (herr) {
+        fmk_footprint_free(ctx, fp);
+        return fmk_fail(ctx, FMK_ERR_LEVEL, "Something went wrong! Invalid price level index!");
+    }
+    *out = fp;
+    return FMK_OK;
+}
+
+extern "C" int fmk_footprint_download(fmk_ctx *ctx, const fmk_footprint *fp, int64_t *level_offsets,
+                                      int32_t *price_levels, float *buy_volumes, float *sell_volumes,
+                                      int32_t *buy_ticks, int32_t *sell_ticks, uint8_t *buy_imbalances,
+                                      uint8_t *sell_imbalances, uint16_t *buy_imb_sum, uint16_t *sell_imb_sum,
+                                      int32_t *cot_price_level, int16_t *imb_max_run_signed, double *vp_skew,
+                                      double *vp_gini) {
+    const int64_t nb = fp->n_bars, nl = fp->n_levels;
+    FMK_TRY(d2h(ctx, level_offsets, fp->level_offsets, nb + 1));
+    FMK_TRY(d2h(ctx, price_levels, fp->price_levels, nl));
+    FMK_TRY(d2h(ctx, buy_volumes, fp->buy_vol, nl)); FMK_TRY(d2h(ctx, sell_volumes, fp->sell_vol, nl));
+    FMK_TRY(d2h(ctx, buy_ticks, fp->buy_ticks, nl)); FMK_TRY(d2h(ctx, sell_ticks, fp->sell_ticks, nl));
+    FMK_TRY(d2h(ctx, buy_imbalances, fp->buy_imb, nl)); FMK_TRY(d2h(ctx, sell_imbalances, fp->sell_imb, nl));
+    FMK_TRY(d2h(ctx, buy_imb_sum, fp->buy_imb_sum, nb)); FMK_TRY(d2h(ctx, sell_imb_sum, fp->sell_imb_sum, nb));
+    FMK_TRY(d2h(ctx, cot_price_level, fp->cot, nb)); FMK_TRY(d2h(ctx, imb_max_run_signed, fp->run_signed, nb));
+    FMK_TRY(d2h(ctx, vp_skew, fp->vp_skew, nb)); FMK_TRY(d2h(ctx, vp_gini, fp->vp_gini, nb));
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMK_OK;
+}

@@ -1,0 +1,139 @@
+/*
+ * fmk.h -- C ABI of libfmk.so: the B200-native tick -> bars -> features -> labels hot path.
+ *
+ * The reference (quantscious/finmlkit v0.1.11) is pure Python + Numba and has NO FFI; this header is the boundary a
+ * maintainer would bind with ctypes.  Every entry point cites the reference function it replaces
+ * (paths relative to the reference tree).  Conventions:
+ *   - plain C types only; host arrays are caller-allocated (NumPy), device memory lives behind opaque handles;
+ *   - every function returns an int status: 0 = ok, negative = fmk_status (fmk_last_error(ctx) gives the text, which
+ *     for argument errors is the reference's own ValueError message);
+ *   - a ctx is bound to one device and one stream and is single-threaded; distinct contexts are independent;
+ *   - there is no CPU fallback anywhere: without a CUDA device every compute entry point fails with FMK_ERR_CUDA.
+ */
+#ifndef FMK_H
+#define FMK_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    FMK_OK = 0,
+    FMK_ERR_CUDA = -1,        /* CUDA runtime error / no device */
+    FMK_ERR_ARG = -2,         /* invalid argument (message = the reference's ValueError text) */
+    FMK_ERR_ALLOC = -3,
+    FMK_ERR_CAPACITY = -4,    /* caller buffer too small */
+    FMK_ERR_LEVEL = -5,       /* "Something went wrong! Invalid price level index!" (bar/base.py:719) */
+    FMK_ERR_INTERNAL = -6
+} fmk_status;
+
+typedef struct fmk_ctx fmk_ctx;         /* device + stream + scratch */
+typedef struct fmk_trades fmk_trades;   /* device SoA: ts i64[n], price f64[n], amount f64[n], side i8[n] */
+typedef struct fmk_index fmk_index;     /* device bar-close arrays: close_ts i64[m], close_idx i64[m] (m = n_bars + 1) */
+typedef struct fmk_buf fmk_buf;         /* generic device array */
+typedef struct fmk_footprint fmk_footprint; /* device CSR footprint (bar/data_model.py:775 FootprintData) */
+
+/* ---- library / context ------------------------------------------------------------------------------------------ */
+const char *fmk_version(void);
+int fmk_device_count(void);
+int fmk_ctx_create(int device, fmk_ctx **out);
+void fmk_ctx_destroy(fmk_ctx *ctx);
+const char *fmk_last_error(fmk_ctx *ctx);
+int fmk_ctx_sync(fmk_ctx *ctx);
+/* CUDA-event timer on the ctx stream (the stream every kernel of this ctx is launched on). */
+int fmk_timer_start(fmk_ctx *ctx);
+int fmk_timer_stop(fmk_ctx *ctx, float *ms_out);
+/* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
+int64_t fmk_launch_count(fmk_ctx *ctx);
+/* Writes > L2-size bytes so the next timed step starts with a cold L2. */
+int fmk_flush_l2(fmk_ctx *ctx);
+/* pinned host memory for the end-to-end path */
+int fmk_host_alloc(void **out, int64_t bytes);
+void fmk_host_free(void *p);
+
+/* ---- trades: TradesData columns (bar/data_model.py:121-244) as device SoA --------------------------------------- */
+/* side may be NULL (directional/footprint calls then fail with FMK_ERR_ARG). amount is float64. */
+int fmk_trades_upload(fmk_ctx *ctx, const int64_t *ts, const double *price, const double *amount, const int8_t *side,
+                      int64_t n, fmk_trades **out);
+/* Device-side synthetic BTCUSDT-like stream (SURVEY 8d shape) for bench-size runs. */
+int fmk_trades_synth(fmk_ctx *ctx, int64_t n, uint64_t seed, fmk_trades **out);
+/* Re-fill an existing handle from host arrays (async H2D on the ctx stream; arrays should be pinned). */
+int fmk_trades_refill(fmk_ctx *ctx, fmk_trades *t, const int64_t *ts, const double *price, const double *amount,
+                      const int8_t *side, int64_t n);
+int fmk_trades_download(fmk_ctx *ctx, const fmk_trades *t, int64_t *ts, double *price, double *amount, int8_t *side);
+int64_t fmk_trades_size(const fmk_trades *t);
+void fmk_trades_free(fmk_ctx *ctx, fmk_trades *t);
+
+/* ---- generic device arrays -------------------------------------------------------------------------------------- */
+int fmk_buf_upload(fmk_ctx *ctx, const void *host, int64_t bytes, fmk_buf **out);
+int fmk_buf_alloc(fmk_ctx *ctx, int64_t bytes, fmk_buf **out);
+int fmk_buf_download(fmk_ctx *ctx, const fmk_buf *b, void *host, int64_t bytes);
+int64_t fmk_buf_bytes(const fmk_buf *b);
+void *fmk_buf_devptr(const fmk_buf *b);
+void fmk_buf_free(fmk_ctx *ctx, fmk_buf *b);
+
+/* ---- bar indexers (bar/logic.py) -> device index handle ----------------------------------------------------------
+ * close_idx follows the reference exactly: element 0 is the "open" marker (-1 possible for time bars). */
+int fmk_time_bar_index(fmk_ctx *ctx, const fmk_trades *t, double interval_seconds, fmk_index **out); /* logic.py:12-51 */
+int fmk_tick_bar_index(fmk_ctx *ctx, const fmk_trades *t, int64_t threshold, fmk_index **out);       /* logic.py:54-84 */
+int fmk_volume_bar_index(fmk_ctx *ctx, const fmk_trades *t, double threshold, fmk_index **out);      /* logic.py:87-115 */
+int fmk_dollar_bar_index(fmk_ctx *ctx, const fmk_trades *t, double threshold, fmk_index **out);      /* logic.py:118-149 */
+/* sigma: device f64[n] buffer; it is forward-filled in place like the reference (logic.py:181-189). */
+int fmk_cusum_bar_index(fmk_ctx *ctx, const fmk_trades *t, fmk_buf *sigma, double sigma_floor, double sigma_mult,
+                        fmk_index **out);                                                             /* logic.py:152-221 */
+/* wrap caller-provided close indices (comp_bar_* called directly, MockBarBuilder-style tests) */
+int fmk_index_from_host(fmk_ctx *ctx, const fmk_trades *t, const int64_t *close_idx, int64_t m, fmk_index **out);
+int64_t fmk_index_size(const fmk_index *ix);      /* m = n_bars + 1 */
+int fmk_index_download(fmk_ctx *ctx, const fmk_index *ix, int64_t *close_ts, int64_t *close_idx);
+void fmk_index_free(fmk_ctx *ctx, fmk_index *ix);
+/* diagnostics of the last dollar/volume index build: [0]=speculative tasks, [1]=serial repairs, [2]=passes */
+int fmk_index_stats(fmk_ctx *ctx, int64_t *stats3);
+
+/* ---- per-bar reductions (bar/base.py:303-850); outputs are host arrays of n_bars elements ----------------------- */
+/* comp_bar_ohlcv, base.py:306-407.  Any output pointer may be NULL to skip its D2H copy. */
+int fmk_bar_ohlcv(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, double *open, double *high, double *low,
+                  double *close, float *volume, double *vwap, int64_t *trades, double *median_trade_size);
+/* Device-resident variant: computes into ctx-owned device columns and returns nothing to the host (bench `value`). */
+int fmk_bar_ohlcv_device(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, int with_median);
+/* comp_bar_directional_features, base.py:409-546 (tuple order of the reference) */
+int fmk_bar_directional(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, int64_t *ticks_buy, int64_t *ticks_sell,
+                        float *volume_buy, float *volume_sell, float *dollars_buy, float *dollars_sell,
+                        float *mean_spread, float *max_spread, int64_t *cum_ticks_min, int64_t *cum_ticks_max,
+                        float *cum_volume_min, float *cum_volume_max, float *cum_dollars_min, float *cum_dollars_max);
+/* comp_bar_trade_size_features, base.py:549-612 */
+int fmk_bar_trade_size(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, const double *theta, int64_t n_theta,
+                       double theta_mult, float *mean_size_rel, float *size_95_rel, float *pct_block, float *size_gini);
+/* comp_bar_footprints + comp_footprint_features, base.py:615-850.  Two-phase: build on device, then download CSR. */
+int fmk_bar_footprints(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, double price_tick_size,
+                       const double *bar_lows, const double *bar_highs, double imbalance_factor, fmk_footprint **out);
+int64_t fmk_footprint_levels(const fmk_footprint *fp);   /* total number of (bar, level) rows */
+int fmk_footprint_download(fmk_ctx *ctx, const fmk_footprint *fp, int64_t *level_offsets, int32_t *price_levels,
+                           float *buy_volumes, float *sell_volumes, int32_t *buy_ticks, int32_t *sell_ticks,
+                           uint8_t *buy_imbalances, uint8_t *sell_imbalances, uint16_t *buy_imb_sum,
+                           uint16_t *sell_imb_sum, int32_t *cot_price_level, int16_t *imb_max_run_signed,
+                           double *vp_skew, double *vp_gini);
+void fmk_footprint_free(fmk_ctx *ctx, fmk_footprint *fp);
+
+/* ---- tick-level series (feature/core) --------------------------------------------------------------------------- */
+/* comp_lagged_returns, feature/core/utils.py:12-64: host in / host out */
+int fmk_lagged_returns(fmk_ctx *ctx, const int64_t *ts, const double *close, int64_t n, double window_sec, int is_log,
+                       double *out);
+/* ewmst, feature/core/volatility.py:139-219 */
+int fmk_ewmst(fmk_ctx *ctx, const int64_t *ts, const double *y, int64_t n, double half_life, double sigma_floor,
+              double *out);
+/* device-resident variants used by the fused sigma pipeline (ts/price taken from the trades handle) */
+int fmk_lagged_returns_dev(fmk_ctx *ctx, const fmk_trades *t, double window_sec, int is_log, fmk_buf **out);
+int fmk_ewmst_dev(fmk_ctx *ctx, const fmk_trades *t, const fmk_buf *y, double half_life, double sigma_floor,
+                  fmk_buf **out);
+
+/* ---- labels: triple_barrier, label/tbm.py:11-158 ------------------------------------------------------------------
+ * side may be NULL (side prediction). Skipped events get touch_idx = event_idx (the reference leaves it uninitialised). */
+int fmk_triple_barrier(fmk_ctx *ctx, const fmk_trades *t, const int64_t *event_idx, const double *targets,
+                       int64_t n_events, int64_t n_targets, double bottom_mult, double top_mult,
+                       double vertical_barrier_s, double min_close_time_s, const int8_t *side, int64_t n_side,
+                       double min_ret, int8_t *labels, int64_t *touch_idx, double *rets, double *max_rb_ratios);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
