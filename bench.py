@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark: ticks/s of the bar + feature build (BASELINE.json metric) on B200.
+
+Workload (BASELINE.json configs[1]): N synthetic BTCUSDT-like ticks per GPU -> dollar bars ($1M threshold, bit-exact
+boundaries) + OHLCV/VWAP/trade count/median trade size, float64.  One "step" = one full pass of that path over one
+stream: fmk_dollar_bar_index + fmk_bar_ohlcv_device on device-resident SoA columns (`value`), and the same through the
+host-buffer C ABI with H2D/D2H inside the timed region (`e2e`).  N>1: one independent symbol stream per GPU (weak
+scaling, no data-path collective inside a symbol) plus one NCCL gather of the finished bar frames to rank 0 per step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--ticks T] [--impl ours|reference]
+
+Prints ONE JSON line.  `--impl reference` times the CPU restatement of the reference (oracle/, OpenMP where the
+reference uses prange) on the host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+THRESHOLD = 1e6
+METRIC = "ticks/sec bar+feature build"
+UNIT = "ticks/s"
+# algorithmic HBM bytes per tick of each streaming kernel
+ALGO_BYTES_PER_TICK = {"k_dollar_tasks": 16, "k_dollar_chunk_sums": 16, "k_bar_ohlcv_warp": 16, "k_bar_ohlcv_thread": 16,
+                       "k_bar_order_stats": 8, "k_dollar_fused": 16}
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full summary, if one exists for this workload."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t.get(kernel)
+    except Exception:
+        return None
+
+
+def run_reference(args):
+    """CPU arm: oracle port of the reference (dollar indexer serial like the reference; comp_bar_ohlcv over all cores)."""
+    import oracle
+    from finmlkit_b200.synth import synth_trades
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    sample = int(min(args.ticks, args.cpu_sample))
+    ts, px, qty, side = synth_trades(sample, seed=42)
+    cores = oracle.num_threads()
+
+    def step():
+        idx = oracle.dollar_bar_indexer(px, qty, THRESHOLD)
+        oracle.comp_bar_ohlcv(px, qty, idx)
+        return len(idx) - 1
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        nb = step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = sample / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"dollar bars $1e6 + OHLCV (incl. median), {sample} synthetic ticks per step (bounded sample of the "
+                                   f"{args.ticks}-tick workload), CPU port of the reference's Numba path", "bars": nb},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"first {sample} ticks; _dollar_bar_indexer serial + comp_bar_ohlcv on {cores} OpenMP threads"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--ticks", type=float, default=1e9, help="ticks per GPU (one symbol stream per GPU)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=float, default=1e8, help="ticks of the CPU baseline sample")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.ticks = int(args.ticks)
+    args.cpu_sample = int(args.cpu_sample)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    from finmlkit_b200 import core
+    dist = torch = None
+    stream = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        tstream = torch.cuda.Stream()
+        torch.cuda.set_stream(tstream)
+        stream = tstream.cuda_stream
+    ctx = core.Context(local, stream=stream)
+    n = args.ticks
+    tr = core.DeviceTrades.synth(n, seed=42 + rank, ctx=ctx)   # one independent symbol per rank
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    gather_bytes = [0]
+
+    def gather_frames():
+        """One NCCL gather of the finished bar frame (all OHLCV columns) to rank 0."""
+        ptr, nb, nbytes = ctx.result_cols()
+
+        class _Arr:   # zero-copy view of the library-owned device columns
+            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+        frame = torch.as_tensor(_Arr(), device=f"cuda:{local}")
+        sizes = torch.zeros(world, dtype=torch.int64, device=frame.device)
+        mine = torch.tensor([nbytes], dtype=torch.int64, device=frame.device)
+        dist.all_gather_into_tensor(sizes, mine)
+        mx = int(sizes.max().item())
+        padded = torch.zeros(mx, dtype=torch.uint8, device=frame.device)
+        padded[:nbytes] = frame
+        out = [torch.empty(mx, dtype=torch.uint8, device=frame.device) for _ in range(world)] if rank == 0 else None
+        dist.gather(padded, out, dst=0)
+        gather_bytes[0] = mx * world
+
+    nbars = [0]
+
+    def step():
+        ix = core.dollar_bar_index(tr, THRESHOLD)
+        ctx.check(ctx._L.fmk_bar_ohlcv_device(ctx.h, tr.h, ix.h, 1))
+        nbars[0] = ix.m - 1
+        if dist is not None:
+            gather_frames()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = ctx.launch_count()
+    ctx.prof_enable(True)
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = ctx.timer_stop()
+    barrier()
+    ctx.prof_enable(False)
+    prof = ctx.prof_report()
+    launches = ctx.launch_count() - l0
+    clk = clocks.stop()
+    stats = ctx.index_stats()
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (CUDA events around every launch of the timed region) ----------------------
+    peak, peak_src = measured_peak()
+    roofline = None
+    if prof:
+        dom = max(prof.items(), key=lambda kv: kv[1][1])
+        name, (cnt, tot_ms) = dom
+        per_launch_ms = tot_ms / cnt
+        algo = ALGO_BYTES_PER_TICK.get(name)
+        if algo:
+            achieved = algo * n / (per_launch_ms * 1e-3) / 1e9
+            traffic = ncu_traffic(name)
+            roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": traffic, "algorithmic_bytes_per_launch": algo * n, "launch_ms": per_launch_ms,
+                        "share_of_step": tot_ms / ms if dist is None else None, "peak_source": peak_src,
+                        "all_kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
+
+    # ---- end to end through the host-buffer C ABI --------------------------------------------------------------------
+    e2e = None
+    cpu_baseline = None
+    if not args.no_e2e:
+        import ctypes as C
+        L = ctx._L
+        n_e = n
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+            while 24 * n_e > 0.6 * avail / max(world, 1) and n_e > 1_000_000:
+                n_e //= 2
+        except Exception:
+            pass
+        hp = []
+        for _ in range(3):
+            p = C.c_void_p()
+            if L.fmk_host_alloc(C.byref(p), 8 * n_e) != 0:
+                raise RuntimeError("pinned allocation failed")
+            hp.append(p)
+        h_ts = np.ctypeslib.as_array(C.cast(hp[0], C.POINTER(C.c_int64)), shape=(n_e,))
+        h_px = np.ctypeslib.as_array(C.cast(hp[1], C.POINTER(C.c_double)), shape=(n_e,))
+        h_qty = np.ctypeslib.as_array(C.cast(hp[2], C.POINTER(C.c_double)), shape=(n_e,))
+        if n_e == n:
+            tr.download(out=(h_ts, h_px, h_qty, None))
+            tr_e = tr
+        else:
+            tr_e = core.DeviceTrades.synth(n_e, seed=42 + rank, ctx=ctx)
+            tr_e.download(out=(h_ts, h_px, h_qty, None))
+        d2h = [0]
+
+        def e2e_step():
+            tr_e.refill(h_ts, h_px, h_qty, None)                    # H2D of the step's inputs (pinned)
+            ix = core.dollar_bar_index(tr_e, THRESHOLD)
+            cts, cidx = ix.download()                                 # D2H close timestamps / indices
+            cols = core.bar_ohlcv(tr_e, ix)                           # D2H of the 8 OHLCV columns
+            d2h[0] = cts.nbytes + cidx.nbytes + sum(c.nbytes for c in cols)
+            return cols
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        ctx.sync()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * n_e / dt, "unit": UNIT, "h2d_bytes_per_step": 24 * n_e, "d2h_bytes_per_step": int(d2h[0]),
+               "ticks_per_step_per_gpu": n_e, "ms_per_step": dt * 1e3,
+               "api": "fmk_trades_refill + fmk_dollar_bar_index + fmk_index_download + fmk_bar_ohlcv (host buffers)"}
+
+        # ---- CPU baseline beside it (rank 0, N=1 only): oracle port on a bounded sample of the same arrays ----------
+        if world == 1 and rank == 0:
+            import oracle
+            s = int(min(n_e, args.cpu_sample))
+            px, qty = np.array(h_px[:s]), np.array(h_qty[:s])
+            oracle.comp_bar_ohlcv(px[:1000], qty[:1000], np.array([0, 999], np.int64))
+            best = 1e30
+            for _ in range(2):
+                t0 = time.perf_counter()
+                idx = oracle.dollar_bar_indexer(px, qty, THRESHOLD)
+                oracle.comp_bar_ohlcv(px, qty, idx)
+                best = min(best, time.perf_counter() - t0)
+            cpu_baseline = {"value": s / best, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+                            "sample": f"first {s} ticks of the same stream; dollar indexer serial (as in the reference) + "
+                                      f"comp_bar_ohlcv on {oracle.num_threads()} OpenMP threads, best of 2"}
+        for p in hp:
+            L.fmk_host_free(p)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"BASELINE configs[1]: {n} synthetic ticks per GPU -> dollar bars ($1e6, bit-exact boundaries) "
+                                       "+ OHLCV/VWAP/trades/median, fp64; one symbol stream per GPU"
+                                       + (", NCCL gather of bar frames to rank 0 each step" if world > 1 else ""),
+                           "ticks_per_gpu": n, "bars_per_gpu": nbars[0], "threshold": THRESHOLD,
+                           "l2": "inputs (16-24 GB/step) exceed the 126 MB L2; no flush needed" if n * 16 > 4e8 else "inputs fit L2: timing is warm-L2",
+                           "parallelism": f"symbols x{world}", "index_stats": stats,
+                           "gather_bytes_per_step": gather_bytes[0]},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

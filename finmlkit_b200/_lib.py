@@ -18,7 +18,11 @@ SIGNATURES = {
     "fmk_version": (C.c_char_p, []),
     "fmk_device_count": (INT, []),
     "fmk_ctx_create": (INT, [INT, C.POINTER(P)]),
+    "fmk_ctx_create_on_stream": (INT, [INT, P, C.POINTER(P)]),
     "fmk_ctx_destroy": (None, [P]),
+    "fmk_prof_enable": (INT, [P, INT]),
+    "fmk_prof_report": (INT, [P, P, P, P, INT]),
+    "fmk_result_cols": (INT, [P, C.POINTER(P), C.POINTER(I64), C.POINTER(I64)]),
     "fmk_last_error": (C.c_char_p, [P]),
     "fmk_ctx_sync": (INT, [P]),
     "fmk_timer_start": (INT, [P]),

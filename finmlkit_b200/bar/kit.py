@@ -1,0 +1,81 @@
+"""Bar kits with the reference's constructors (finmlkit/bar/kit.py:12-181); indices are computed on the device."""
+from typing import Tuple
+
+import numpy as np
+import pandas as pd
+
+from .. import core
+from .base import BarBuilderBase
+
+
+class TimeBarKit(BarBuilderBase):
+    """kit.py:12-35."""
+
+    def __init__(self, trades, period: pd.Timedelta, ctx=None):
+        super().__init__(trades, ctx)
+        self.interval = period.total_seconds()
+
+    def _comp_bar_close(self) -> Tuple[np.ndarray, np.ndarray]:
+        self._dev_index = core.time_bar_index(self._device(), self.interval)
+        return self._dev_index.download()
+
+
+class TickBarKit(BarBuilderBase):
+    """kit.py:38-69."""
+
+    def __init__(self, trades, tick_count_thrs: int, ctx=None):
+        super().__init__(trades, ctx)
+        self.tick_count_thrs = tick_count_thrs
+
+    def _comp_bar_close(self):
+        self._dev_index = core.tick_bar_index(self._device(), self.tick_count_thrs)
+        return self._dev_index.download()
+
+
+class VolumeBarKit(BarBuilderBase):
+    """kit.py:72-104."""
+
+    def __init__(self, trades, volume_ths: float, ctx=None):
+        super().__init__(trades, ctx)
+        self.volume_ths = volume_ths
+
+    def _comp_bar_close(self):
+        self._dev_index = core.volume_bar_index(self._device(), self.volume_ths)
+        return self._dev_index.download()
+
+
+class DollarBarKit(BarBuilderBase):
+    """kit.py:107-138."""
+
+    def __init__(self, trades, dollar_thrs: float, ctx=None):
+        super().__init__(trades, ctx)
+        self.dollar_thrs = dollar_thrs
+
+    def _comp_bar_close(self):
+        self._dev_index = core.dollar_bar_index(self._device(), self.dollar_thrs)
+        return self._dev_index.download()
+
+
+class CUSUMBarKit(BarBuilderBase):
+    """kit.py:141-181.  Like the reference, NaNs of ``sigma`` are forward-filled in place by the indexer."""
+
+    def __init__(self, trades, sigma, sigma_floor: float = 5e-4, sigma_mult: float = 2., ctx=None):
+        super().__init__(trades, ctx)
+        self.lambda_mult = sigma_mult
+        self._sigma = sigma
+        self.sigma_floor = sigma_floor
+
+    def _comp_bar_close(self):
+        if not (len(self.trades_df) == len(self._sigma)):
+            raise ValueError("Prices, timestamps, and sigma arrays must have the same length.")
+        dev = self._device()
+        sg = core.DeviceBuf.upload(dev.ctx, np.ascontiguousarray(self._sigma, dtype=np.float64))
+        self._dev_index = core.cusum_bar_index(dev, sg, self.sigma_floor, self.lambda_mult)
+        if isinstance(self._sigma, np.ndarray) and self._sigma.dtype == np.float64 and self._sigma.flags.writeable:
+            self._sigma[...] = sg.download(np.float64, len(self._sigma))
+        else:
+            self._sigma = sg.download(np.float64, len(self._sigma))
+        return self._dev_index.download()
+
+    def get_sigma(self):
+        return self._sigma[self.bar_close_indices]

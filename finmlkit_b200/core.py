@@ -29,12 +29,15 @@ def _c(a, dt):
 class Context:
     """One CUDA device + stream (fmk_ctx). Single-threaded; create one per device."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, stream: int = None):
         self._L = lib()
         if self._L.fmk_device_count() <= 0:
             raise FmkError("no CUDA device: finmlkit_b200 has no CPU fallback")
         h = C.c_void_p()
-        rc = self._L.fmk_ctx_create(int(device), C.byref(h))
+        if stream is None:
+            rc = self._L.fmk_ctx_create(int(device), C.byref(h))
+        else:
+            rc = self._L.fmk_ctx_create_on_stream(int(device), C.c_void_p(stream), C.byref(h))
         if rc != 0:
             raise FmkError(f"fmk_ctx_create(device={device}) failed: {_ERRORS.get(rc, rc)}")
         self.h = h
@@ -62,6 +65,26 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._L.fmk_launch_count(self.h))
+
+    def prof_enable(self, on=True):
+        self._L.fmk_prof_enable(self.h, int(on))
+
+    def prof_report(self, cap=64):
+        """{kernel name: (launches, total ms)} of everything launched since the last report while profiling was on."""
+        names = C.create_string_buffer(64 * cap)
+        counts = np.zeros(cap, np.int64)
+        ms = np.zeros(cap, np.float32)
+        nk = self._L.fmk_prof_report(self.h, names, _ptr(counts), _ptr(ms), cap)
+        out = {}
+        for k in range(nk):
+            nm = names.raw[64 * k:64 * (k + 1)].split(b"\0", 1)[0].decode()
+            out[nm] = (int(counts[k]), float(ms[k]))
+        return out
+
+    def result_cols(self):
+        p, nb, nbytes = C.c_void_p(), C.c_int64(), C.c_int64()
+        self._L.fmk_result_cols(self.h, C.byref(p), C.byref(nb), C.byref(nbytes))
+        return p.value, int(nb.value), int(nbytes.value)
 
     def flush_l2(self):
         self.check(self._L.fmk_flush_l2(self.h))

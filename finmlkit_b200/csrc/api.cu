@@ -14,7 +14,11 @@ int fmk_device_count(void) {
     return n;
 }
 
-int fmk_ctx_create(int device, fmk_ctx **out) {
+static int ctx_create(int device, void *ext_stream, int use_ext, fmk_ctx **out);
+int fmk_ctx_create(int device, fmk_ctx **out) { return ctx_create(device, nullptr, 0, out); }
+int fmk_ctx_create_on_stream(int device, void *stream, fmk_ctx **out) { return ctx_create(device, stream, 1, out); }
+
+static int ctx_create(int device, void *ext_stream, int use_ext, fmk_ctx **out) {
     *out = nullptr;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device >= n) return FMK_ERR_CUDA;
@@ -22,8 +26,14 @@ int fmk_ctx_create(int device, fmk_ctx **out) {
     if (!ctx) return FMK_ERR_ALLOC;
     memset(ctx, 0, sizeof(*ctx));
     ctx->device = device;
+    ctx->prof = new std::vector<fmk_prof_rec>();
+    ctx->ev_pool = new std::vector<cudaEvent_t>();
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return FMK_ERR_CUDA; }
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FMK_ERR_CUDA; }
+    if (use_ext) { ctx->stream = (cudaStream_t)ext_stream; ctx->owns_stream = 0; }
+    else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FMK_ERR_CUDA; }
+        ctx->owns_stream = 1;
+    }
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -45,7 +55,11 @@ void fmk_ctx_destroy(fmk_ctx *ctx) {
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
-    cudaStreamDestroy(ctx->stream);
+    for (auto &r : *ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto &e : *ctx->ev_pool) cudaEventDestroy(e);
+    delete ctx->prof;
+    delete ctx->ev_pool;
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -69,6 +83,44 @@ int fmk_timer_stop(fmk_ctx *ctx, float *ms_out) {
 }
 
 int64_t fmk_launch_count(fmk_ctx *ctx) { return ctx->launches; }
+
+int fmk_prof_enable(fmk_ctx *ctx, int on) {
+    ctx->prof_on = on;
+    return FMK_OK;
+}
+
+// Drains the recorded launches: writes up to cap rows of (name, launches, total ms); returns the number of distinct
+// kernels.  names_out receives cap * 64 bytes of NUL-terminated names.
+int fmk_prof_report(fmk_ctx *ctx, char *names_out, int64_t *counts_out, float *ms_out, int cap) {
+    cudaStreamSynchronize(ctx->stream);
+    int nk = 0;
+    for (auto &r : *ctx->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        int k = 0;
+        for (; k < nk; k++) if (strncmp(names_out + 64 * k, r.name, 63) == 0) break;
+        if (k == nk) {
+            if (nk >= cap) { ctx->ev_pool->push_back(r.a); ctx->ev_pool->push_back(r.b); continue; }
+            strncpy(names_out + 64 * k, r.name, 63);
+            names_out[64 * k + 63] = 0;
+            counts_out[k] = 0; ms_out[k] = 0.f;
+            nk++;
+        }
+        counts_out[k]++;
+        ms_out[k] += ms;
+        ctx->ev_pool->push_back(r.a);
+        ctx->ev_pool->push_back(r.b);
+    }
+    ctx->prof->clear();
+    return nk;
+}
+
+// device pointer / bar count of the columns written by fmk_bar_ohlcv_device (layout: 6 x f64[nb] open, high, low,
+// close, vwap, median ; i64[nb] trades ; f32[nb] volume)
+int fmk_result_cols(fmk_ctx *ctx, void **ptr, int64_t *n_bars, int64_t *bytes) {
+    *ptr = ctx->res_cols; *n_bars = ctx->res_nb; *bytes = ctx->res_nb * (6 * 8 + 8 + 4);
+    return FMK_OK;
+}
 
 int fmk_index_stats(fmk_ctx *ctx, int64_t *s) {
     s[0] = ctx->stats[0]; s[1] = ctx->stats[1]; s[2] = ctx->stats[2];

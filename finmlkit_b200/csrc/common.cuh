@@ -5,7 +5,10 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <vector>
 #include "../../include/fmk.h"
+
+struct fmk_prof_rec { const char *name; cudaEvent_t a, b; };
 
 struct fmk_ctx {
     int device;
@@ -20,7 +23,19 @@ struct fmk_ctx {
     void *flush_buf;
     int64_t flush_bytes;
     int64_t stats[3];
+    int owns_stream;
+    int prof_on;                          // per-kernel CUDA-event timing (bench.py roofline leg)
+    std::vector<fmk_prof_rec> *prof;
+    std::vector<cudaEvent_t> *ev_pool;
+    int64_t res_nb;                       // number of bars held in res_cols
 };
+
+static inline cudaEvent_t fmk_prof_event(fmk_ctx *ctx) {
+    cudaEvent_t e;
+    if (!ctx->ev_pool->empty()) { e = ctx->ev_pool->back(); ctx->ev_pool->pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
 
 struct fmk_trades {
     int64_t n;
@@ -83,7 +98,16 @@ static inline int fmk_fail(fmk_ctx *ctx, int code, const char *msg) {
 // Launch on the ctx stream, count it, and surface launch-configuration errors immediately.
 #define FMK_LAUNCH(ctx, kernel, grid, block, smem, ...)                                  \
     do {                                                                                 \
+        fmk_prof_rec pr__ = {#kernel, nullptr, nullptr};                                 \
+        if ((ctx)->prof_on) {                                                            \
+            pr__.a = fmk_prof_event(ctx); pr__.b = fmk_prof_event(ctx);                  \
+            cudaEventRecord(pr__.a, (ctx)->stream);                                      \
+        }                                                                                \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                 \
+        if ((ctx)->prof_on) {                                                            \
+            cudaEventRecord(pr__.b, (ctx)->stream);                                      \
+            (ctx)->prof->push_back(pr__);                                                \
+        }                                                                                \
         (ctx)->launches++;                                                               \
         FMK_CUDA((ctx), cudaGetLastError());                                             \
     } while (0)

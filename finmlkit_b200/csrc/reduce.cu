@@ -309,6 +309,7 @@ extern "C" int fmk_bar_ohlcv_device(fmk_ctx *ctx, const fmk_trades *t, const fmk
         FMK_CUDA(ctx, cudaMalloc(&ctx->res_cols, (size_t)need));
         ctx->res_cols_bytes = need;
     }
+    ctx->res_nb = nb;
     double *d = (double *)ctx->res_cols;
     int64_t *l = (int64_t *)(d + 6 * nb);
     float *f = (float *)(l + nb);

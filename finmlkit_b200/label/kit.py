@@ -1,0 +1,99 @@
+"""``TBMLabel`` with the reference's constructor, properties and outputs (label/kit.py:12-322)."""
+import numpy as np
+import pandas as pd
+
+from .tbm import triple_barrier
+
+
+class TBMLabel:
+    def __init__(self, features: pd.DataFrame, target_ret_col: str, min_ret: float, horizontal_barriers: tuple,
+                 vertical_barrier: pd.Timedelta, min_close_time: pd.Timedelta = pd.Timedelta(seconds=1), is_meta: bool = False):
+        if target_ret_col not in features.columns:
+            raise ValueError(f"Target column '{target_ret_col}' not found in features DataFrame.")
+        if not isinstance(features.index, pd.DatetimeIndex):
+            raise ValueError("Features index must be a DatetimeIndex.")
+        if not isinstance(horizontal_barriers, tuple) or len(horizontal_barriers) != 2:
+            raise ValueError("Horizontal barriers must be a tuple of two floats (bottom, top).")
+        if min_ret < 0.:
+            raise ValueError("Minimum return must be non-negative.")
+        if is_meta:
+            if 'side' not in features.columns:
+                raise ValueError("For meta labeling, 'side' column must be present in features DataFrame.")
+            if not pd.api.types.is_integer_dtype(features['side']):
+                raise ValueError("The 'side' column must be of integer type (e.g., -1, 0, 1).")
+        self._orig_features = self._preprocess_features(features, target_ret_col, min_ret, horizontal_barriers)
+        self._features = self._orig_features
+        self.target_ret_col = target_ret_col
+        self.min_ret = min_ret
+        self.horizontal_barriers = horizontal_barriers
+        self.vertical_barrier = vertical_barrier.total_seconds()
+        self.min_close_time_sec = min_close_time.total_seconds()
+        self.is_meta = is_meta
+        self._out = None
+
+    @staticmethod
+    def _preprocess_features(x, target_ret_col, min_ret, horizontal_barriers):
+        first_valid = [x[c].first_valid_index() for c in x.columns if x[c].first_valid_index() is not None]
+        if not first_valid:
+            raise ValueError("All columns contain only NaN values.")
+        x = x.loc[max(first_valid):]
+        x = x[x[target_ret_col].abs() * np.max(horizontal_barriers) >= min_ret]
+        if x.empty:
+            raise ValueError("No valid events found after filtering by minimum return and removing leading NaNs.")
+        if x[target_ret_col].isna().any():
+            raise ValueError(f"Target return column '{target_ret_col}' contains NaN values. Please ensure it is fully populated.")
+        return x
+
+    @property
+    def event_count(self):
+        return len(self._features)
+
+    @property
+    def features(self):
+        return self._features
+
+    @property
+    def target_returns(self):
+        return self._features[self.target_ret_col]
+
+    @property
+    def labels(self):
+        if self._out is None:
+            raise ValueError("Labels have not been computed yet. Call `compute_labels()` first.")
+        return self._out['labels']
+
+    @property
+    def event_returns(self):
+        if self._out is None or 'returns' not in self._out.columns:
+            raise ValueError("Log returns have not been computed yet. Call `compute_labels()` first.")
+        return self._out['returns']
+
+    @property
+    def full_output(self):
+        if self._out is None:
+            raise ValueError("Labels have not been computed yet. Call `compute_labels()` and `compute_weights` first.")
+        return self._out
+
+    def _drop_trailing_events(self, trades):
+        last = pd.Timestamp(trades.data.timestamp.values[-1], unit='ns')
+        return self._orig_features[self._orig_features.index + pd.Timedelta(self.vertical_barrier, unit="s") <= last]
+
+    def compute_labels(self, trades):
+        """label/kit.py:272-313 -> (features, out) with columns touch_time, event_idx, touch_idx, labels, returns,
+        vertical_touch_weights."""
+        if not hasattr(trades, "data"):
+            raise ValueError("Trades must be an instance of TradesData.")
+        self._features = self._drop_trailing_events(trades)
+        ts = trades.data.timestamp.values.astype(np.int64)
+        if "event_idx" in self._features.columns:
+            event_idx = self._features.event_idx.values
+        else:
+            event_idx = np.searchsorted(ts, self._features.index.as_unit("ns").asi8)
+        labels, touch_idx, rets, ratios = triple_barrier(
+            timestamps=ts, close=trades.data.price.values, event_idxs=event_idx, targets=self.target_returns.values,
+            horizontal_barriers=self.horizontal_barriers, vertical_barrier=self.vertical_barrier,
+            min_close_time_sec=self.min_close_time_sec,
+            side=self.features['side'].values.astype(np.int8) if self.is_meta else None, min_ret=self.min_ret)
+        self._out = pd.DataFrame({'touch_time': pd.to_datetime(ts[touch_idx]), 'event_idx': event_idx, 'touch_idx': touch_idx,
+                                  'labels': labels, 'returns': rets, 'vertical_touch_weights': ratios}, index=self.features.index)
+        return self.features, self.full_output

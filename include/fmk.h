@@ -37,6 +37,9 @@ typedef struct fmk_footprint fmk_footprint; /* device CSR footprint (bar/data_mo
 const char *fmk_version(void);
 int fmk_device_count(void);
 int fmk_ctx_create(int device, fmk_ctx **out);
+/* Same, but every kernel is launched on the caller's CUDA stream (cudaStream_t passed as void*), so a host that
+ * already owns a stream (e.g. the one NCCL collectives are enqueued on) gets one ordered timeline. */
+int fmk_ctx_create_on_stream(int device, void *stream, fmk_ctx **out);
 void fmk_ctx_destroy(fmk_ctx *ctx);
 const char *fmk_last_error(fmk_ctx *ctx);
 int fmk_ctx_sync(fmk_ctx *ctx);
@@ -45,6 +48,11 @@ int fmk_timer_start(fmk_ctx *ctx);
 int fmk_timer_stop(fmk_ctx *ctx, float *ms_out);
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 int64_t fmk_launch_count(fmk_ctx *ctx);
+/* per-kernel CUDA-event timing: enable, run, then drain (names_out: cap*64 bytes; returns number of distinct kernels) */
+int fmk_prof_enable(fmk_ctx *ctx, int on);
+int fmk_prof_report(fmk_ctx *ctx, char *names_out, int64_t *counts_out, float *ms_out, int cap);
+/* device columns of the last fmk_bar_ohlcv_device call (for a host that gathers bar frames over NCCL) */
+int fmk_result_cols(fmk_ctx *ctx, void **ptr, int64_t *n_bars, int64_t *bytes);
 /* Writes > L2-size bytes so the next timed step starts with a cold L2. */
 int fmk_flush_l2(fmk_ctx *ctx);
 /* pinned host memory for the end-to-end path */
