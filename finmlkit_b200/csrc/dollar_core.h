@@ -120,41 +120,61 @@ struct DollarTaskRec {
 
 struct DollarParams {
     double T, u, top_lim, sub_lim;  // u = ulp(T); top_lim = 4*2^e; sub_lim = 2*2^e
+    double margin0;                 // 2^(e-35): distance guaranteed by the coarse per-tick tests
+    uint32_t hi_tiny, hi_near, hi_top, hi_sub;   // high words of 2^(e-24), 2^(e-34), top_lim, sub_lim
     int64_t n, CH, cap;
 };
 
+DC_HD uint32_t dc_hi(double x) { return (uint32_t)(dc_bits(x) >> 32); }
+
 DC_HD bool dollar_params_init(DollarParams *P, double T, int64_t n, int64_t CH, int64_t cap) {
     P->T = T; P->n = n; P->CH = CH; P->cap = cap;
-    if (!(T > 0) || !(T < 1e300) || T < 1e-290) return false;
+    if (!(T > 1e-250) || !(T < 1e250)) return false;
     uint64_t b = dc_bits(T);
     double pow2 = dc_from_bits(b & 0xFFF0000000000000ull);  // 2^e
     P->u = pow2 * 2.220446049250313e-16;                    // 2^(e-52)
     P->top_lim = pow2 * 4.0;
     P->sub_lim = pow2 * 2.0;
+    P->margin0 = pow2 * 2.9103830456733704e-11;             // 2^-35
+    P->hi_tiny = dc_hi(pow2 * 5.9604644775390625e-08);      // 2^-24
+    P->hi_near = dc_hi(pow2 * 5.820766091346741e-11);       // 2^-34
+    P->hi_top = dc_hi(P->top_lim);
+    P->hi_sub = dc_hi(P->sub_lim);
     return true;
 }
 
 // One exact step of the reference recurrence for one chain, with margin tracking.
 // Returns true when the chain emits at this tick.
+//
+// Margin = smallest distance of any intermediate value to a decision threshold (T) or a binade boundary (a power of
+// two).  Computing it exactly every tick costs more than the recurrence itself, so the common path only runs cheap
+// integer tests on the high word of r = c + d and of r - T that PROVE the distance is >= margin0 = 2^(e-35):
+//   * r >= 2^(e-24) and the top 10 mantissa bits of r are neither all 0 nor all 1  =>  r is >= 2^(e-34) away from
+//     every power of two;
+//   * |r - T| >= 2^(e-34).
+// Only when a test fails (a few 1e-3 of the ticks) is the exact distance folded into the running minimum.
 DC_HD bool dollar_chain_tick(double &c, double d, const DollarParams &P, uint64_t &mbits, bool &bad) {
     const double r = dc_add(c, d);
-    const uint64_t rb = dc_bits(r);
-    const double lowb = dc_from_bits(rb & 0xFFF0000000000000ull);
-    const double dlo = dc_sub(r, lowb);
-    const double dhi = dc_sub(lowb, dlo);
-    const double am = fabs(dc_sub(r, P.T));
-    // positive doubles order like their bit patterns; negative/NaN values have the sign bit set -> never the minimum,
-    // they are caught by the explicit range test below
-    uint64_t m = mbits;
-    uint64_t x;
-    x = dc_bits(dlo); m = x < m ? x : m;
-    x = dc_bits(dhi); m = x < m ? x : m;
-    x = dc_bits(am);  m = x < m ? x : m;
-    mbits = m;
-    if (!(r >= 0.0) || !(r < P.top_lim)) bad = true;
+    const double c2 = dc_sub(r, P.T);
+    const uint32_t hr = dc_hi(r);
+    const uint32_t hc = dc_hi(c2) & 0x7FFFFFFFu;
+    const bool rare = (((hr + 0x400u) & 0xFF800u) == 0u) | (hr < P.hi_tiny) | (hr >= P.hi_top) | (hc < P.hi_near);
+    if (rare) {
+        const uint64_t rb = dc_bits(r);
+        const double lowb = dc_from_bits(rb & 0xFFF0000000000000ull);
+        const double dlo = dc_sub(r, lowb);
+        const double dhi = dc_sub(lowb, dlo);
+        const double am = fabs(c2);
+        // non-negative doubles order like their bit patterns; negative/NaN values are caught by the range test
+        uint64_t m = mbits, x;
+        x = dc_bits(dlo); m = x < m ? x : m;
+        x = dc_bits(dhi); m = x < m ? x : m;
+        x = dc_bits(am);  m = x < m ? x : m;
+        mbits = m;
+        if (!(r >= 0.0) || !(r < P.top_lim)) bad = true;
+    }
     if (r >= P.T) {
-        const double c2 = dc_sub(r, P.T);
-        if (!(c2 < P.sub_lim)) bad = true;
+        if (dc_hi(c2) >= P.hi_sub) bad = true;     // carry would leave the binades where it is a multiple of u
         c = c2;
         return true;
     }
@@ -162,85 +182,103 @@ DC_HD bool dollar_chain_tick(double &c, double d, const DollarParams &P, uint64_
     return false;
 }
 
-// Task k.  carry_in / K_in: guess for the state before tick k*CH (ignored for k == 0).
-// out: global index array (out[0] = 0 is written by the caller), cap = its capacity.
-template <typename LoadP, typename LoadV>
-DC_HD void dollar_task(LoadP p, LoadV v, const DollarParams &P, int64_t k, double carry_in, int64_t K_in,
-                       int64_t *out, DollarTaskRec *rec) {
-    const int64_t n = P.n;
-    const int64_t lo = k * P.CH;
-    int64_t hi = lo + P.CH;
-    if (hi > n) hi = n;
-    const bool last_chunk = (hi >= n);
-    rec->start_idx = -1; rec->k_start = 0; rec->end_idx = -2; rec->count = 0; rec->start_units = 0;
-    rec->bad = 0; rec->nch = DC_NCH;
-    for (int r = 0; r < DC_NCH; r++) { rec->end_units[r] = 0; rec->margin[r] = 0.0; }
-
+// Per-task state machine.  Ticks are fed in order with consume(); the same code runs on the host (CPU emulation in
+// tests/cpu) and in k_dollar_tasks, where the ticks come from a shared-memory staging tile.
+struct DollarTask {
     double c[DC_NCH];
     uint64_t mb[DC_NCH];
     bool bad[DC_NCH];
-    int64_t B, K;
-    int nch;
+    double x;            // phase 1: approximate carry
+    int64_t B, K, cnt, end_idx, hi, start_units;
+    int nch, phase;      // phase 1: locating the first boundary; 2: exact replay; 3: finished
+    bool last_chunk;
+};
+
+// first tick the task wants to see
+DC_HD int64_t dollar_task_init(DollarTask &t, const DollarParams &P, int64_t k, double carry_in, int64_t K_in, double d0) {
+    const int64_t lo = k * P.CH;
+    t.hi = lo + P.CH < P.n ? lo + P.CH : P.n;
+    t.last_chunk = t.hi >= P.n;
+    t.B = -1; t.K = K_in; t.cnt = 0; t.end_idx = -2; t.start_units = 0; t.x = carry_in;
+    for (int r = 0; r < DC_NCH; r++) { t.mb[r] = dc_bits(P.margin0); t.bad[r] = false; t.c[r] = 0.0; }
     if (k == 0) {
-        B = 0; K = 0;
-        c[0] = dc_mul(p(0), v(0));      // exact start: cum = prices[0] * volumes[0]
-        nch = 1;
-    } else {
-        // phase 1: locate the first boundary inside this chunk with the approximate carry
-        double x = carry_in;
-        B = -1;
-        for (int64_t i = lo; i < hi; i++) {
-            x = dc_add(x, dc_mul(p(i), v(i)));
-            if (x >= P.T) { x = dc_sub(x, P.T); B = i; break; }
-        }
-        if (B < 0) return;              // empty task
-        K = K_in + 1;
-        double units = rint(x / P.u);
-        if (!(units >= 0)) units = 0;
-        rec->start_units = (int64_t)units;
-        nch = DC_NCH;
-        for (int r = 0; r < DC_NCH; r++) c[r] = dc_mul((double)(rec->start_units + r), P.u);
+        t.B = 0; t.K = 0; t.nch = 1; t.phase = 2;
+        t.c[0] = d0;                 // exact start: cum = prices[0] * volumes[0]
+        return 1;
     }
-    for (int r = 0; r < DC_NCH; r++) { mb[r] = 0x7FF0000000000000ull; bad[r] = false; }
-    rec->start_idx = B;
-    rec->k_start = K;
-    if (nch == DC_NCH) {
-        for (int r = 0; r < DC_NCH; r++) {
-            // the start must be exactly representable (it is unless units ~ 2^53)
-            double chk = c[r] / P.u;
-            if (chk != (double)(rec->start_units + r)) bad[r] = true;
+    t.nch = DC_NCH; t.phase = 1;
+    return lo;
+}
+
+// Feed tick i (d = fl(p_i * v_i)).  Returns true when the task is finished.
+DC_HD bool dollar_task_consume(DollarTask &t, const DollarParams &P, int64_t i, double d, int64_t *out) {
+    if (t.phase == 1) {
+        t.x = dc_add(t.x, d);
+        if (t.x >= P.T) {
+            t.x = dc_sub(t.x, P.T);
+            t.B = i;
+            t.K += 1;
+            double units = rint(t.x / P.u);
+            if (!(units >= 0)) units = 0;
+            t.start_units = (int64_t)units;
+            for (int r = 0; r < DC_NCH; r++) {
+                t.c[r] = dc_mul((double)(t.start_units + r), P.u);
+                // the start must be exactly representable (it is unless units ~ 2^53)
+                if (t.c[r] / P.u != (double)(t.start_units + r)) t.bad[r] = true;
+            }
+            t.phase = 2;
+            return false;
         }
+        if (i + 1 >= t.hi) { t.phase = 3; return true; }   // no boundary located in this chunk: empty task
+        return false;
     }
-    // phase 2: exact replay
-    int64_t cnt = 0;
-    int64_t end_idx = -2;
-    for (int64_t i = B + 1; i < n; i++) {
-        const double d = dc_mul(p(i), v(i));
-        const bool e0 = dollar_chain_tick(c[0], d, P, mb[0], bad[0]);
-        for (int r = 1; r < nch; r++) {
-            const bool er = dollar_chain_tick(c[r], d, P, mb[r], bad[r]);
-            if (er != e0) bad[r] = true;
-        }
-        if (e0) {
-            cnt++;
-            if (K + cnt < P.cap) out[K + cnt] = i;   // speculative writes stay in bounds; cap bounds the true count
-            if (!last_chunk && i >= hi) { end_idx = i; break; }
+    const bool e0 = dollar_chain_tick(t.c[0], d, P, t.mb[0], t.bad[0]);
+    if (t.nch == DC_NCH) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int r = 1; r < DC_NCH; r++) {
+            const bool er = dollar_chain_tick(t.c[r], d, P, t.mb[r], t.bad[r]);
+            if (er != e0) t.bad[r] = true;
         }
     }
-    rec->count = cnt;
-    rec->end_idx = end_idx;
-    rec->nch = nch;
-    if (end_idx >= 0) {
-        for (int r = 0; r < nch; r++) {
-            double eu = c[r] / P.u;          // exact when c is a multiple of u below 2^(e+1)
-            rec->end_units[r] = (int64_t)eu;
-            if ((double)rec->end_units[r] != eu || dc_mul(eu, P.u) != c[r]) bad[r] = true;
-        }
+    if (e0) {
+        t.cnt++;
+        if (t.K + t.cnt < P.cap) out[t.K + t.cnt] = i;   // speculative writes stay in bounds; cap bounds the true count
+        if (!t.last_chunk && i >= t.hi) { t.end_idx = i; t.phase = 3; return true; }
     }
-    for (int r = 0; r < nch; r++) rec->margin[r] = dc_from_bits(mb[r]);
+    return false;
+}
+
+DC_HD void dollar_task_finish(const DollarTask &t, const DollarParams &P, DollarTaskRec *rec) {
+    rec->start_idx = t.B; rec->k_start = t.B >= 0 ? t.K : 0; rec->end_idx = t.end_idx; rec->count = t.cnt;
+    rec->start_units = t.start_units; rec->nch = t.nch;
     int32_t bm = 0;
-    for (int r = 0; r < nch; r++) if (bad[r]) bm |= (1 << r);
+    for (int r = 0; r < DC_NCH; r++) {
+        rec->end_units[r] = 0;
+        rec->margin[r] = dc_from_bits(t.mb[r]);
+        bool bad = t.bad[r];
+        if (t.end_idx >= 0 && r < t.nch) {
+            const double eu = t.c[r] / P.u;          // exact when c is a multiple of u below 2^(e+1)
+            rec->end_units[r] = (int64_t)eu;
+            if ((double)rec->end_units[r] != eu || dc_mul(eu, P.u) != t.c[r]) bad = true;
+        }
+        if (bad) bm |= (1 << r);
+    }
     rec->bad = bm;
+}
+
+// Host-style driver of the state machine (CPU emulation; the device kernel stages ticks through shared memory).
+template <typename LoadP, typename LoadV>
+DC_HD void dollar_task(LoadP p, LoadV v, const DollarParams &P, int64_t k, double carry_in, int64_t K_in,
+                       int64_t *out, DollarTaskRec *rec) {
+    DollarTask t;
+    int64_t i = dollar_task_init(t, P, k, carry_in, K_in, k == 0 ? dc_mul(p(0), v(0)) : 0.0);
+    if (!(k > 0 && i >= t.hi)) {
+        for (; i < P.n; i++)
+            if (dollar_task_consume(t, P, i, dc_mul(p(i), v(i)), out)) break;
+    }
+    dollar_task_finish(t, P, rec);
 }
 
 // ---- carry chain ---------------------------------------------------------------------------------------------

@@ -52,26 +52,49 @@ constexpr int DOLLAR_P_THREADS = 1024;
 __global__ void __launch_bounds__(DOLLAR_P_THREADS) k_dollar_prefix(const dd_t *__restrict__ sums, int64_t nt, double T,
                                                                     int64_t *__restrict__ K_in,
                                                                     double *__restrict__ carry, dd_t *total) {
-    __shared__ dd_t seg[DOLLAR_P_THREADS];
+    __shared__ dd_t wsum[DOLLAR_P_THREADS / 32];
     const int64_t per = (nt + DOLLAR_P_THREADS - 1) / DOLLAR_P_THREADS;
     const int64_t a = (int64_t)threadIdx.x * per;
     int64_t b = a + per;
     if (b > nt) b = nt;
     dd_t s = {0.0, 0.0};
     for (int64_t k = a; k < b; k++) s = dd_add(s, sums[k]);
-    seg[threadIdx.x] = s;
+    // block-wide exclusive scan of the per-thread sums (warp shuffles, then the 32 warp totals)
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    dd_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        dd_t y;
+        y.hi = __shfl_up_sync(0xffffffffu, inc.hi, o);
+        y.lo = __shfl_up_sync(0xffffffffu, inc.lo, o);
+        if (lane >= o) inc = dd_add(y, inc);
+    }
+    if (lane == 31) wsum[w] = inc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        dd_t run = {0.0, 0.0};
-        for (int t = 0; t < DOLLAR_P_THREADS; t++) {
-            dd_t x = seg[t];
-            seg[t] = run;
-            run = dd_add(run, x);
+    if (w == 0) {
+        dd_t x = wsum[lane];
+        dd_t xi = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            dd_t y;
+            y.hi = __shfl_up_sync(0xffffffffu, xi.hi, o);
+            y.lo = __shfl_up_sync(0xffffffffu, xi.lo, o);
+            if (lane >= o) xi = dd_add(y, xi);
         }
-        *total = run;
+        if (lane == 31) *total = xi;
+        // exclusive warp offsets
+        dd_t ex;
+        ex.hi = __shfl_up_sync(0xffffffffu, xi.hi, 1);
+        ex.lo = __shfl_up_sync(0xffffffffu, xi.lo, 1);
+        if (lane == 0) { ex.hi = 0.0; ex.lo = 0.0; }
+        wsum[lane] = ex;
     }
     __syncthreads();
-    dd_t run = seg[threadIdx.x];
+    dd_t ex;
+    ex.hi = __shfl_up_sync(0xffffffffu, inc.hi, 1);
+    ex.lo = __shfl_up_sync(0xffffffffu, inc.lo, 1);
+    if (lane == 0) { ex.hi = 0.0; ex.lo = 0.0; }
+    dd_t run = dd_add(wsum[w], ex);
     for (int64_t k = a; k < b; k++) {
         int64_t K;
         double c;
@@ -82,15 +105,58 @@ __global__ void __launch_bounds__(DOLLAR_P_THREADS) k_dollar_prefix(const dd_t *
     }
 }
 
-__global__ void __launch_bounds__(128) k_dollar_tasks(const double *__restrict__ p, const double *__restrict__ v,
-                                                      DollarParams P, int64_t nt, const int64_t *__restrict__ K_in,
-                                                      const double *__restrict__ carry, int64_t *__restrict__ out,
-                                                      DollarTaskRec *__restrict__ recs) {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nt) return;
-    DollarTaskRec rec;
-    dollar_task(LdG{p}, LdG{v}, P, k, k > 0 ? carry[k] : 0.0, k > 0 ? K_in[k] : 0, out, &rec);
-    recs[k] = rec;
+// One lane per task; a warp's 32 tasks stream their ticks through a shared-memory tile that the warp fills with
+// coalesced loads (row r = the next DT_R ticks of lane r's task), so HBM sees full 128-byte requests even though
+// every task walks its own contiguous range sequentially.
+constexpr int DT_WARPS = 4;
+constexpr int DT_R = 16;
+__global__ void __launch_bounds__(DT_WARPS * 32) k_dollar_tasks(const double *__restrict__ p, const double *__restrict__ v,
+                                                                DollarParams P, int64_t nt,
+                                                                const int64_t *__restrict__ K_in,
+                                                                const double *__restrict__ carry,
+                                                                int64_t *__restrict__ out,
+                                                                DollarTaskRec *__restrict__ recs) {
+    __shared__ double sp[DT_WARPS][32][DT_R + 1];
+    __shared__ double sv[DT_WARPS][32][DT_R + 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t k = ((int64_t)blockIdx.x * DT_WARPS + w) * 32 + lane;
+    const int64_t n = P.n;
+    DollarTask t;
+    int64_t pos = 0;
+    bool active = k < nt;
+    if (active) pos = dollar_task_init(t, P, k, k > 0 ? carry[k] : 0.0, k > 0 ? K_in[k] : 0, k == 0 ? __dmul_rn(p[0], v[0]) : 0.0);
+    else { t.B = -1; t.K = 0; t.cnt = 0; t.end_idx = -2; t.nch = DC_NCH; t.start_units = 0; }
+    const int half = lane >> 4, col = lane & 15;
+    while (__any_sync(0xffffffffu, active)) {
+#pragma unroll 4
+        for (int q = 0; q < 16; q++) {
+            const int row = 2 * q + half;
+            const int64_t rp = __shfl_sync(0xffffffffu, pos, row);
+            const int ra = __shfl_sync(0xffffffffu, (int)active, row);
+            const int64_t idx = rp + col;
+            double a = 0.0, b = 0.0;
+            if (ra && idx < n) { a = __ldg(p + idx); b = __ldg(v + idx); }
+            sp[w][row][col] = a;
+            sv[w][row][col] = b;
+        }
+        __syncwarp();
+        if (active) {
+#pragma unroll 1
+            for (int tt = 0; tt < DT_R; tt++) {
+                const int64_t i = pos + tt;
+                if (i >= n) { active = false; break; }
+                const double d = __dmul_rn(sp[w][lane][tt], sv[w][lane][tt]);
+                if (dollar_task_consume(t, P, i, d, out)) { active = false; break; }
+            }
+            pos += DT_R;
+        }
+        __syncwarp();
+    }
+    if (k < nt) {
+        DollarTaskRec rec;
+        dollar_task_finish(t, P, &rec);
+        recs[k] = rec;
+    }
 }
 
 // status block shared between chain / serial kernels and the host
@@ -101,104 +167,143 @@ struct DollarStatus {
     int64_t K_total;
     double c;           // serial start state as a double (used when the state is not a multiple of u)
     int64_t use_c;
-    int64_t n_certified;
+    unsigned long long ev_min;   // scratch: smallest task index that raised an event in the current chain pass
 };
 
-constexpr int DOLLAR_C_THREADS = 1024;
+// ---- carry chain as a 3-kernel scan over tasks [k0, nt) --------------------------------------------------------
+constexpr int DC_THREADS = 256;
+struct ChainElem { DollarXfer f; long long last; };
 
-// Chain over tasks [k0, nt) entering with state (s0,pos0,K0).  k0 == 0 additionally consumes task 0 (exact start).
-__global__ void __launch_bounds__(DOLLAR_C_THREADS) k_dollar_chain(const DollarTaskRec *__restrict__ recs, int64_t nt,
-                                                                   int64_t k0, int64_t s0, int64_t pos0, int64_t K0,
-                                                                   double u, const double *p, const double *v,
-                                                                   DollarStatus *st) {
-    __shared__ DollarXfer pre[DOLLAR_C_THREADS];
-    __shared__ long long lastne[DOLLAR_C_THREADS];
-    __shared__ unsigned long long ev_min;
-    __shared__ int64_t sh_s0, sh_pos0, sh_K0, sh_k0;
-    __shared__ int early;
-    if (threadIdx.x == 0) {
-        ev_min = ~0ull;
-        early = 0;
-        sh_s0 = s0; sh_pos0 = pos0; sh_K0 = K0; sh_k0 = k0;
-        st->n_certified = 0;
-        if (k0 == 0) {
-            const DollarTaskRec t0 = recs[0];
-            if (t0.end_idx == -2) {
-                st->event = 1; st->k_ev = 0; st->K_total = t0.count; early = 1;
-            } else if (t0.bad & 1) {
-                st->event = 2; st->k_ev = 0; st->s = 0; st->pos = 0; st->K = 0;
-                st->c = __dmul_rn(p[0], v[0]); st->use_c = 1; early = 1;
-            } else {
-                sh_s0 = t0.end_units[0]; sh_pos0 = t0.end_idx; sh_K0 = t0.count; sh_k0 = 1;
-            }
-        }
+__device__ __forceinline__ ChainElem chain_elem(const DollarTaskRec &t, int64_t k) {
+    ChainElem e;
+    e.f = dollar_xfer_identity();
+    e.last = -1;
+    if (t.start_idx >= 0) {
+        if (t.nch == DC_NCH && t.end_idx != -2) e.f = dollar_task_xfer(t);
+        e.last = k;
     }
+    return e;
+}
+// a then b
+__device__ __forceinline__ ChainElem chain_combine(const ChainElem &a, const ChainElem &b) {
+    ChainElem r;
+    r.f = dollar_xfer_compose(a.f, b.f);
+    r.last = b.last >= 0 ? b.last : a.last;
+    return r;
+}
+// block-wide inclusive scan (Hillis-Steele in shared memory); returns the inclusive value of this thread
+__device__ ChainElem chain_block_scan(ChainElem x, ChainElem *buf /* 2 * DC_THREADS */) {
+    int cur = 0;
+    buf[threadIdx.x] = x;
     __syncthreads();
-    if (early) return;
-    const int64_t kb = sh_k0;
-    if (kb >= nt) {
-        if (threadIdx.x == 0) { st->event = 0; st->k_ev = nt; st->s = sh_s0; st->pos = sh_pos0; st->K = sh_K0; st->use_c = 0; }
-        return;
+#pragma unroll 1
+    for (int o = 1; o < DC_THREADS; o <<= 1) {
+        ChainElem y = buf[cur * DC_THREADS + threadIdx.x];
+        if ((int)threadIdx.x >= o) y = chain_combine(buf[cur * DC_THREADS + threadIdx.x - o], y);
+        buf[(cur ^ 1) * DC_THREADS + threadIdx.x] = y;
+        cur ^= 1;
+        __syncthreads();
     }
-    const int64_t per = (nt - kb + DOLLAR_C_THREADS - 1) / DOLLAR_C_THREADS;
-    const int64_t a = kb + (int64_t)threadIdx.x * per;
-    int64_t b = a + per;
-    if (b > nt) b = nt;
-    // phase 1: segment composite under the assumption that every task is valid
-    DollarXfer f = dollar_xfer_identity();
-    long long last = -1;
-    for (int64_t k = a; k < b; k++) {
-        const DollarTaskRec &t = recs[k];
-        if (t.start_idx < 0) continue;
-        if (t.nch == DC_NCH && t.end_idx != -2) f = dollar_xfer_compose(f, dollar_task_xfer(t));
-        last = k;
-    }
-    pre[threadIdx.x] = f;
-    lastne[threadIdx.x] = last;
+    ChainElem r = buf[cur * DC_THREADS + threadIdx.x];
     __syncthreads();
-    // phase 2: exclusive scan over segments (serial over 1024 small elements)
-    if (threadIdx.x == 0) {
-        DollarXfer run = dollar_xfer_identity();
-        long long lr = -1;
-        for (int t = 0; t < DOLLAR_C_THREADS; t++) {
-            DollarXfer x = pre[t];
-            long long l = lastne[t];
-            pre[t] = run;
-            lastne[t] = lr;
-            run = dollar_xfer_compose(run, x);
-            if (l >= 0) lr = l;
-        }
-    }
+    return r;
+}
+
+__global__ void __launch_bounds__(DC_THREADS) k_dollar_chain_reduce(const DollarTaskRec *__restrict__ recs, int64_t nt,
+                                                                    int64_t k0, ChainElem *agg) {
+    __shared__ ChainElem buf[2 * DC_THREADS];
+    const int64_t k = k0 + (int64_t)blockIdx.x * DC_THREADS + threadIdx.x;
+    ChainElem e;
+    e.f = dollar_xfer_identity(); e.last = -1;
+    if (k < nt) e = chain_elem(recs[k], k);
+    ChainElem inc = chain_block_scan(e, buf);
+    if (threadIdx.x == DC_THREADS - 1) agg[blockIdx.x] = inc;
+}
+
+// single block: in-place exclusive scan of the per-block aggregates
+__global__ void __launch_bounds__(DC_THREADS) k_dollar_chain_top(ChainElem *agg, int64_t nblocks) {
+    __shared__ ChainElem buf[2 * DC_THREADS];
+    __shared__ ChainElem carry;
+    if (threadIdx.x == 0) { carry.f = dollar_xfer_identity(); carry.last = -1; }
     __syncthreads();
-    // phase 3: walk the segment with the true entering state
-    DollarWalk w;
-    w.fail_task = -1; w.done = 0; w.K_total = 0;
-    w.s = sh_s0 + pre[threadIdx.x].off[sh_s0 & 3];
-    if (lastne[threadIdx.x] >= 0) {
-        const DollarTaskRec &t = recs[lastne[threadIdx.x]];
-        w.pos = t.end_idx;
-        w.K = t.k_start + t.count;
-    } else {
-        w.pos = sh_pos0; w.K = sh_K0;
-    }
-    int64_t kf = -1, ncert = 0;
-    int rc = 0;
-    if (a < b) rc = dollar_walk_range(recs, a, b, u, w, &kf, &ncert, true);
-    if (rc != 0) atomicMin(&ev_min, (unsigned long long)kf);
-    __syncthreads();
-    const unsigned long long evk = ev_min;
-    if (evk == ~0ull) {
-        // no event anywhere: the thread whose segment reaches nt holds the final state
-        atomicAdd((unsigned long long *)&st->n_certified, (unsigned long long)ncert);
-        if (b == nt && a < b) {
-            st->event = 0; st->k_ev = nt; st->s = w.s; st->pos = w.pos; st->K = w.K; st->use_c = 0;
-        }
-        return;
-    }
-    if (rc != 0 && (unsigned long long)kf == evk) {
-        st->event = rc; st->k_ev = kf; st->s = w.s; st->pos = w.pos; st->K = w.K; st->K_total = w.K_total; st->use_c = 0;
+    for (int64_t b = 0; b < nblocks; b += DC_THREADS) {
+        const int64_t j = b + threadIdx.x;
+        ChainElem e;
+        e.f = dollar_xfer_identity(); e.last = -1;
+        if (j < nblocks) e = agg[j];
+        ChainElem inc = chain_block_scan(e, buf);
+        const ChainElem c = carry;
+        // exclusive = carry + (inclusive of previous thread)
+        buf[threadIdx.x] = inc;
+        __syncthreads();
+        ChainElem ex = c;
+        if (threadIdx.x > 0) ex = chain_combine(c, buf[threadIdx.x - 1]);
+        if (j < nblocks) agg[j] = ex;
+        __syncthreads();
+        if (threadIdx.x == DC_THREADS - 1) carry = chain_combine(c, inc);
+        __syncthreads();
     }
 }
+
+// mode 0: find the first task that raises an event (atomicMin into st->ev_min)
+// mode 1: the thread owning that task (or the last task when there is no event) writes the walk state
+__global__ void __launch_bounds__(DC_THREADS) k_dollar_chain_apply(const DollarTaskRec *__restrict__ recs, int64_t nt,
+                                                                   int64_t k0, int64_t s0, int64_t pos0, int64_t K0,
+                                                                   double u, const ChainElem *__restrict__ agg, int mode,
+                                                                   DollarStatus *st) {
+    __shared__ ChainElem buf[2 * DC_THREADS];
+    const int64_t k = k0 + (int64_t)blockIdx.x * DC_THREADS + threadIdx.x;
+    ChainElem e;
+    e.f = dollar_xfer_identity(); e.last = -1;
+    DollarTaskRec t;
+    t.start_idx = -1;
+    if (k < nt) { t = recs[k]; e = chain_elem(t, k); }
+    ChainElem inc = chain_block_scan(e, buf);
+    buf[threadIdx.x] = inc;
+    __syncthreads();
+    ChainElem ex = agg[blockIdx.x];
+    if (threadIdx.x > 0) ex = chain_combine(ex, buf[threadIdx.x - 1]);
+    if (k >= nt) return;
+    DollarWalk w;
+    w.fail_task = -1; w.done = 0; w.K_total = 0;
+    w.s = s0 + ex.f.off[s0 & 3];
+    if (ex.last >= 0) {
+        const DollarTaskRec &pt = recs[ex.last];
+        w.pos = pt.end_idx;
+        w.K = pt.k_start + pt.count;
+    } else { w.pos = pos0; w.K = K0; }
+    const DollarWalk w_in = w;
+    const int rc = dollar_walk_step(t, u, w, true);
+    const bool event = (rc == 1 || rc == 2 || rc == 4);
+    if (mode == 0) {
+        if (event) atomicMin(&st->ev_min, (unsigned long long)k);
+        return;
+    }
+    const unsigned long long evk = st->ev_min;
+    if (evk == ~0ull) {
+        if (k == nt - 1) {   // no event: range exhausted; state after the last task
+            st->event = 0; st->k_ev = nt; st->s = w.s; st->pos = w.pos; st->K = w.K; st->use_c = 0;
+        }
+    } else if ((unsigned long long)k == evk) {
+        st->event = rc; st->k_ev = k; st->s = w_in.s; st->pos = w_in.pos; st->K = w_in.K; st->K_total = w.K_total; st->use_c = 0;
+    }
+}
+
+// task 0 (exact start) is consumed on its own: it decides how the chain is entered
+__global__ void k_dollar_chain_task0(const DollarTaskRec *__restrict__ recs, const double *p, const double *v,
+                                     DollarStatus *st) {
+    const DollarTaskRec t0 = recs[0];
+    st->ev_min = ~0ull;
+    if (t0.end_idx == -2) { st->event = 1; st->k_ev = 0; st->K_total = t0.count; }
+    else if (t0.bad & 1) {
+        st->event = 2; st->k_ev = 0; st->s = 0; st->pos = 0; st->K = 0; st->c = __dmul_rn(p[0], v[0]); st->use_c = 1;
+    } else {
+        st->event = 7;   // proceed with the chain from task 1
+        st->k_ev = 1; st->s = t0.end_units[0]; st->pos = t0.end_idx; st->K = t0.count; st->use_c = 0;
+    }
+}
+
+__global__ void k_dollar_reset_ev(DollarStatus *st) { st->ev_min = ~0ull; }
 
 // single-thread exact repair from (pos, c, K); resync allowed at tasks >= kmin
 __global__ void k_dollar_serial(const double *__restrict__ p, const double *__restrict__ v, int64_t n, double T,
@@ -289,16 +394,37 @@ int fmk_dollar_index_impl(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index
         K_total = hs.K_total;
     }
     if (fast) {
-    FMK_LAUNCH(ctx, k_dollar_tasks, (unsigned)cdiv(nt, 128), 128, 0, t->price, t->amount, P, nt,
+    FMK_LAUNCH(ctx, k_dollar_tasks, (unsigned)cdiv(nt, DT_WARPS * 32), DT_WARPS * 32, 0, t->price, t->amount, P, nt,
                (const int64_t *)K_in.p, (const double *)carry.p, idx, recs.p);
-    int64_t k0 = 0, s0 = 0, pos0 = 0, K0 = 0;
-    for (int iter = 0;; iter++) {
-        ctx->stats[2]++;
-        FMK_LAUNCH(ctx, k_dollar_chain, 1, DOLLAR_C_THREADS, 0, (const DollarTaskRec *)recs.p, nt, k0, s0, pos0, K0, P.u,
-                   (const double *)t->price, (const double *)t->amount, st.p);
-        FMK_CUDA(ctx, cudaMemcpyAsync(&hs, st.p, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
-        FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (hs.event == 1) { K_total = hs.K_total; break; }
+    Scratch<ChainElem> agg(ctx);
+    FMK_TRY(agg.alloc(cdiv(nt, DC_THREADS) + 1));
+    // task 0 runs from the exact initial state and decides how the chain is entered
+    FMK_LAUNCH(ctx, k_dollar_chain_task0, 1, 1, 0, (const DollarTaskRec *)recs.p, (const double *)t->price,
+               (const double *)t->amount, st.p);
+    FMK_CUDA(ctx, cudaMemcpyAsync(&hs, st.p, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int64_t k0 = 1, s0 = hs.s, pos0 = hs.pos, K0 = hs.K;
+    bool need_chain = hs.event == 7;
+    if (hs.event == 1) K_total = hs.K_total;
+    while (K_total < 0) {
+        if (need_chain) {
+            ctx->stats[2]++;
+            if (k0 >= nt) {
+                hs.event = 0; hs.k_ev = nt; hs.s = s0; hs.pos = pos0; hs.K = K0; hs.use_c = 0;
+            } else {
+                const int64_t nblk = cdiv(nt - k0, DC_THREADS);
+                FMK_LAUNCH(ctx, k_dollar_reset_ev, 1, 1, 0, st.p);
+                FMK_LAUNCH(ctx, k_dollar_chain_reduce, (unsigned)nblk, DC_THREADS, 0, (const DollarTaskRec *)recs.p, nt, k0, agg.p);
+                FMK_LAUNCH(ctx, k_dollar_chain_top, 1, DC_THREADS, 0, agg.p, nblk);
+                FMK_LAUNCH(ctx, k_dollar_chain_apply, (unsigned)nblk, DC_THREADS, 0, (const DollarTaskRec *)recs.p, nt, k0, s0, pos0,
+                           K0, P.u, (const ChainElem *)agg.p, 0, st.p);
+                FMK_LAUNCH(ctx, k_dollar_chain_apply, (unsigned)nblk, DC_THREADS, 0, (const DollarTaskRec *)recs.p, nt, k0, s0, pos0,
+                           K0, P.u, (const ChainElem *)agg.p, 1, st.p);
+                FMK_CUDA(ctx, cudaMemcpyAsync(&hs, st.p, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+                FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            }
+            if (hs.event == 1) { K_total = hs.K_total; break; }
+        }
         // failure (2/4) or range exhausted (0): exact serial repair from the last certified state
         const int64_t kmin = hs.event == 4 ? hs.k_ev : (hs.event == 0 ? nt : hs.k_ev + 1);
         const double c = hs.use_c ? hs.c : (double)hs.s * P.u;
@@ -310,6 +436,7 @@ int fmk_dollar_index_impl(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index
         if (hs.event == -1) return fmk_fail(ctx, FMK_ERR_INTERNAL, "dollar index overflow");
         if (hs.event == 1) { K_total = hs.K_total; break; }
         k0 = hs.k_ev; s0 = hs.s; pos0 = hs.pos; K0 = hs.K;
+        need_chain = true;
         if (k0 <= 0) return fmk_fail(ctx, FMK_ERR_INTERNAL, "dollar chain resync at task 0");
     }
     }

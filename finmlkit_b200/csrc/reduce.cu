@@ -112,11 +112,17 @@ __global__ void __launch_bounds__(256) k_bar_ohlcv_thread(const double *__restri
 // ---------------------------------------------------------------------------------------------------------------
 // order statistics per bar: np.median (base.py:401-405) and np.percentile(., 95) (base.py:593) with Numba's
 // definitions (numba/np/arraymath.py _median_inner / _collect_percentiles_inner).
-// One block per bar (grid-stride).  Bars that fit in shared memory are bitonic-sorted there; longer bars use an
-// 8-pass MSB radix select over the bar's global-memory segment.
+//
+// One WARP per bar, adaptive MSB radix select on the order-preserving 64-bit key of each amount:
+//   diff pass  : OR/AND of the keys still in play -> first bit where they differ (common prefixes and all-equal
+//                groups -- heavy on exchange-quantised sizes -- cost one pass, not eight)
+//   hist pass  : 256-bin shared-memory histogram of the 8 bits below that bit, pick the bucket holding rank k
+//   gather     : once <= 32 candidates remain they are compacted into the lanes and ranked by counting
+// Every pass also tracks the smallest key ABOVE the selected range, which is the (k+1)-th order statistic when the
+// k-th is the largest candidate (median of an even count, percentile interpolation).  The bar's amounts are re-read
+// from L1/L2 on each pass (a 1000-tick bar is 8 KB); HBM sees them once.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int OS_THREADS = 128;
-constexpr int OS_CAP = 4096;  // doubles in shared memory (32 KB)
+constexpr int OS_WARPS = 8;
 
 __device__ __forceinline__ unsigned long long dkey(double x) {  // order-preserving map double -> uint64
     unsigned long long b = (unsigned long long)__double_as_longlong(x);
@@ -126,115 +132,161 @@ __device__ __forceinline__ double dunkey(unsigned long long k) {
     unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
     return __longlong_as_double((long long)b);
 }
+__device__ __forceinline__ unsigned long long warp_or64(unsigned long long x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x |= __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+__device__ __forceinline__ unsigned long long warp_and64(unsigned long long x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x &= __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+__device__ __forceinline__ unsigned long long warp_min64(unsigned long long x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long y = __shfl_xor_sync(FULL, x, o);
+        x = y < x ? y : x;
+    }
+    return x;
+}
 
-// k-th smallest (0-based) of a[0..cnt) in global memory, plus the (k+1)-th; block-cooperative.
-__device__ void radix_select_two(const double *__restrict__ a, int64_t cnt, int64_t k, double *r0, double *r1) {
-    __shared__ unsigned int hist[256];
-    __shared__ unsigned long long s_prefix;
-    __shared__ long long s_k;
-    __shared__ unsigned long long s_next;
-    __shared__ long long s_le;
-    if (threadIdx.x == 0) { s_prefix = 0; s_k = k; }
-    __syncthreads();
-    for (int pass = 0; pass < 8; pass++) {
-        const int shift = 56 - 8 * pass;
-        for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
-        __syncthreads();
-        const unsigned long long prefix = s_prefix;
-        const unsigned long long mask = pass == 0 ? 0ull : (~0ull << (shift + 8));
-        for (int64_t j = threadIdx.x; j < cnt; j += blockDim.x) {
-            unsigned long long key = dkey(a[j]);
-            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1u);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            long long kk = s_k;
-            int b = 0;
-            for (; b < 256; b++) {
-                if (kk < (long long)hist[b]) break;
-                kk -= hist[b];
+// k-th (0-based) and (k+1)-th smallest of a[0..cnt): warp-cooperative.  hist: 256 words of this warp's shared memory,
+// cand: 32 u64 of this warp's shared memory.  If k+1 == cnt, *r1 = *r0.
+__device__ void warp_select_two(const double *__restrict__ a, int64_t cnt, int64_t k, unsigned *hist,
+                                unsigned long long *cand, double *r0, double *r1) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long mask = 0ull, prefix = 0ull;   // keys in play: (key & mask) == prefix
+    int64_t kk = k, c = cnt;
+    for (;;) {
+        const unsigned long long hi_bound = prefix | ~mask;   // largest key of the selected range
+        if (c <= 32) {
+            // gather the candidates (ballot compaction keeps tick order) and the smallest key above the range
+            unsigned long long amin = ~0ull;
+            int filled = 0;
+            for (int64_t j0 = 0; j0 < cnt; j0 += 32) {
+                const int64_t j = j0 + lane;
+                unsigned long long key = 0ull;
+                bool m = false;
+                if (j < cnt) {
+                    key = dkey(__ldg(a + j));
+                    m = (key & mask) == prefix;
+                    if (key > hi_bound && key < amin) amin = key;
+                }
+                const unsigned bal = __ballot_sync(FULL, m);
+                if (m) cand[filled + __popc(bal & ((1u << lane) - 1u))] = key;
+                filled += __popc(bal);
             }
-            s_k = kk;
-            s_prefix = prefix | ((unsigned long long)b << shift);
+            __syncwarp();
+            amin = warp_min64(amin);
+            const unsigned long long mine = lane < c ? cand[lane] : ~0ull;
+            int rank = 0;
+            for (int q = 0; q < (int)c; q++) {
+                const unsigned long long o = __shfl_sync(FULL, mine, q);
+                rank += (o < mine) || (o == mine && q < lane);
+            }
+            const unsigned b0 = __ballot_sync(FULL, lane < c && rank == (int)kk);
+            const unsigned b1 = __ballot_sync(FULL, lane < c && rank == (int)kk + 1);
+            const unsigned long long k0 = __shfl_sync(FULL, mine, __ffs(b0) - 1);
+            unsigned long long k1 = b1 ? __shfl_sync(FULL, mine, __ffs(b1) - 1) : amin;
+            if (k1 == ~0ull && !b1) k1 = k0;   // k is the last element of the bar
+            *r0 = dunkey(k0); *r1 = dunkey(k1);
+            __syncwarp();
+            return;
         }
-        __syncthreads();
+        // diff pass
+        unsigned long long orv = 0ull, andv = ~0ull, amin = ~0ull;
+        for (int64_t j = lane; j < cnt; j += 32) {
+            const unsigned long long key = dkey(__ldg(a + j));
+            if ((key & mask) == prefix) { orv |= key; andv &= key; }
+            else if (key > hi_bound && key < amin) amin = key;
+        }
+        orv = warp_or64(orv); andv = warp_and64(andv);
+        const unsigned long long diff = orv ^ andv;
+        if (diff == 0ull) {     // every key in play is identical
+            amin = warp_min64(amin);
+            *r0 = dunkey(orv);
+            *r1 = (kk + 1 < c) ? dunkey(orv) : (amin == ~0ull ? dunkey(orv) : dunkey(amin));
+            return;
+        }
+        const int hb = 63 - __clzll((long long)diff);
+        const int shift = hb >= 7 ? hb - 7 : 0;
+        for (int b = lane; b < 256; b += 32) hist[b] = 0u;
+        __syncwarp();
+        for (int64_t j = lane; j < cnt; j += 32) {
+            const unsigned long long key = dkey(__ldg(a + j));
+            if ((key & mask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+        }
+        __syncwarp();
+        // bucket holding rank kk: each lane owns 8 consecutive bins
+        unsigned loc[8];
+        unsigned s = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { loc[q] = hist[lane * 8 + q]; s += loc[q]; }
+        unsigned inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += y;
+        }
+        const unsigned exc = inc - s;
+        const bool mineb = (unsigned long long)kk >= exc && (unsigned long long)kk < inc;
+        const int owner = __ffs(__ballot_sync(FULL, mineb)) - 1;
+        int bsel = 0;
+        unsigned below = 0, csel = 0;
+        if (lane == owner) {
+            unsigned run = exc;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if ((unsigned long long)kk >= run && (unsigned long long)kk < run + loc[q]) { bsel = lane * 8 + q; below = run; csel = loc[q]; }
+                run += loc[q];
+            }
+        }
+        bsel = __shfl_sync(FULL, bsel, owner);
+        below = __shfl_sync(FULL, below, owner);
+        csel = __shfl_sync(FULL, csel, owner);
+        kk -= below;
+        c = csel;
+        // new range: common bits above the digit come from any key in play (orv), the digit is bsel
+        const unsigned long long above_mask = (shift + 8 >= 64) ? 0ull : (~0ull << (shift + 8));
+        mask = above_mask | (255ull << shift);
+        prefix = (orv & above_mask) | ((unsigned long long)bsel << shift);
+        __syncwarp();
     }
-    const unsigned long long kth = s_prefix;
-    // count elements <= kth and the smallest element > kth
-    if (threadIdx.x == 0) { s_next = ~0ull; s_le = 0; }
-    __syncthreads();
-    unsigned long long mn = ~0ull;
-    long long le = 0;
-    for (int64_t j = threadIdx.x; j < cnt; j += blockDim.x) {
-        unsigned long long key = dkey(a[j]);
-        if (key <= kth) le++;
-        else if (key < mn) mn = key;
-    }
-    atomicMin(&s_next, mn);
-    atomicAdd((unsigned long long *)&s_le, (unsigned long long)le);
-    __syncthreads();
-    *r0 = dunkey(kth);
-    *r1 = (k + 1 < s_le) ? dunkey(kth) : (s_next == ~0ull ? dunkey(kth) : dunkey(s_next));
-    __syncthreads();
 }
 
 // mode bit 0: median -> median_out ; bit 1: 95th percentile -> p95_out
-__global__ void __launch_bounds__(OS_THREADS) k_bar_order_stats(const double *__restrict__ a,
-                                                                const int64_t *__restrict__ ci, int64_t nb, int mode,
-                                                                double *__restrict__ median_out,
-                                                                double *__restrict__ p95_out) {
-    __shared__ double buf[OS_CAP];
-    for (int64_t i = blockIdx.x; i < nb; i += gridDim.x) {
+__global__ void __launch_bounds__(OS_WARPS * 32) k_bar_order_stats(const double *__restrict__ a,
+                                                                   const int64_t *__restrict__ ci, int64_t nb, int mode,
+                                                                   double *__restrict__ median_out,
+                                                                   double *__restrict__ p95_out) {
+    __shared__ unsigned hist_s[OS_WARPS][256];
+    __shared__ unsigned long long cand_s[OS_WARPS][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nb; i += nwarps) {
         const int64_t start = ci[i] + 1, e = ci[i + 1];
         const int64_t cnt = e - start + 1;
-        if (cnt <= 0) {  // empty bar: median 0.0 (base.py:360); percentile untouched (NaN path handled by caller)
-            if (threadIdx.x == 0 && (mode & 1)) median_out[i] = 0.0;
+        if (cnt <= 0) {  // empty bar: median 0.0 (base.py:360); the percentile is not evaluated for empty bars
+            if (lane == 0 && (mode & 1)) median_out[i] = 0.0;
             continue;
         }
         const double *seg = a + start;
-        // ranks needed
-        const int64_t mk = (cnt & 1) ? (cnt >> 1) : (cnt >> 1) - 1;  // median: a[mk] (odd) or (a[mk]+a[mk+1])/2
-        double rank = 1.0 + (double)(cnt - 1) * (95.0 / 100.0);       // numba: 1 + (n-1)*true_divide(q,100)
-        double f = floor(rank), mfrac = rank - f;
-        const int64_t pk = (int64_t)(f - 1.0);
-        if (cnt <= OS_CAP) {
-            int64_t m2 = 1;
-            while (m2 < cnt) m2 <<= 1;
-            for (int64_t j = threadIdx.x; j < m2; j += OS_THREADS) buf[j] = j < cnt ? seg[j] : INFINITY;
-            __syncthreads();
-            for (int64_t k = 2; k <= m2; k <<= 1) {
-                for (int64_t jj = k >> 1; jj > 0; jj >>= 1) {
-                    for (int64_t t = threadIdx.x; t < (m2 >> 1); t += OS_THREADS) {
-                        // t-th compare-exchange pair of this step
-                        int64_t lo = 2 * t - (t & (jj - 1));
-                        int64_t hi = lo + jj;
-                        bool up = ((lo & k) == 0);
-                        double x = buf[lo], y = buf[hi];
-                        if ((x > y) == up) { buf[lo] = y; buf[hi] = x; }
-                    }
-                    __syncthreads();
-                }
-            }
-            if (threadIdx.x == 0) {
-                if (mode & 1) median_out[i] = (cnt & 1) ? buf[mk] : (buf[mk] + buf[mk + 1]) / 2;
-                if (mode & 2) {
-                    if (cnt == 1) p95_out[i] = buf[0];
-                    else {
-                        double lower = buf[pk], upper = buf[pk + 1 < cnt ? pk + 1 : pk];
-                        p95_out[i] = lower * (1 - mfrac) + upper * mfrac;
-                    }
-                }
-            }
-            __syncthreads();
-        } else {
-            double r0, r1;
-            if (mode & 1) {
-                radix_select_two(seg, cnt, mk, &r0, &r1);
-                if (threadIdx.x == 0) median_out[i] = (cnt & 1) ? r0 : (r0 + r1) / 2;
-            }
-            if (mode & 2) {
-                radix_select_two(seg, cnt, pk, &r0, &r1);
-                if (threadIdx.x == 0) p95_out[i] = r0 * (1 - mfrac) + r1 * mfrac;
+        double r0, r1;
+        if (mode & 1) {
+            // numba _median_inner: odd -> a[n>>1]; even -> (a[n/2-1] + a[n/2]) / 2
+            const int64_t mk = (cnt & 1) ? (cnt >> 1) : (cnt >> 1) - 1;
+            warp_select_two(seg, cnt, mk, hist_s[w], cand_s[w], &r0, &r1);
+            if (lane == 0) median_out[i] = (cnt & 1) ? r0 : (r0 + r1) / 2;
+        }
+        if (mode & 2) {
+            if (cnt == 1) { if (lane == 0) p95_out[i] = seg[0]; }
+            else {
+                // numba _collect_percentiles_inner: rank = 1 + (n-1)*q/100; lower*(1-m) + upper*m
+                const double rank = 1.0 + (double)(cnt - 1) * (95.0 / 100.0);
+                const double f = floor(rank), mfrac = rank - f;
+                warp_select_two(seg, cnt, (int64_t)(f - 1.0), hist_s[w], cand_s[w], &r0, &r1);
+                if (lane == 0) p95_out[i] = r0 * (1 - mfrac) + r1 * mfrac;
             }
         }
     }
@@ -243,8 +295,10 @@ __global__ void __launch_bounds__(OS_THREADS) k_bar_order_stats(const double *__
 static int launch_order_stats(fmk_ctx *ctx, const double *a, const int64_t *ci, int64_t nb, int mode, double *med,
                               double *p95) {
     if (nb <= 0) return FMK_OK;
-    int64_t grid = nb < (int64_t)ctx->sm_count * 32 ? nb : (int64_t)ctx->sm_count * 32;
-    FMK_LAUNCH(ctx, k_bar_order_stats, (unsigned)grid, OS_THREADS, 0, a, ci, nb, mode, med, p95);
+    int64_t blocks = cdiv(nb, OS_WARPS);
+    const int64_t maxb = (int64_t)ctx->sm_count * 16;
+    if (blocks > maxb) blocks = maxb;
+    FMK_LAUNCH(ctx, k_bar_order_stats, (unsigned)blocks, OS_WARPS * 32, 0, a, ci, nb, mode, med, p95);
     return FMK_OK;
 }
 

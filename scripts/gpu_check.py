@@ -66,3 +66,8 @@ t0 = time.time(); lr = oracle.triple_barrier(ts[:M], px[:M], ev, tg, (2.0, 2.0),
 print("  tbm labels equal:", np.array_equal(lab[0], lr[0]), "touch equal:", np.array_equal(lab[1], lr[1]), "mean path", float(np.mean(lr[1]-ev)))
 assert_f64(lab[2], lr[2], "tbm rets", atol=1e-15); assert_f64(lab[3], lr[3], "tbm ratios", atol=1e-15); print("  tbm parity OK")
 print("launches", ctx.launch_count())
+vix = timed("volume_bar_index T=5", lambda: core.volume_bar_index(tr, 5.0))
+print("  stats", ctx.index_stats(), "bars", vix.m - 1)
+t0 = time.time(); vref = oracle.volume_bar_indexer(qty, 5.0); dt = time.time() - t0
+print(f"  oracle volume: {dt:.3f}s  {N/dt/1e6:.1f} Mticks/s; exact:", np.array_equal(vix.download()[1], vref))
+print("prof", ctx.prof_report())
