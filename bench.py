@@ -181,15 +181,10 @@ def main():
         class _Arr:   # zero-copy view of the library-owned device columns
             __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
         frame = torch.as_tensor(_Arr(), device=f"cuda:{local}")
-        sizes = torch.zeros(world, dtype=torch.int64, device=frame.device)
-        mine = torch.tensor([nbytes], dtype=torch.int64, device=frame.device)
-        dist.all_gather_into_tensor(sizes, mine)
-        mx = int(sizes.max().item())
-        padded = torch.zeros(mx, dtype=torch.uint8, device=frame.device)
-        padded[:nbytes] = frame
-        out = [torch.empty(mx, dtype=torch.uint8, device=frame.device) for _ in range(world)] if rank == 0 else None
-        dist.gather(padded, out, dst=0)
-        gather_bytes[0] = mx * world
+        from finmlkit_b200.parallel import gather_frames as _gather
+        frames = _gather(frame, dst=0)
+        if frames is not None:
+            gather_bytes[0] = int(sum(f.numel() for f in frames))
 
     nbars = [0]
 

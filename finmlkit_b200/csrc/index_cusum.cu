@@ -1,0 +1,281 @@
+// index_cusum.cu -- CUSUM bar indexer on the device (reference: finmlkit/bar/logic.py:152-221).
+//
+// Reference recurrence per tick i (after forward-filling sigma): r = log(p_i/p_{i-1});
+//   s+ = max(0, s+ + r); s- = min(0, s- + r); if ts_i == ts_{i+1}: no test; lam = max(mult*sigma_i, floor);
+//   if s+ >= lam: emit, s+ = 0  elif s- <= -lam: emit, s- = 0.
+// The two accumulators are clamped at exactly 0.0 and reset to exactly 0.0, so trajectories started from different
+// states COALESCE bit-for-bit once both have been clamped/reset at the same tick.  The pipeline exploits that:
+//
+//   C1  k_cusum_fill / k_cusum_prep : forward-fill sigma (scan of "last non-NaN"), then per tick r_i, lam_i and the
+//                                     "may close" flag (fully parallel; the libm calls live here)
+//   C2  k_cusum_tasks   : one lane per chunk; warm-up over the PREVIOUS chunk from the zero state, record the state
+//                         reached at the chunk start (speculative), then replay the chunk marking closes in a bitmap
+//   C3  k_cusum_verify  : single thread walks the chunks with the TRUE state; a chunk whose speculative start state
+//                         is bit-identical to the true one is accepted as is, otherwise it is replayed exactly
+//   C4  bitmap -> index list (popcount scan + ordered write)
+// Given identical r_i the result is the reference's, bit for bit; r_i itself uses CUDA's log (<= 1 ulp from glibc's),
+// which can only matter at an exact tie of a ~1e-19-wide band (documented in DESIGN.md).
+#include <math.h>
+#include <new>
+#include "common.cuh"
+#include "scan.cuh"
+
+// ---- forward fill: scan with the operator "right if right is not NaN else left" over (value) ---------------------
+__device__ __forceinline__ double ff_nan() { return __longlong_as_double(0x7ff8000000000000ll); }
+struct FF {
+    double v;
+    __device__ FF() { v = ff_nan(); }
+    __device__ explicit FF(int) { v = ff_nan(); }   // identity (T(0))
+    __device__ explicit FF(double x) { v = x; }
+};
+__device__ __forceinline__ FF operator+(const FF &a, const FF &b) { return (b.v == b.v) ? b : a; }
+__device__ __forceinline__ FF __shfl_up_sync(unsigned m, const FF &x, int o) {
+    FF r;
+    r.v = ::__shfl_up_sync(m, x.v, o);
+    return r;
+}
+struct FFIn {
+    const double *s;
+    __device__ FF operator()(int64_t i) const { return FF(s[i]); }
+};
+struct FFOut {
+    double *s;
+    int64_t first;
+    __device__ void operator()(int64_t i, const FF &cs) const {
+        if (i >= first) s[i] = cs.v;   // logic.py:186-189 fills from the first non-NaN index on
+    }
+};
+
+__global__ void k_cusum_first(const double *__restrict__ sigma, int64_t n, unsigned long long *first) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && sigma[i] == sigma[i]) atomicMin(first, (unsigned long long)i);
+}
+
+__global__ void k_cusum_prep(const int64_t *__restrict__ ts, const double *__restrict__ p,
+                             const double *__restrict__ sigma, int64_t n, double floor_, double mult,
+                             double *__restrict__ r, double *__restrict__ lam, uint8_t *__restrict__ allowed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    r[i] = i > 0 ? log(__ddiv_rn(p[i], p[i - 1])) : 0.0;
+    const double l = __dmul_rn(mult, sigma[i]);
+    lam[i] = (floor_ > l) ? floor_ : l;            // python max(l, floor): floor only if floor > l (NaN l stays NaN)
+    allowed[i] = !(i + 1 < n && ts[i] == ts[i + 1]);
+}
+
+struct CusumState { double sp, sn; };
+
+// one reference step; returns true when the bar closes at this tick
+__device__ __forceinline__ bool cusum_step(CusumState &s, double r, double lam, bool allowed) {
+    const double a = __dadd_rn(s.sp, r), b = __dadd_rn(s.sn, r);
+    s.sp = (a > 0.0) ? a : 0.0;      // python max(0.0, a): a only if a > 0.0 (NaN -> 0.0)
+    s.sn = (b < 0.0) ? b : 0.0;
+    if (!allowed) return false;
+    if (s.sp >= lam) { s.sp = 0.0; return true; }
+    if (s.sn <= -lam) { s.sn = 0.0; return true; }
+    return false;
+}
+
+constexpr int CT_WARPS = 4;
+constexpr int CT_R = 16;
+
+// lane = chunk.  Replay [warm_start, chunk_start) silently from the zero state, then [chunk_start, chunk_end) with
+// closes recorded in the bitmap (chunk bounds are multiples of 32 ticks, so words are never shared between lanes).
+__global__ void __launch_bounds__(CT_WARPS * 32) k_cusum_tasks(const double *__restrict__ r, const double *__restrict__ lam,
+                                                               const uint8_t *__restrict__ allowed, int64_t n,
+                                                               int64_t first, int64_t CH, int64_t nchunks,
+                                                               unsigned *__restrict__ bitmap,
+                                                               CusumState *__restrict__ spec_start,
+                                                               CusumState *__restrict__ spec_end) {
+    __shared__ double sr[CT_WARPS][32][CT_R + 1];
+    __shared__ double sl[CT_WARPS][32][CT_R + 1];
+    __shared__ uint8_t sa[CT_WARPS][32][CT_R];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t k = ((int64_t)blockIdx.x * CT_WARPS + w) * 32 + lane;
+    const int64_t lo = first + 1 + k * CH;              // first tick of the chunk (ticks <= first are never tested)
+    int64_t hi = lo + CH;
+    if (hi > n) hi = n;
+    bool active = k < nchunks && lo < n;
+    int64_t pos = lo - CH;                              // warm-up over the previous chunk
+    if (pos < first + 1) pos = first + 1;
+    CusumState s{0.0, 0.0};
+    unsigned word = 0;
+    const int half = lane >> 4, col = lane & 15;
+    if (active && pos == lo) spec_start[k] = s;        // chunk 0: the true initial state
+    while (__any_sync(0xffffffffu, active)) {
+#pragma unroll 4
+        for (int q = 0; q < 16; q++) {
+            const int row = 2 * q + half;
+            const int64_t rp = __shfl_sync(0xffffffffu, pos, row);
+            const int ra = __shfl_sync(0xffffffffu, (int)active, row);
+            const int64_t idx = rp + col;
+            double a = 0.0, b = 0.0;
+            uint8_t c = 0;
+            if (ra && idx < n) { a = __ldg(r + idx); b = __ldg(lam + idx); c = __ldg(allowed + idx); }
+            sr[w][row][col] = a; sl[w][row][col] = b; sa[w][row][col] = c;
+        }
+        __syncwarp();
+        if (active) {
+#pragma unroll 1
+            for (int tt = 0; tt < CT_R; tt++) {
+                const int64_t i = pos + tt;
+                if (i >= hi) { active = false; break; }
+                if (i == lo) spec_start[k] = s;
+                const bool close = cusum_step(s, sr[w][lane][tt], sl[w][lane][tt], sa[w][lane][tt] != 0);
+                if (i >= lo) {
+                    const int64_t rel = i - (first + 1);
+                    if (close) word |= 1u << (rel & 31);
+                    if ((rel & 31) == 31 || i + 1 == hi) { bitmap[rel >> 5] = word; word = 0; }
+                }
+            }
+            pos += CT_R;
+            if (pos >= hi) active = false;
+        }
+        __syncwarp();
+    }
+    if (k < nchunks && lo < n) spec_end[k] = s;
+}
+
+// C3: accept or repair, chunk by chunk, with the true state.  One block: the speculative states are staged through
+// shared memory in tiles so the serial walk of thread 0 never waits on a dependent global load.
+constexpr int CV_TILE = 1024;
+__global__ void __launch_bounds__(256) k_cusum_verify(const double *__restrict__ r, const double *__restrict__ lam,
+                                                      const uint8_t *__restrict__ allowed, int64_t n, int64_t first,
+                                                      int64_t CH, int64_t nchunks, unsigned *bitmap,
+                                                      const CusumState *__restrict__ spec_start,
+                                                      const CusumState *__restrict__ spec_end, int64_t *repairs) {
+    __shared__ CusumState ss[CV_TILE], se[CV_TILE];
+    __shared__ CusumState cur;
+    __shared__ long long rep_s;
+    if (threadIdx.x == 0) { cur.sp = 0.0; cur.sn = 0.0; rep_s = 0; }
+    for (int64_t k0 = 0; k0 < nchunks; k0 += CV_TILE) {
+        __syncthreads();
+        for (int q = threadIdx.x; q < CV_TILE && k0 + q < nchunks; q += 256) { ss[q] = spec_start[k0 + q]; se[q] = spec_end[k0 + q]; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            CusumState s = cur;
+            for (int q = 0; q < CV_TILE && k0 + q < nchunks; q++) {
+                const int64_t k = k0 + q;
+                const int64_t lo = first + 1 + k * CH;
+                if (lo >= n) break;
+                int64_t hi = lo + CH;
+                if (hi > n) hi = n;
+                const CusumState g = ss[q];
+                if (__double_as_longlong(g.sp) == __double_as_longlong(s.sp) &&
+                    __double_as_longlong(g.sn) == __double_as_longlong(s.sn)) {
+                    s = se[q];
+                    continue;
+                }
+                rep_s++;
+                unsigned word = 0;
+                for (int64_t i = lo; i < hi; i++) {
+                    const bool close = cusum_step(s, r[i], lam[i], allowed[i] != 0);
+                    const int64_t rel = i - (first + 1);
+                    if (close) word |= 1u << (rel & 31);
+                    if ((rel & 31) == 31 || i + 1 == hi) { bitmap[rel >> 5] = word; word = 0; }
+                }
+            }
+            cur = s;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *repairs = rep_s;
+}
+
+// C4: bitmap -> ordered index list
+struct PopIn {
+    const unsigned *bm;
+    __device__ int64_t operator()(int64_t w) const { return __popc(bm[w]); }
+};
+struct PopOut {
+    const unsigned *bm;
+    int64_t *out;
+    int64_t base;     // tick index of bit 0
+    __device__ void operator()(int64_t w, int64_t incl) const {
+        unsigned x = bm[w];
+        int64_t pos = incl - __popc(x) + 1;   // out[0] is the open marker
+        while (x) {
+            const int b = __ffs(x) - 1;
+            out[pos++] = base + w * 32 + b;
+            x &= x - 1;
+        }
+    }
+};
+
+struct CountOut {
+    __device__ void operator()(int64_t, int64_t) const {}
+};
+
+__global__ void k_set_first(int64_t *out, int64_t v) { out[0] = v; }
+
+int fmk_cusum_index_impl(fmk_ctx *ctx, const fmk_trades *t, fmk_buf *sigma, double sigma_floor, double sigma_mult,
+                         fmk_index **out_ix) {
+    *out_ix = nullptr;
+    const int64_t n = t->n;
+    if (n <= 0) return fmk_fail(ctx, FMK_ERR_ARG, "empty trades");
+    if (sigma->bytes < n * 8) return fmk_fail(ctx, FMK_ERR_ARG, "Prices, timestamps, and sigma arrays must have the same length.");
+    double *sg = (double *)sigma->ptr;
+    ctx->stats[0] = ctx->stats[1] = ctx->stats[2] = 0;
+
+    // first non-NaN sigma (logic.py:175-179; 0 when every element is NaN)
+    Scratch<unsigned long long> dfirst(ctx);
+    FMK_TRY(dfirst.alloc(1));
+    FMK_CUDA(ctx, cudaMemsetAsync(dfirst.p, 0xff, 8, ctx->stream));
+    FMK_LAUNCH(ctx, k_cusum_first, (unsigned)cdiv(n, 256), 256, 0, (const double *)sg, n, dfirst.p);
+    unsigned long long hfirst = 0;
+    FMK_CUDA(ctx, cudaMemcpyAsync(&hfirst, dfirst.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t first = hfirst == ~0ull ? 0 : (int64_t)hfirst;
+    if (hfirst != ~0ull) FMK_TRY((device_inclusive_scan<FF>(ctx, FFIn{sg}, FFOut{sg, first}, n, (FF *)nullptr)));
+
+    Scratch<double> r(ctx), lam(ctx);
+    Scratch<uint8_t> allowed(ctx);
+    FMK_TRY(r.alloc(n)); FMK_TRY(lam.alloc(n)); FMK_TRY(allowed.alloc(n));
+    FMK_LAUNCH(ctx, k_cusum_prep, (unsigned)cdiv(n, 256), 256, 0, (const int64_t *)t->ts, (const double *)t->price,
+               (const double *)sg, n, sigma_floor, sigma_mult, r.p, lam.p, allowed.p);
+
+    const int64_t m_ticks = n - (first + 1);   // ticks that can close a bar
+    int64_t total = 0;
+    int64_t *idx = nullptr;
+    if (m_ticks > 0) {
+        int64_t CH = cdiv(m_ticks, 8192);
+        if (CH < 4096) CH = 4096;
+        CH = cdiv(CH, 32) * 32;
+        const int64_t nchunks = cdiv(m_ticks, CH);
+        const int64_t nwords = cdiv(m_ticks, 32);
+        Scratch<unsigned> bitmap(ctx);
+        Scratch<CusumState> ss(ctx), se(ctx);
+        Scratch<int64_t> rep(ctx), dtotal(ctx);
+        FMK_TRY(bitmap.alloc(nwords)); FMK_TRY(ss.alloc(nchunks)); FMK_TRY(se.alloc(nchunks)); FMK_TRY(rep.alloc(1));
+        FMK_TRY(dtotal.alloc(1));
+        FMK_LAUNCH(ctx, k_cusum_tasks, (unsigned)cdiv(nchunks, CT_WARPS * 32), CT_WARPS * 32, 0, (const double *)r.p,
+                   (const double *)lam.p, (const uint8_t *)allowed.p, n, first, CH, nchunks, bitmap.p, ss.p, se.p);
+        FMK_LAUNCH(ctx, k_cusum_verify, 1, 256, 0, (const double *)r.p, (const double *)lam.p, (const uint8_t *)allowed.p, n,
+                   first, CH, nchunks, bitmap.p, (const CusumState *)ss.p, (const CusumState *)se.p, rep.p);
+        // count, allocate, write
+        Scratch<int64_t> wsum(ctx);
+        FMK_TRY(wsum.alloc(1));
+        FMK_TRY((device_inclusive_scan<int64_t>(ctx, PopIn{bitmap.p}, CountOut{}, nwords, dtotal.p)));
+        int64_t hrep = 0;
+        FMK_CUDA(ctx, cudaMemcpyAsync(&hrep, rep.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        FMK_CUDA(ctx, cudaMemcpyAsync(&total, dtotal.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->stats[0] = nchunks; ctx->stats[1] = hrep; ctx->stats[2] = 1;
+        FMK_TRY(fmk_dalloc(ctx, &idx, total + 1));
+        int rc = device_inclusive_scan<int64_t>(ctx, PopIn{bitmap.p}, PopOut{bitmap.p, idx, first + 1}, nwords, (int64_t *)nullptr);
+        if (rc) { fmk_dfree(ctx, idx); return rc; }
+    } else {
+        FMK_TRY(fmk_dalloc(ctx, &idx, 1));
+    }
+    k_set_first<<<1, 1, 0, ctx->stream>>>(idx, first);
+    ctx->launches++;
+    fmk_index *ix = new (std::nothrow) fmk_index();
+    if (!ix) { fmk_dfree(ctx, idx); return FMK_ERR_ALLOC; }
+    memset(ix, 0, sizeof(*ix));
+    ix->m = total + 1;
+    ix->n_ticks = n;
+    ix->close_idx = idx;
+    int rc = fmk_gather_close_ts(ctx, t, ix);
+    if (rc) { fmk_index_free(ctx, ix); return rc; }
+    *out_ix = ix;
+    return FMK_OK;
+}

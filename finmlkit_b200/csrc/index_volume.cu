@@ -103,29 +103,27 @@ __global__ void k_volume_first(const double *__restrict__ v, int64_t n, double T
 __global__ void __launch_bounds__(256) k_volume_exit0(const int32_t *__restrict__ next, int64_t n,
                                                       int32_t *__restrict__ exit0) {
     __shared__ int32_t tgt[VC0];
-    __shared__ int changed;
     const int64_t base = (int64_t)blockIdx.x * VC0;
     const int64_t end = base + VC0 < n ? base + VC0 : n;
     for (int k = threadIdx.x; k < VC0; k += 256) tgt[k] = base + k < n ? next[base + k] : (int32_t)n;
     __syncthreads();
     for (int round = 0; round < 12; round++) {
-        if (threadIdx.x == 0) changed = 0;
-        __syncthreads();
         int32_t nv[VC0 / 256];
-        bool ch = false;
+        int ch = 0;
 #pragma unroll
         for (int q = 0; q < VC0 / 256; q++) {
             const int k = threadIdx.x + q * 256;
             int32_t t = tgt[k];
-            if ((int64_t)t < end) { t = tgt[t - base]; ch = true; }
+            if ((int64_t)t < end) { t = tgt[t - base]; ch = 1; }
             nv[q] = t;
         }
-        if (ch) changed = 1;
-        __syncthreads();
+        // barrier + block-wide vote in one step: every thread sees the same verdict (a shared flag that is reset by
+        // thread 0 at the top of the next round would race with the threads still reading it)
+        const int any = __syncthreads_or(ch);
 #pragma unroll
         for (int q = 0; q < VC0 / 256; q++) tgt[threadIdx.x + q * 256] = nv[q];
         __syncthreads();
-        if (!changed) break;
+        if (!any) break;
     }
     for (int k = threadIdx.x; k < VC0; k += 256)
         if (base + k < n) exit0[base + k] = tgt[k];
@@ -311,7 +309,3 @@ int fmk_volume_index_impl(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index
     return finish_index(ctx, t, idx, nb + 1, out_ix);
 }
 
-int fmk_cusum_index_impl(fmk_ctx *ctx, const fmk_trades *, fmk_buf *, double, double, fmk_index **out) {
-    *out = nullptr;
-    return fmk_fail(ctx, FMK_ERR_INTERNAL, "cusum bars: not built yet");
-}

@@ -13,12 +13,13 @@ __device__ __forceinline__ T warp_incl_scan_sum(T x) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         T y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= (unsigned)o) x = x + y;
+        if (lane >= (unsigned)o) x = y + x;   // earlier lanes on the left: the operator may be non-commutative
     }
     return x;
 }
 
-// Block-wide exclusive scan of one value per thread (blockDim.x == SCAN_THREADS). Returns exclusive prefix; total in *tot.
+// Block-wide exclusive scan of one value per thread (blockDim.x == SCAN_THREADS) for any associative `+` with
+// identity T(0) (no subtraction: the operator need not be invertible).  Returns the exclusive prefix; total in *tot.
 template <typename T>
 __device__ __forceinline__ T block_excl_scan_sum(T x, T *tot) {
     __shared__ T warp_tot[SCAN_THREADS / 32];
@@ -30,11 +31,15 @@ __device__ __forceinline__ T block_excl_scan_sum(T x, T *tot) {
     if (w == 0) {
         T v = lane < SCAN_THREADS / 32 ? warp_tot[lane] : T(0);
         T s = warp_incl_scan_sum(v);
-        if (lane < SCAN_THREADS / 32) warp_tot[lane] = s - v;  // exclusive warp offsets
+        T e = __shfl_up_sync(0xffffffffu, s, 1);
+        if (lane == 0) e = T(0);
+        if (lane < SCAN_THREADS / 32) warp_tot[lane] = e;  // exclusive warp offsets
         if (lane == SCAN_THREADS / 32 - 1) block_tot = s;
     }
     __syncthreads();
-    T r = warp_tot[w] + (inc - x);
+    T ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) ex = T(0);
+    T r = warp_tot[w] + ex;
     *tot = block_tot;
     __syncthreads();
     return r;

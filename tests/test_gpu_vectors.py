@@ -1,0 +1,37 @@
+"""GPU: the CUDA path, called through the mirrored reference API, against the reference's hand-computed vectors."""
+import types
+
+import pytest
+
+import _vector_checks as chk
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from finmlkit_b200.bar import base, logic
+    from finmlkit_b200.label import tbm
+    return types.SimpleNamespace(comp_bar_ohlcv=base.comp_bar_ohlcv, time_bar_indexer=logic._time_bar_indexer,
+                                 comp_bar_directional_features=base.comp_bar_directional_features,
+                                 comp_bar_footprints=base.comp_bar_footprints, triple_barrier=tbm.triple_barrier)
+
+
+def test_ohlcv(api):
+    chk.check_ohlcv(api)
+
+
+def test_time_clock(api):
+    chk.check_time_clock(api)
+
+
+def test_directional(api):
+    chk.check_directional(api)
+
+
+def test_footprint(api):
+    chk.check_footprint(api)
+
+
+def test_tbm(api):
+    chk.check_tbm(api)

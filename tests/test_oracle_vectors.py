@@ -1,0 +1,45 @@
+"""CPU: the oracle against the reference's own hand-computed test vectors (tests/ref_vectors.py)."""
+import types
+
+import numpy as np
+import pytest
+
+import _vector_checks as chk
+import oracle
+import ref_vectors as V
+
+API = types.SimpleNamespace(comp_bar_ohlcv=oracle.comp_bar_ohlcv, time_bar_indexer=oracle.time_bar_indexer,
+                            comp_bar_directional_features=oracle.comp_bar_directional_features,
+                            comp_bar_footprints=oracle.comp_bar_footprints, triple_barrier=oracle.triple_barrier)
+
+
+def test_ohlcv():
+    chk.check_ohlcv(API)
+
+
+def test_time_clock():
+    chk.check_time_clock(API)
+
+
+def test_directional():
+    chk.check_directional(API)
+
+
+def test_footprint():
+    chk.check_footprint(API)
+
+
+def test_tbm():
+    chk.check_tbm(API)
+
+
+@pytest.mark.parametrize("prices,want", V.TICK_SIZE)
+def test_tick_size_host(prices, want):
+    from finmlkit_b200.bar.utils import comp_price_tick_size
+    assert comp_price_tick_size(np.array(prices)) == pytest.approx(want, rel=1e-9, abs=1e-15)
+
+
+def test_tick_size_empty_raises():
+    from finmlkit_b200.bar.utils import comp_price_tick_size
+    with pytest.raises(ValueError):
+        comp_price_tick_size(np.array([]))
