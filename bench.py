@@ -267,9 +267,9 @@ def main():
         d2h = [0]
 
         def e2e_step():
-            tr_e.refill(h_ts, h_px, h_qty, None)                    # H2D of the step's inputs (pinned)
+            tr_e.refill(None, h_px, h_qty, None)                    # H2D of the step's inputs (pinned): price, amount
             ix = core.dollar_bar_index(tr_e, THRESHOLD)
-            cts, cidx = ix.download()                                 # D2H close timestamps / indices
+            cts, cidx = ix.download(host_ts=h_ts)                     # D2H close indices; close_ts = ts[idx] on the host
             cols = core.bar_ohlcv(tr_e, ix)                           # D2H of the 8 OHLCV columns
             d2h[0] = cts.nbytes + cidx.nbytes + sum(c.nbytes for c in cols)
             return cols
@@ -285,9 +285,10 @@ def main():
             t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": world * n_e / dt, "unit": UNIT, "h2d_bytes_per_step": 24 * n_e, "d2h_bytes_per_step": int(d2h[0]),
+        e2e = {"value": world * n_e / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * n_e, "d2h_bytes_per_step": int(d2h[0]),
                "ticks_per_step_per_gpu": n_e, "ms_per_step": dt * 1e3,
-               "api": "fmk_trades_refill + fmk_dollar_bar_index + fmk_index_download + fmk_bar_ohlcv (host buffers)"}
+               "api": "fmk_trades_refill(price, amount) + fmk_dollar_bar_index + fmk_index_download + host ts[idx] + fmk_bar_ohlcv "
+                      "(host buffers; timestamps stay on the host, as in DollarBarKit.build_ohlcv)"}
 
         # ---- CPU baseline beside it (rank 0, N=1 only): oracle port on a bounded sample of the same arrays ----------
         if world == 1 and rank == 0:

@@ -106,14 +106,23 @@ class BarBuilderBase(ABC):
         return f"Class: {self.__class__.__name__} with members:\n{members}\nRaw trades data:\n{info}"
 
     # -- device residency -------------------------------------------------------------------------------------------
+    _needs_device_ts = False   # time / CUSUM kits override: their indexers read the timestamps on the device
+
+    def _host_ts(self):
+        return self.trades_df['timestamp'].astype(np.int64).values
+
     def _device(self) -> core.DeviceTrades:
-        """Upload the trade columns once (device SoA: ts i64, price f64, amount f64, side i8)."""
+        """Upload the trade columns once (device SoA: [ts i64,] price f64, amount f64, side i8).  Kits whose indexer
+        only needs ts[close_idx] keep the timestamps on the host (a third less H2D traffic)."""
         if self._dev_trades is None:
             df = self.trades_df
-            ts = df['timestamp'].astype(np.int64).values
+            ts = self._host_ts() if self._needs_device_ts else None
             side = df['side'].values.astype(np.int8) if 'side' in df.columns else None
             self._dev_trades = core.DeviceTrades.upload(ts, df['price'].values, df['amount'].values, side, ctx=self._ctx)
         return self._dev_trades
+
+    def _download_index(self):
+        return self._dev_index.download(host_ts=None if self._needs_device_ts else self._host_ts())
 
     @abstractmethod
     def _comp_bar_close(self) -> Tuple[np.ndarray, np.ndarray]:

@@ -11,6 +11,8 @@ from .base import BarBuilderBase
 class TimeBarKit(BarBuilderBase):
     """kit.py:12-35."""
 
+    _needs_device_ts = True
+
     def __init__(self, trades, period: pd.Timedelta, ctx=None):
         super().__init__(trades, ctx)
         self.interval = period.total_seconds()
@@ -29,7 +31,7 @@ class TickBarKit(BarBuilderBase):
 
     def _comp_bar_close(self):
         self._dev_index = core.tick_bar_index(self._device(), self.tick_count_thrs)
-        return self._dev_index.download()
+        return self._download_index()
 
 
 class VolumeBarKit(BarBuilderBase):
@@ -41,7 +43,7 @@ class VolumeBarKit(BarBuilderBase):
 
     def _comp_bar_close(self):
         self._dev_index = core.volume_bar_index(self._device(), self.volume_ths)
-        return self._dev_index.download()
+        return self._download_index()
 
 
 class DollarBarKit(BarBuilderBase):
@@ -53,11 +55,13 @@ class DollarBarKit(BarBuilderBase):
 
     def _comp_bar_close(self):
         self._dev_index = core.dollar_bar_index(self._device(), self.dollar_thrs)
-        return self._dev_index.download()
+        return self._download_index()
 
 
 class CUSUMBarKit(BarBuilderBase):
     """kit.py:141-181.  Like the reference, NaNs of ``sigma`` are forward-filled in place by the indexer."""
+
+    _needs_device_ts = True
 
     def __init__(self, trades, sigma, sigma_floor: float = 5e-4, sigma_mult: float = 2., ctx=None):
         super().__init__(trades, ctx)

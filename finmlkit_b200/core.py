@@ -136,19 +136,23 @@ class DeviceTrades:
 
     def __init__(self, ctx: Context, h, n):
         self.ctx, self.h, self.n = ctx, h, n
+        self.has_ts = True
         self._fin = weakref.finalize(self, ctx._L.fmk_trades_free, ctx.h, h)
 
     @classmethod
     def upload(cls, ts, price, amount, side=None, ctx: Context = None):
         ctx = ctx or default_context()
-        ts, price, amount = _c(ts, np.int64), _c(price, np.float64), _c(amount, np.float64)
-        if not (len(ts) == len(price) == len(amount)):
+        price, amount = _c(price, np.float64), _c(amount, np.float64)
+        ts = _c(ts, np.int64) if ts is not None else None      # None: the host keeps the timestamps (see fmk.h)
+        if len(price) != len(amount) or (ts is not None and len(ts) != len(price)):
             raise ValueError("Prices and volumes arrays must have the same length.")
         sd = _c(side, np.int8) if side is not None else None
         h = C.c_void_p()
-        ctx.check(ctx._L.fmk_trades_upload(ctx.h, _ptr(ts), _ptr(price), _ptr(amount), _ptr(sd), len(ts), C.byref(h)))
+        ctx.check(ctx._L.fmk_trades_upload(ctx.h, _ptr(ts), _ptr(price), _ptr(amount), _ptr(sd), len(price), C.byref(h)))
         ctx.sync()
-        return cls(ctx, h, len(ts))
+        obj = cls(ctx, h, len(price))
+        obj.has_ts = ts is not None
+        return obj
 
     @classmethod
     def synth(cls, n, seed=42, ctx: Context = None):
@@ -178,9 +182,13 @@ class DeviceIndex:
         self.m = int(ctx._L.fmk_index_size(h))
         self._fin = weakref.finalize(self, ctx._L.fmk_index_free, ctx.h, h)
 
-    def download(self):
+    def download(self, host_ts=None):
+        """(close_ts, close_idx).  When the trades were uploaded without timestamps pass the host array: close_ts is
+        then ts[close_idx] gathered on the host (bar/kit.py:67 `close_ts = timestamps[close_indices]`)."""
         ts, idx = np.empty(self.m, np.int64), np.empty(self.m, np.int64)
-        self.ctx.check(self.ctx._L.fmk_index_download(self.ctx.h, self.h, _ptr(ts), _ptr(idx)))
+        self.ctx.check(self.ctx._L.fmk_index_download(self.ctx.h, self.h, _ptr(ts) if host_ts is None else None, _ptr(idx)))
+        if host_ts is not None:
+            ts = np.asarray(host_ts)[idx]
         return ts, idx
 
     @classmethod

@@ -189,13 +189,14 @@ void fmk_buf_free(fmk_ctx *ctx, fmk_buf *b) {
     delete b;
 }
 
-static int trades_alloc(fmk_ctx *ctx, int64_t n, int with_side, fmk_trades **out) {
+static int trades_alloc(fmk_ctx *ctx, int64_t n, int with_ts, int with_side, fmk_trades **out) {
     *out = nullptr;
     fmk_trades *t = new (std::nothrow) fmk_trades();
     if (!t) return FMK_ERR_ALLOC;
     memset(t, 0, sizeof(*t));
     t->n = n;
-    int rc = fmk_dalloc(ctx, &t->ts, n);
+    int rc = FMK_OK;
+    if (with_ts) rc = fmk_dalloc(ctx, &t->ts, n);
     if (!rc) rc = fmk_dalloc(ctx, &t->price, n);
     if (!rc) rc = fmk_dalloc(ctx, &t->amount, n);
     if (!rc && with_side) rc = fmk_dalloc(ctx, &t->side, n);
@@ -208,7 +209,7 @@ int fmk_trades_refill(fmk_ctx *ctx, fmk_trades *t, const int64_t *ts, const doub
                       const int8_t *side, int64_t n) {
     if (n != t->n) return fmk_fail(ctx, FMK_ERR_ARG, "refill length differs from handle length");
     if (n == 0) return FMK_OK;
-    FMK_CUDA(ctx, cudaMemcpyAsync(t->ts, ts, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (ts && t->ts) FMK_CUDA(ctx, cudaMemcpyAsync(t->ts, ts, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
     FMK_CUDA(ctx, cudaMemcpyAsync(t->price, price, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
     FMK_CUDA(ctx, cudaMemcpyAsync(t->amount, amount, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (side && t->side) FMK_CUDA(ctx, cudaMemcpyAsync(t->side, side, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
@@ -219,7 +220,7 @@ int fmk_trades_refill(fmk_ctx *ctx, fmk_trades *t, const int64_t *ts, const doub
 int fmk_trades_upload(fmk_ctx *ctx, const int64_t *ts, const double *price, const double *amount, const int8_t *side,
                       int64_t n, fmk_trades **out) {
     if (n < 0) return fmk_fail(ctx, FMK_ERR_ARG, "negative length");
-    FMK_TRY(trades_alloc(ctx, n, side != nullptr, out));
+    FMK_TRY(trades_alloc(ctx, n, ts != nullptr, side != nullptr, out));
     int rc = fmk_trades_refill(ctx, *out, ts, price, amount, side, n);
     if (rc) { fmk_trades_free(ctx, *out); *out = nullptr; return rc; }
     // pageable host memory: the copies above are staged synchronously by the runtime, so the caller's arrays can be
@@ -229,7 +230,7 @@ int fmk_trades_upload(fmk_ctx *ctx, const int64_t *ts, const double *price, cons
 
 int fmk_trades_download(fmk_ctx *ctx, const fmk_trades *t, int64_t *ts, double *price, double *amount, int8_t *side) {
     const size_t n = (size_t)t->n;
-    if (ts) FMK_CUDA(ctx, cudaMemcpyAsync(ts, t->ts, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ts && t->ts) FMK_CUDA(ctx, cudaMemcpyAsync(ts, t->ts, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (price) FMK_CUDA(ctx, cudaMemcpyAsync(price, t->price, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (amount) FMK_CUDA(ctx, cudaMemcpyAsync(amount, t->amount, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (side && t->side) FMK_CUDA(ctx, cudaMemcpyAsync(side, t->side, n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -280,6 +281,7 @@ __global__ void k_gather_ts(const int64_t *ts, const int64_t *ci, int64_t m, int
 }
 
 int fmk_gather_close_ts(fmk_ctx *ctx, const fmk_trades *t, fmk_index *ix) {
+    if (!t->ts) return FMK_OK;   // timestamps were not uploaded: the host gathers ts[close_idx] itself
     if (!ix->close_ts) FMK_TRY(fmk_dalloc(ctx, &ix->close_ts, ix->m));
     if (ix->m > 0)
         FMK_LAUNCH(ctx, k_gather_ts, (unsigned)cdiv(ix->m, 256), 256, 0, t->ts, ix->close_idx, ix->m, t->n, ix->close_ts);
@@ -343,6 +345,7 @@ __global__ void k_time_bar(const int64_t *__restrict__ ts, int64_t n, double sta
 extern "C" int fmk_time_bar_index(fmk_ctx *ctx, const fmk_trades *t, double interval_seconds, fmk_index **out) {
     *out = nullptr;
     if (t->n <= 0) return fmk_fail(ctx, FMK_ERR_ARG, "empty trades");
+    if (!t->ts) return fmk_fail(ctx, FMK_ERR_ARG, "time bars need the timestamp column on the device");
     if (!(interval_seconds > 0)) return fmk_fail(ctx, FMK_ERR_ARG, "interval must be positive");
     int64_t ends[2];
     FMK_CUDA(ctx, cudaMemcpyAsync(&ends[0], t->ts, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -472,7 +475,7 @@ __global__ void k_synth_amount(uint64_t seed, int64_t n, double *amt) {
 
 extern "C" int fmk_trades_synth(fmk_ctx *ctx, int64_t n, uint64_t seed, fmk_trades **out) {
     if (n <= 0) return fmk_fail(ctx, FMK_ERR_ARG, "n must be positive");
-    FMK_TRY(trades_alloc(ctx, n, 1, out));
+    FMK_TRY(trades_alloc(ctx, n, 1, 1, out));
     fmk_trades *t = *out;
     int rc = device_inclusive_scan<int64_t>(ctx, GapIn{seed}, TsOut{t->ts}, n, (int64_t *)nullptr);
     if (!rc) rc = device_inclusive_scan<double>(ctx, RetIn{seed}, PxOut{t->price}, n, (double *)nullptr);

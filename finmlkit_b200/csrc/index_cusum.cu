@@ -212,6 +212,7 @@ int fmk_cusum_index_impl(fmk_ctx *ctx, const fmk_trades *t, fmk_buf *sigma, doub
     *out_ix = nullptr;
     const int64_t n = t->n;
     if (n <= 0) return fmk_fail(ctx, FMK_ERR_ARG, "empty trades");
+    if (!t->ts) return fmk_fail(ctx, FMK_ERR_ARG, "CUSUM bars need the timestamp column on the device");
     if (sigma->bytes < n * 8) return fmk_fail(ctx, FMK_ERR_ARG, "Prices, timestamps, and sigma arrays must have the same length.");
     double *sg = (double *)sigma->ptr;
     ctx->stats[0] = ctx->stats[1] = ctx->stats[2] = 0;

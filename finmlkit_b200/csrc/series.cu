@@ -262,6 +262,7 @@ extern "C" int fmk_ewmst(fmk_ctx *ctx, const int64_t *ts, const double *y, int64
 }
 
 extern "C" int fmk_lagged_returns_dev(fmk_ctx *ctx, const fmk_trades *t, double window_sec, int is_log, fmk_buf **out) {
+    if (!t->ts) return fmk_fail(ctx, FMK_ERR_ARG, "lagged returns need the timestamp column on the device");
     FMK_TRY(fmk_buf_alloc(ctx, t->n * 8, out));
     int rc = run_lagged_returns(ctx, t->ts, t->price, t->n, window_sec, is_log, (double *)(*out)->ptr);
     if (rc) { fmk_buf_free(ctx, *out); *out = nullptr; }
@@ -270,6 +271,7 @@ extern "C" int fmk_lagged_returns_dev(fmk_ctx *ctx, const fmk_trades *t, double 
 
 extern "C" int fmk_ewmst_dev(fmk_ctx *ctx, const fmk_trades *t, const fmk_buf *y, double half_life, double sigma_floor,
                              fmk_buf **out) {
+    if (!t->ts) return fmk_fail(ctx, FMK_ERR_ARG, "ewmst needs the timestamp column on the device");
     if (y->bytes < t->n * 8) return fmk_fail(ctx, FMK_ERR_ARG, "y is shorter than the trades");
     FMK_TRY(fmk_buf_alloc(ctx, t->n * 8, out));
     int rc = run_ewmst(ctx, t->ts, (const double *)y->ptr, t->n, half_life, sigma_floor, (double *)(*out)->ptr);
@@ -378,6 +380,7 @@ extern "C" int fmk_triple_barrier(fmk_ctx *ctx, const fmk_trades *t, const int64
     if (ne == 0) return fmk_fail(ctx, FMK_ERR_ARG, "The event_idxs array must not be empty.");
     if (side && n_side != ne) return fmk_fail(ctx, FMK_ERR_ARG, "The length of event_idxs must match the length of side.");
     const int64_t n = t->n;
+    if (!t->ts) return fmk_fail(ctx, FMK_ERR_ARG, "triple_barrier needs the timestamp column on the device");
     // event indices must address the trade arrays (the reference would read out of bounds / wrap)
     for (int64_t e = 0; e < ne; e++)
         if (event_idx[e] < 0 || event_idx[e] >= n) return fmk_fail(ctx, FMK_ERR_ARG, "event index out of range");

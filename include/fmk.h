@@ -60,7 +60,9 @@ int fmk_host_alloc(void **out, int64_t bytes);
 void fmk_host_free(void *p);
 
 /* ---- trades: TradesData columns (bar/data_model.py:121-244) as device SoA --------------------------------------- */
-/* side may be NULL (directional/footprint calls then fail with FMK_ERR_ARG). amount is float64. */
+/* side may be NULL (directional/footprint calls then fail with FMK_ERR_ARG). amount is float64.
+ * ts may be NULL for tick/volume/dollar bars + reductions: close timestamps are then gathered by the host from its own
+ * array (ts[close_idx]), which saves a third of the H2D traffic; time/CUSUM bars, lagged returns, ewmst and TBM need ts. */
 int fmk_trades_upload(fmk_ctx *ctx, const int64_t *ts, const double *price, const double *amount, const int8_t *side,
                       int64_t n, fmk_trades **out);
 /* Device-side synthetic BTCUSDT-like stream (SURVEY 8d shape) for bench-size runs. */
