@@ -122,6 +122,7 @@ struct DollarParams {
     double T, u, top_lim, sub_lim;  // u = ulp(T); top_lim = 4*2^e; sub_lim = 2*2^e
     double margin0;                 // 2^(e-35): distance guaranteed by the coarse per-tick tests
     uint32_t hi_tiny, hi_near, hi_top, hi_sub;   // high words of 2^(e-24), 2^(e-34), top_lim, sub_lim
+    uint32_t eTb;                                // biased exponent of T
     int64_t n, CH, cap;
 };
 
@@ -140,6 +141,7 @@ DC_HD bool dollar_params_init(DollarParams *P, double T, int64_t n, int64_t CH, 
     P->hi_near = dc_hi(pow2 * 5.820766091346741e-11);       // 2^-34
     P->hi_top = dc_hi(P->top_lim);
     P->hi_sub = dc_hi(P->sub_lim);
+    P->eTb = (uint32_t)(b >> 52) & 0x7FFu;
     return true;
 }
 
@@ -182,17 +184,49 @@ DC_HD bool dollar_chain_tick(double &c, double d, const DollarParams &P, uint64_
     return false;
 }
 
-// Per-task state machine.  Ticks are fed in order with consume(); the same code runs on the host (CPU emulation in
-// tests/cpu) and in k_dollar_tasks, where the ticks come from a shared-memory staging tile.
+// ---- virtual chains ------------------------------------------------------------------------------------------
+// Replaying four chains costs four dependent float recurrences per tick.  But the chains differ only by small
+// multiples of u, and translation by a multiple of u commutes with a float add EXCEPT at three kinds of "residue
+// sensitive" adds, all of which can be recognised from chain 0 alone:
+//   (b) result in T's binade (ulp u) and the exact sum is a tie (|err| == u/2): ties-to-even sends odd offsets the
+//       other way  ->  o' = o + sign(err) for odd o;
+//   (c) result one binade above T (ulp 2u): the result is 2u * rhe((X0 + o)/2), derived from chain 0's result R,
+//       sign(err) and whether |err| == u;
+//   (a) result below T's binade (ulp <= u/2): never sensitive.
+// So only chain 0 is run in floating point; the other three are integer offsets o[rho] (units of u) relative to it,
+// updated in a rare branch that needs the TwoSum error of the add.  A cheap integer pre-filter (is d's fraction
+// w.r.t. u exactly one half?  did the binade change?  is the result above T's binade?) guards that branch.
+// DC_EXPLICIT_CHAINS keeps the four explicit chains (reference implementation for the CPU cross-check).
 struct DollarTask {
+#ifdef DC_EXPLICIT_CHAINS
     double c[DC_NCH];
     uint64_t mb[DC_NCH];
     bool bad[DC_NCH];
+#else
+    double c[1];
+    uint64_t mb[1];
+    bool bad[1];
+    int32_t o[DC_NCH];   // virtual chain offsets relative to chain 0, in units of u
+#endif
     double x;            // phase 1: approximate carry
     int64_t B, K, cnt, end_idx, hi, start_units;
     int nch, phase;      // phase 1: locating the first boundary; 2: exact replay; 3: finished
     bool last_chunk;
 };
+
+#ifdef DC_EXPLICIT_CHAINS
+constexpr int DC_NSIM = DC_NCH;
+#else
+constexpr int DC_NSIM = 1;
+#endif
+
+DC_HD int dc_ffsll(uint64_t x) {
+#ifdef __CUDA_ARCH__
+    return __ffsll((long long)x);
+#else
+    return __builtin_ffsll((long long)x);
+#endif
+}
 
 // first tick the task wants to see
 DC_HD int64_t dollar_task_init(DollarTask &t, const DollarParams &P, int64_t k, double carry_in, int64_t K_in, double d0) {
@@ -200,7 +234,10 @@ DC_HD int64_t dollar_task_init(DollarTask &t, const DollarParams &P, int64_t k, 
     t.hi = lo + P.CH < P.n ? lo + P.CH : P.n;
     t.last_chunk = t.hi >= P.n;
     t.B = -1; t.K = K_in; t.cnt = 0; t.end_idx = -2; t.start_units = 0; t.x = carry_in;
-    for (int r = 0; r < DC_NCH; r++) { t.mb[r] = dc_bits(P.margin0); t.bad[r] = false; t.c[r] = 0.0; }
+    for (int r = 0; r < DC_NSIM; r++) { t.mb[r] = dc_bits(P.margin0); t.bad[r] = false; t.c[r] = 0.0; }
+#ifndef DC_EXPLICIT_CHAINS
+    for (int r = 0; r < DC_NCH; r++) t.o[r] = r;
+#endif
     if (k == 0) {
         t.B = 0; t.K = 0; t.nch = 1; t.phase = 2;
         t.c[0] = d0;                 // exact start: cum = prices[0] * volumes[0]
@@ -209,6 +246,87 @@ DC_HD int64_t dollar_task_init(DollarTask &t, const DollarParams &P, int64_t k, 
     t.nch = DC_NCH; t.phase = 1;
     return lo;
 }
+
+#ifndef DC_EXPLICIT_CHAINS
+// rare branch of the virtual-chain tick: update the offsets at a residue-sensitive add (c + d -> r)
+DC_HD void dollar_virtual_update(DollarTask &t, const DollarParams &P, double c, double d, double r, bool in_upper) {
+    // TwoSum error: err = (c + d) - r exactly
+    const double bb = dc_sub(r, c);
+    const double err = dc_add(dc_sub(c, dc_sub(r, bb)), dc_sub(d, bb));
+    const int sd = err > 0.0 ? 1 : (err < 0.0 ? -1 : 0);
+    const double ae = fabs(err);
+    if (!in_upper) {
+        // (b) ulp(r) == u: only an exact tie is residue sensitive
+        if (ae == 0.5 * P.u) {
+            for (int q = 1; q < DC_NCH; q++) if (t.o[q] & 1) t.o[q] += sd;
+        }
+    } else {
+        // (c) ulp(r) == 2u: r = 2u*R, exact sum = 2u*(R + delta), delta = err/(2u) in [-1/2, 1/2]
+        const int64_t R = (int64_t)(r / (2.0 * P.u));
+        const int Rpar = (int)(R & 1);
+        const bool half = (ae == P.u);
+        for (int q = 1; q < DC_NCH; q++) {
+            const int o = t.o[q];
+            const int a = o >> 1, b = o & 1;     // o = 2a + b, b in {0,1} (arithmetic shift = floor)
+            int res;
+            if (b == 0) {
+                if (!half) res = a;
+                else res = (((Rpar + a) & 1) == 0) ? a : a + sd;          // tie at (R+a) + sd/2 -> even
+            } else {
+                if (half) res = a + (sd > 0 ? 1 : 0);                      // delta + 1/2 is exactly 0 or 1
+                else if (sd < 0) res = a;
+                else if (sd > 0) res = a + 1;
+                else res = (((Rpar + a) & 1) == 0) ? a : a + 1;           // exact tie at (R+a) + 1/2 -> even
+            }
+            t.o[q] = 2 * res;
+        }
+    }
+    for (int q = 1; q < DC_NCH; q++) if (t.o[q] > 32 || t.o[q] < -32) t.bad[0] = true;
+}
+
+DC_HD bool dollar_virtual_tick(DollarTask &t, double d, const DollarParams &P) {
+    const double c = t.c[0];
+    const double r = dc_add(c, d);
+    const double c2 = dc_sub(r, P.T);
+    const uint32_t hr = dc_hi(r);
+    const uint32_t hcp = dc_hi(c);
+    const uint32_t hc = dc_hi(c2) & 0x7FFFFFFFu;
+    const bool rare_m = (((hr + 0x400u) & 0xFF800u) == 0u) | (hr < P.hi_tiny) | (hr >= P.hi_top) | (hc < P.hi_near);
+    // residue-sensitivity pre-filter
+    const uint32_t eb = hr >> 20;                         // sign + biased exponent of r
+    const bool in_upper = eb > P.eTb;                     // r >= 2^(e+1)
+    const bool in_top = eb == P.eTb;
+    const bool crossing = ((hr ^ hcp) >> 20) != 0u;
+    const uint64_t db = dc_bits(d);
+    const uint32_t ed = (uint32_t)(db >> 52) & 0x7FFu;
+    const uint64_t md = (db & 0x000FFFFFFFFFFFFFull) | (ed ? 0x0010000000000000ull : 0ull);
+    const bool dtie = (uint32_t)dc_ffsll(md) + ed == P.eTb;   // fraction of d/u is exactly one half
+    const bool sens = in_upper | (in_top & (dtie | crossing));
+    if (rare_m | sens) {
+        if (rare_m) {
+            const uint64_t rb = dc_bits(r);
+            const double lowb = dc_from_bits(rb & 0xFFF0000000000000ull);
+            const double dlo = dc_sub(r, lowb);
+            const double dhi = dc_sub(lowb, dlo);
+            const double am = fabs(c2);
+            uint64_t m = t.mb[0], x;
+            x = dc_bits(dlo); m = x < m ? x : m;
+            x = dc_bits(dhi); m = x < m ? x : m;
+            x = dc_bits(am);  m = x < m ? x : m;
+            t.mb[0] = m;
+            if (!(r >= 0.0) || !(r < P.top_lim)) t.bad[0] = true;
+        }
+        if (sens && t.nch == DC_NCH && r < P.top_lim) dollar_virtual_update(t, P, c, d, r, in_upper);
+    }
+    if (r >= P.T) {
+        if (dc_hi(c2) >= P.hi_sub) t.bad[0] = true;
+        t.c[0] = c2;
+        return true;
+    }
+    t.c[0] = r;
+    return false;
+}
+#endif
 
 // Feed tick i (d = fl(p_i * v_i)).  Returns true when the task is finished.
 DC_HD bool dollar_task_consume(DollarTask &t, const DollarParams &P, int64_t i, double d, int64_t *out) {
@@ -221,27 +339,31 @@ DC_HD bool dollar_task_consume(DollarTask &t, const DollarParams &P, int64_t i, 
             double units = rint(t.x / P.u);
             if (!(units >= 0)) units = 0;
             t.start_units = (int64_t)units;
-            for (int r = 0; r < DC_NCH; r++) {
+            for (int r = 0; r < DC_NSIM; r++) {
                 t.c[r] = dc_mul((double)(t.start_units + r), P.u);
                 // the start must be exactly representable (it is unless units ~ 2^53)
                 if (t.c[r] / P.u != (double)(t.start_units + r)) t.bad[r] = true;
             }
+#ifndef DC_EXPLICIT_CHAINS
+            if (!(units < 4503599627370000.0)) t.bad[0] = true;   // start + 3 must stay below 2^52
+#endif
             t.phase = 2;
             return false;
         }
         if (i + 1 >= t.hi) { t.phase = 3; return true; }   // no boundary located in this chunk: empty task
         return false;
     }
+#ifdef DC_EXPLICIT_CHAINS
     const bool e0 = dollar_chain_tick(t.c[0], d, P, t.mb[0], t.bad[0]);
     if (t.nch == DC_NCH) {
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
         for (int r = 1; r < DC_NCH; r++) {
             const bool er = dollar_chain_tick(t.c[r], d, P, t.mb[r], t.bad[r]);
             if (er != e0) t.bad[r] = true;
         }
     }
+#else
+    const bool e0 = dollar_virtual_tick(t, d, P);
+#endif
     if (e0) {
         t.cnt++;
         if (t.K + t.cnt < P.cap) out[t.K + t.cnt] = i;   // speculative writes stay in bounds; cap bounds the true count
@@ -254,6 +376,7 @@ DC_HD void dollar_task_finish(const DollarTask &t, const DollarParams &P, Dollar
     rec->start_idx = t.B; rec->k_start = t.B >= 0 ? t.K : 0; rec->end_idx = t.end_idx; rec->count = t.cnt;
     rec->start_units = t.start_units; rec->nch = t.nch;
     int32_t bm = 0;
+#ifdef DC_EXPLICIT_CHAINS
     for (int r = 0; r < DC_NCH; r++) {
         rec->end_units[r] = 0;
         rec->margin[r] = dc_from_bits(t.mb[r]);
@@ -265,6 +388,23 @@ DC_HD void dollar_task_finish(const DollarTask &t, const DollarParams &P, Dollar
         }
         if (bad) bm |= (1 << r);
     }
+#else
+    bool bad = t.bad[0];
+    int64_t e0 = 0;
+    if (t.end_idx >= 0) {
+        const double eu = t.c[0] / P.u;              // exact when c is a multiple of u below 2^(e+1)
+        e0 = (int64_t)eu;
+        if ((double)e0 != eu || dc_mul(eu, P.u) != t.c[0]) bad = true;
+    }
+    // the virtual chains sit within 32u of chain 0: certify them against chain 0's margin minus that slack
+    double m = dc_from_bits(t.mb[0]) - 64.0 * P.u;
+    if (!(m > 0.0)) m = 0.0;
+    for (int r = 0; r < DC_NCH; r++) {
+        rec->end_units[r] = e0 + (r < t.nch ? t.o[r] : 0);
+        rec->margin[r] = (r == 0) ? dc_from_bits(t.mb[0]) : m;
+        if (bad) bm |= (1 << r);
+    }
+#endif
     rec->bad = bm;
 }
 
@@ -352,7 +492,8 @@ DC_HD int dollar_walk_step(const DollarTaskRec &t, double u, DollarWalk &w, bool
     const int rho = (int)(delta & 3);
     const int64_t D = delta - rho;
     if ((t.bad >> rho) & 1) return 2;
-    if (D != 0) {
+    if (D != 0 || rho != 0) {
+        // rho != 0: the chain is a translate of chain 0 by a few u even when D == 0, so it needs a positive margin too
         double ad = fabs((double)D) * u;
         if (!(ad < t.margin[rho])) return 2;
     }

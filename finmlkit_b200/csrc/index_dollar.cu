@@ -10,6 +10,7 @@
 #include <new>
 #include "common.cuh"
 #include "dollar_core.h"
+#include "scan.cuh"
 
 constexpr int DOLLAR_CH = 2048;
 constexpr int DOLLAR_A_THREADS = 256;
@@ -47,63 +48,48 @@ __global__ void __launch_bounds__(DOLLAR_A_THREADS) k_dollar_chunk_sums(const do
     }
 }
 
-// single block: exclusive dd scan over chunk sums; emits the (K_in, carry) guess per chunk and the grand total
-constexpr int DOLLAR_P_THREADS = 1024;
-__global__ void __launch_bounds__(DOLLAR_P_THREADS) k_dollar_prefix(const dd_t *__restrict__ sums, int64_t nt, double T,
-                                                                    int64_t *__restrict__ K_in,
-                                                                    double *__restrict__ carry, dd_t *total) {
-    __shared__ dd_t wsum[DOLLAR_P_THREADS / 32];
-    const int64_t per = (nt + DOLLAR_P_THREADS - 1) / DOLLAR_P_THREADS;
-    const int64_t a = (int64_t)threadIdx.x * per;
-    int64_t b = a + per;
-    if (b > nt) b = nt;
-    dd_t s = {0.0, 0.0};
-    for (int64_t k = a; k < b; k++) s = dd_add(s, sums[k]);
-    // block-wide exclusive scan of the per-thread sums (warp shuffles, then the 32 warp totals)
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    dd_t inc = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        dd_t y;
-        y.hi = __shfl_up_sync(0xffffffffu, inc.hi, o);
-        y.lo = __shfl_up_sync(0xffffffffu, inc.lo, o);
-        if (lane >= o) inc = dd_add(y, inc);
-    }
-    if (lane == 31) wsum[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-        dd_t x = wsum[lane];
-        dd_t xi = x;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            dd_t y;
-            y.hi = __shfl_up_sync(0xffffffffu, xi.hi, o);
-            y.lo = __shfl_up_sync(0xffffffffu, xi.lo, o);
-            if (lane >= o) xi = dd_add(y, xi);
-        }
-        if (lane == 31) *total = xi;
-        // exclusive warp offsets
-        dd_t ex;
-        ex.hi = __shfl_up_sync(0xffffffffu, xi.hi, 1);
-        ex.lo = __shfl_up_sync(0xffffffffu, xi.lo, 1);
-        if (lane == 0) { ex.hi = 0.0; ex.lo = 0.0; }
-        wsum[lane] = ex;
-    }
-    __syncthreads();
-    dd_t ex;
-    ex.hi = __shfl_up_sync(0xffffffffu, inc.hi, 1);
-    ex.lo = __shfl_up_sync(0xffffffffu, inc.lo, 1);
-    if (lane == 0) { ex.hi = 0.0; ex.lo = 0.0; }
-    dd_t run = dd_add(wsum[w], ex);
-    for (int64_t k = a; k < b; k++) {
-        int64_t K;
-        double c;
-        dollar_guess(run, T, &K, &c);
-        K_in[k] = K;
-        carry[k] = c;
-        run = dd_add(run, sums[k]);
-    }
+// Exclusive double-double scan over the chunk sums (scan.cuh, 3 small grid-wide kernels) -> the (K_in, carry) guess of
+// every chunk and the grand total.
+struct DD {
+    double hi, lo;
+    __device__ DD() {}
+    __device__ explicit DD(int) { hi = 0.0; lo = 0.0; }
+};
+__device__ __forceinline__ DD operator+(const DD &a, const DD &b) {
+    dd_t x = {a.hi, a.lo}, y = {b.hi, b.lo};
+    dd_t r = dd_add(x, y);
+    DD o;
+    o.hi = r.hi; o.lo = r.lo;
+    return o;
 }
+__device__ __forceinline__ DD __shfl_up_sync(unsigned m, const DD &x, int o) {
+    DD r;
+    r.hi = ::__shfl_up_sync(m, x.hi, o);
+    r.lo = ::__shfl_up_sync(m, x.lo, o);
+    return r;
+}
+struct SumIn {
+    const dd_t *s;
+    __device__ DD operator()(int64_t k) const { DD d; d.hi = s[k].hi; d.lo = s[k].lo; return d; }
+};
+struct GuessOut {
+    int64_t *K_in;
+    double *carry;
+    int64_t nt;
+    double T;
+    __device__ void operator()(int64_t k, const DD &incl) const {
+        // inclusive prefix through chunk k = exclusive prefix of chunk k+1
+        if (k == 0) { K_in[0] = 0; carry[0] = 0.0; }
+        if (k + 1 < nt) {
+            dd_t P = {incl.hi, incl.lo};
+            int64_t K;
+            double c;
+            dollar_guess(P, T, &K, &c);
+            K_in[k + 1] = K;
+            carry[k + 1] = c;
+        }
+    }
+};
 
 // One lane per task; a warp's 32 tasks stream their ticks through a shared-memory tile that the warp fills with
 // coalesced loads (row r = the next DT_R ticks of lane r's task), so HBM sees full 128-byte requests even though
@@ -361,9 +347,11 @@ int fmk_dollar_index_impl(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index
     int64_t cap = n + 1;
     if (fast) {
         FMK_LAUNCH(ctx, k_dollar_chunk_sums, (unsigned)nt, DOLLAR_A_THREADS, 0, t->price, t->amount, n, sums.p);
-        FMK_LAUNCH(ctx, k_dollar_prefix, 1, DOLLAR_P_THREADS, 0, sums.p, nt, T, K_in.p, carry.p, sums.p + nt);
+        Scratch<DD> dtot(ctx);
+        FMK_TRY(dtot.alloc(1));
+        FMK_TRY((device_inclusive_scan<DD>(ctx, SumIn{sums.p}, GuessOut{K_in.p, carry.p, nt, T}, nt, dtot.p)));
         dd_t total;
-        FMK_CUDA(ctx, cudaMemcpyAsync(&total, sums.p + nt, sizeof(dd_t), cudaMemcpyDeviceToHost, ctx->stream));
+        FMK_CUDA(ctx, cudaMemcpyAsync(&total, dtot.p, sizeof(dd_t), cudaMemcpyDeviceToHost, ctx->stream));
         FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         // every emission removes T from a non-negative running sum, so count <= total/T (+ slack for rounding)
         double bound = total.hi / T;

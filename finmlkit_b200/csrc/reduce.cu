@@ -196,10 +196,22 @@ __device__ void warp_select_two(const double *__restrict__ a, int64_t cnt, int64
         }
         // diff pass
         unsigned long long orv = 0ull, andv = ~0ull, amin = ~0ull;
-        for (int64_t j = lane; j < cnt; j += 32) {
-            const unsigned long long key = dkey(__ldg(a + j));
-            if ((key & mask) == prefix) { orv |= key; andv &= key; }
-            else if (key > hi_bound && key < amin) amin = key;
+        {
+            int64_t j = lane;
+            for (; j + 96 < cnt; j += 128) {   // 4 independent loads in flight per lane
+                const double x0 = __ldg(a + j), x1 = __ldg(a + j + 32), x2 = __ldg(a + j + 64), x3 = __ldg(a + j + 96);
+                const unsigned long long ks[4] = {dkey(x0), dkey(x1), dkey(x2), dkey(x3)};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if ((ks[q] & mask) == prefix) { orv |= ks[q]; andv &= ks[q]; }
+                    else if (ks[q] > hi_bound && ks[q] < amin) amin = ks[q];
+                }
+            }
+            for (; j < cnt; j += 32) {
+                const unsigned long long key = dkey(__ldg(a + j));
+                if ((key & mask) == prefix) { orv |= key; andv &= key; }
+                else if (key > hi_bound && key < amin) amin = key;
+            }
         }
         orv = warp_or64(orv); andv = warp_and64(andv);
         const unsigned long long diff = orv ^ andv;
@@ -213,9 +225,19 @@ __device__ void warp_select_two(const double *__restrict__ a, int64_t cnt, int64
         const int shift = hb >= 7 ? hb - 7 : 0;
         for (int b = lane; b < 256; b += 32) hist[b] = 0u;
         __syncwarp();
-        for (int64_t j = lane; j < cnt; j += 32) {
-            const unsigned long long key = dkey(__ldg(a + j));
-            if ((key & mask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+        {
+            int64_t j = lane;
+            for (; j + 96 < cnt; j += 128) {
+                const double x0 = __ldg(a + j), x1 = __ldg(a + j + 32), x2 = __ldg(a + j + 64), x3 = __ldg(a + j + 96);
+                const unsigned long long ks[4] = {dkey(x0), dkey(x1), dkey(x2), dkey(x3)};
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if ((ks[q] & mask) == prefix) atomicAdd(&hist[(unsigned)(ks[q] >> shift) & 255u], 1u);
+            }
+            for (; j < cnt; j += 32) {
+                const unsigned long long key = dkey(__ldg(a + j));
+                if ((key & mask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+            }
         }
         __syncwarp();
         // bucket holding rank kk: each lane owns 8 consecutive bins

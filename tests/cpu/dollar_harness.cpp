@@ -7,6 +7,33 @@
 
 struct Ld { const double *a; double operator()(int64_t i) const { return a[i]; } };
 
+// per-task records only (pass A + B), for the explicit-vs-virtual chain cross-check:
+// rec_out[k*10 + ...] = start_idx, end_idx, count, start_units, end_units[0..3], bad, nch
+extern "C" int64_t dollar_task_records(const double *p, const double *v, int64_t n, double T, int64_t CH, int64_t *rec_out,
+                                       double *margin_out) {
+    DollarParams P;
+    if (!dollar_params_init(&P, T, n, CH, n + 2)) return -1;
+    Ld lp{p}, lv{v};
+    std::vector<int64_t> out(n + 2);
+    const int64_t nt = (n + CH - 1) / CH;
+    dd_t run = {0.0, 0.0};
+    for (int64_t k = 0; k < nt; k++) {
+        int64_t K_in = 0; double carry = 0;
+        if (k > 0) dollar_guess(run, T, &K_in, &carry);
+        DollarTaskRec r;
+        dollar_task(lp, lv, P, k, carry, K_in, out.data(), &r);
+        int64_t *o = rec_out + k * 10;
+        o[0] = r.start_idx; o[1] = r.end_idx; o[2] = r.count; o[3] = r.start_units;
+        for (int q = 0; q < 4; q++) { o[4 + q] = r.end_units[q]; margin_out[k * 4 + q] = r.margin[q]; }
+        o[8] = r.bad; o[9] = r.nch;
+        int64_t hi = (k + 1) * CH < n ? (k + 1) * CH : n;
+        dd_t s = {0.0, 0.0};
+        for (int64_t i = k * CH; i < hi; i++) s = dd_add_d(s, p[i] * v[i]);
+        run = dd_add(run, s);
+    }
+    return nt;
+}
+
 extern "C" int64_t dollar_emulate(const double *p, const double *v, int64_t n, double T, int64_t CH, int64_t *out,
                                   int64_t cap, int64_t *stats) {
     DollarParams P;

@@ -32,6 +32,49 @@ def harness(tmp_path_factory):
     return emu
 
 
+def _build(tmp, name, extra):
+    so = str(tmp / name)
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", *extra, "-o", so,
+                           os.path.join(HERE, "cpu", "dollar_harness.cpp")])
+    lib = C.CDLL(so)
+    lib.dollar_task_records.restype = C.c_int64
+
+    def recs(p, v, T, CH):
+        p, v = np.ascontiguousarray(p, np.float64), np.ascontiguousarray(v, np.float64)
+        nt = (len(p) + CH - 1) // CH
+        r = np.zeros((nt, 10), np.int64)
+        m = np.zeros((nt, 4), np.float64)
+        got = lib.dollar_task_records(p.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), C.c_int64(len(p)), C.c_double(T),
+                                      C.c_int64(CH), r.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p))
+        assert got == nt
+        return r, m
+    return recs
+
+
+@pytest.mark.parametrize("T,CH", [(1e6, 2048), (1e5, 512), (1048575.0, 512), (float(2 ** 20), 512), (3e4, 257), (1040000.0, 300)])
+def test_virtual_chains_equal_explicit_chains(tmp_path_factory, stream, T, CH):
+    """The shipped core runs ONE float chain plus integer offsets for the other three residues; the reference build
+    (-DDC_EXPLICIT_CHAINS) runs all four chains explicitly.  Wherever the explicit chain rho is usable, the virtual
+    chain must report the same end state."""
+    tmp = tmp_path_factory.mktemp("xchk")
+    virt = _build(tmp, "virt.so", [])
+    expl = _build(tmp, "expl.so", ["-DDC_EXPLICIT_CHAINS"])
+    _, p, v, _ = stream
+    rv, mv = virt(p, v, T, CH)
+    re_, me = expl(p, v, T, CH)
+    assert np.array_equal(rv[:, :4], re_[:, :4])          # same starts / ends / counts / start state
+    checked = 0
+    for k in range(1, len(rv)):
+        if rv[k, 0] < 0 or rv[k, 1] < 0:
+            continue
+        for rho in range(4):
+            if (re_[k, 8] >> rho) & 1 or (rv[k, 8] >> rho) & 1:
+                continue
+            assert rv[k, 4 + rho] == re_[k, 4 + rho], (k, rho, rv[k], re_[k])
+            checked += 1
+    assert checked > 0
+
+
 @pytest.fixture(scope="module")
 def stream():
     return synth_trades(400_000, seed=3)
