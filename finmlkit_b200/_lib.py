@@ -65,6 +65,10 @@ SIGNATURES = {
     "fmk_ewmst": (INT, [P, P, P, I64, F64, F64, P]),
     "fmk_lagged_returns_dev": (INT, [P, P, F64, INT, C.POINTER(P)]),
     "fmk_ewmst_dev": (INT, [P, P, P, F64, F64, C.POINTER(P)]),
+    "fmk_realized_vol": (INT, [P, P, I64, I64, INT, P]),
+    "fmk_ewms": (INT, [P, P, I64, I64, P]),
+    "fmk_vpin": (INT, [P, P, P, I64, I64, P]),
+    "fmk_flow_acceleration": (INT, [P, P, I64, I64, I64, P]),
     "fmk_triple_barrier": (INT, [P, P, P, P, I64, I64, F64, F64, F64, F64, P, I64, F64, P, P, P, P]),
 }
 

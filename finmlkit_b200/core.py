@@ -320,3 +320,36 @@ def triple_barrier_dev(trades: DeviceTrades, event_idxs, targets, horizontal_bar
                                         float(min_close_time_sec), _ptr(sd), len(sd) if sd is not None else 0, float(min_ret),
                                         _ptr(labels), _ptr(touch), _ptr(rets), _ptr(ratios)))
     return labels, touch, rets, ratios
+
+
+# ---- bar-level features (n_bars-length arrays) -----------------------------------------------------------------------
+def realized_vol_series(r, window, is_sample, ctx: Context = None):
+    ctx = ctx or default_context()
+    rr = _c(r, np.float64)
+    out = np.empty(len(rr))
+    ctx.check(ctx._L.fmk_realized_vol(ctx.h, _ptr(rr), len(rr), int(window), int(bool(is_sample)), _ptr(out)))
+    return out
+
+
+def ewms_series(y, span, ctx: Context = None):
+    ctx = ctx or default_context()
+    yy = _c(y, np.float64)
+    out = np.empty(len(yy))
+    ctx.check(ctx._L.fmk_ewms(ctx.h, _ptr(yy), len(yy), int(span), _ptr(out)))
+    return out
+
+
+def vpin_series(volume_buy, volume_sell, window, ctx: Context = None):
+    ctx = ctx or default_context()
+    b, s = _c(volume_buy, np.float64), _c(volume_sell, np.float64)
+    out = np.empty(len(b), np.float32)
+    ctx.check(ctx._L.fmk_vpin(ctx.h, _ptr(b), _ptr(s), len(b), int(window), _ptr(out)))
+    return out
+
+
+def flow_acceleration_series(volumes, window, recent_periods, ctx: Context = None):
+    ctx = ctx or default_context()
+    v = _c(volumes, np.float64)
+    out = np.empty(len(v))
+    ctx.check(ctx._L.fmk_flow_acceleration(ctx.h, _ptr(v), len(v), int(window), int(recent_periods), _ptr(out)))
+    return out

@@ -136,6 +136,14 @@ int fmk_lagged_returns_dev(fmk_ctx *ctx, const fmk_trades *t, double window_sec,
 int fmk_ewmst_dev(fmk_ctx *ctx, const fmk_trades *t, const fmk_buf *y, double half_life, double sigma_floor,
                   fmk_buf **out);
 
+/* ---- bar-level features on n_bars-length host arrays ------------------------------------------------- */
+int fmk_realized_vol(fmk_ctx *ctx, const double *r, int64_t n, int64_t window, int is_sample, double *out);   /* volatility.py:256-286 */
+int fmk_ewms(fmk_ctx *ctx, const double *y, int64_t n, int64_t span, double *out);                               /* volatility.py:9-69 */
+int fmk_vpin(fmk_ctx *ctx, const double *volume_buy, const double *volume_sell, int64_t n, int64_t window,
+             float *out);                                                                                         /* volume.py:610-641 */
+int fmk_flow_acceleration(fmk_ctx *ctx, const double *volumes, int64_t n, int64_t window, int64_t recent_periods,
+                          double *out);                                                                           /* volume.py:572-607 */
+
 /* ---- labels: triple_barrier, label/tbm.py:11-158 ------------------------------------------------------------------
  * side may be NULL (side prediction). Skipped events get touch_idx = event_idx (the reference leaves it uninitialised). */
 int fmk_triple_barrier(fmk_ctx *ctx, const fmk_trades *t, const int64_t *event_idx, const double *targets,

@@ -230,3 +230,31 @@ def triple_barrier(timestamps, close, event_idxs, targets, horizontal_barriers, 
     if rc:
         raise ValueError(ERRORS[rc])
     return labels, touch, rets, ratios
+
+
+def realized_vol(r, window, is_sample):
+    rr = _f64(r)
+    out = np.empty(len(rr))
+    lib().fmko_realized_vol(_p(rr), C.c_int64(len(rr)), C.c_int64(int(window)), C.c_int(bool(is_sample)), _p(out))
+    return out
+
+
+def ewms(y, span):
+    yy = _f64(y)
+    out = np.empty(len(yy))
+    lib().fmko_ewms(_p(yy), C.c_int64(len(yy)), C.c_int64(int(span)), _p(out))
+    return out
+
+
+def vpin(volume_buy, volume_sell, window):
+    b, s = _f64(volume_buy), _f64(volume_sell)
+    out = np.empty(len(b), np.float32)
+    lib().fmko_vpin(_p(b), _p(s), C.c_int64(len(b)), C.c_int64(int(window)), _p(out))
+    return out
+
+
+def comp_flow_acceleration(volumes, window, recent_periods):
+    v = _f64(volumes)
+    out = np.empty(len(v))
+    lib().fmko_flow_acceleration(_p(v), C.c_int64(len(v)), C.c_int64(int(window)), C.c_int64(int(recent_periods)), _p(out))
+    return out

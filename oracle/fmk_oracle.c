@@ -575,3 +575,87 @@ int fmko_triple_barrier(const int64_t *ts, const double *close, int64_t n, int64
     free(lc);
     return FMKO_OK;
 }
+
+/* ---- a15: bar-level volatility / order-flow features ------------------------------------------------------------ */
+/* feature/core/volatility.py:256-286 realized_vol */
+int fmko_realized_vol(const double *r, int64_t n, int64_t window, int is_sample, double *out) {
+    for (int64_t i = 0; i < n; i++) out[i] = NAN;
+    if (window < 1) return FMKO_OK;
+    #pragma omp parallel for schedule(static)
+    for (int64_t i = window - 1; i < n; i++) {
+        int64_t valid = 0;
+        for (int64_t j = i - window + 1; j <= i; j++) if (!isnan(r[j])) valid++;
+        if (valid > 1) {
+            double s = 0.0;                      /* np.nansum(r_window ** 2): sequential, NaN counted as 0 */
+            for (int64_t j = i - window + 1; j <= i; j++) { double x = r[j] * r[j]; if (!isnan(x)) s += x; }
+            int64_t div = is_sample ? valid - 1 : valid;
+            out[i] = sqrt(s / (double)div);
+        }
+    }
+    return FMKO_OK;
+}
+
+/* feature/core/volatility.py:9-69 ewms */
+int fmko_ewms(const double *y, int64_t n, int64_t span, double *out) {
+    if (span <= 1) { for (int64_t i = 0; i < n; i++) out[i] = NAN; return FMKO_OK; }
+    double alpha = 2.0 / ((double)span + 1.0), om = 1.0 - alpha;
+    double Sw = 0, Sw2 = 0, Sy = 0, Sy2 = 0;
+    for (int64_t t = 0; t < n; t++) {
+        double yt = y[t];
+        int nan = isnan(yt);
+        Sw = om * Sw + (nan ? 0.0 : 1.0);
+        Sw2 = (om * om) * Sw2 + (nan ? 0.0 : 1.0);
+        if (!nan) { Sy = om * Sy + yt; Sy2 = om * Sy2 + yt * yt; }
+        else { Sy = om * Sy; Sy2 = om * Sy2; }
+        if (Sw > 0.0) {
+            double mean = Sy / Sw;
+            double den = Sw - (Sw2 / Sw);
+            if (den > 0.0) {
+                double var = (Sy2 / Sw - mean * mean) * Sw / den;
+                if (!(var > 0.0)) var = (var != var) ? var : 0.0;   /* python max(var, 0.0): 0.0 only if 0.0 > var */
+                out[t] = sqrt(var);
+            } else out[t] = NAN;
+        } else out[t] = NAN;
+    }
+    return FMKO_OK;
+}
+
+/* feature/core/volume.py:610-641 vpin (float32 output) */
+int fmko_vpin(const double *vb, const double *vs, int64_t n, int64_t window, float *out) {
+    double *bc = (double *)malloc(sizeof(double) * (size_t)(n + 1)), *sc = (double *)malloc(sizeof(double) * (size_t)(n + 1));
+    double *ac = (double *)malloc(sizeof(double) * (size_t)(n + 1));
+    int64_t *nf = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 1));
+    bc[0] = sc[0] = ac[0] = 0.0; nf[0] = 0;
+    for (int64_t i = 0; i < n; i++) {
+        out[i] = NAN;
+        double b = vb[i], s = vs[i];
+        int nan = isnan(b) || isnan(s);
+        bc[i + 1] = bc[i] + (nan ? 0.0 : b);
+        sc[i + 1] = sc[i] + (nan ? 0.0 : s);
+        ac[i + 1] = ac[i] + (nan ? 0.0 : fabs(b - s));
+        nf[i + 1] = nf[i] + nan;
+        if (i >= window - 1 && nf[i + 1] - nf[i + 1 - window] == 0) {
+            double tot = (bc[i + 1] - bc[i + 1 - window]) + (sc[i + 1] - sc[i + 1 - window]);
+            if (tot > 1e-9) out[i] = (float)((ac[i + 1] - ac[i + 1 - window]) / tot);
+        }
+    }
+    free(bc); free(sc); free(ac); free(nf);
+    return FMKO_OK;
+}
+
+/* feature/core/volume.py:572-607 comp_flow_acceleration */
+int fmko_flow_acceleration(const double *vol, int64_t n, int64_t window, int64_t recent, double *out) {
+    const double eps = 1e-12;
+    for (int64_t i = 0; i < n; i++) out[i] = NAN;
+    if (n < window || recent >= window) return FMKO_OK;
+    double *S = (double *)malloc(sizeof(double) * (size_t)(n + 1));
+    S[0] = 0.0;
+    for (int64_t i = 0; i < n; i++) S[i + 1] = S[i] + vol[i];
+    #pragma omp parallel for schedule(static)
+    for (int64_t i = window - 1; i < n; i++) {
+        double rs = S[i + 1] - S[i + 1 - recent], ps = S[i + 1 - recent] - S[i + 1 - window];
+        out[i] = log((rs + eps) / (ps + eps));
+    }
+    free(S);
+    return FMKO_OK;
+}

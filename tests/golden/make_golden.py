@@ -24,7 +24,8 @@ from finmlkit.bar.logic import (_time_bar_indexer, _tick_bar_indexer, _volume_ba
 from finmlkit.bar.base import (comp_bar_ohlcv, comp_bar_directional_features, comp_bar_trade_size_features,  # noqa: E402
                                comp_bar_footprints)
 from finmlkit.feature.core.utils import comp_lagged_returns  # noqa: E402
-from finmlkit.feature.core.volatility import ewmst  # noqa: E402
+from finmlkit.feature.core.volatility import ewmst, ewms, realized_vol  # noqa: E402
+from finmlkit.feature.core.volume import vpin, comp_flow_acceleration  # noqa: E402
 from finmlkit.label.tbm import triple_barrier  # noqa: E402
 
 from finmlkit_b200.synth import synth_trades  # noqa: E402
@@ -89,6 +90,22 @@ def case_stream(name, ts, px, qty, side, *, interval=60.0, tick_thr=100, vol_thr
     ref_bundle(ts, px, qty, side, out["ref_tick_idx"], "tick", out, tick=tick, footprints=False)
     if len(out["ref_cusum_idx"]) >= 2:
         ref_bundle(ts, px, qty, side, out["ref_cusum_idx"], "cusum", out, tick=tick, footprints=False)
+    # a15: bar-level features on the dollar bars (returns with NaNs injected, buy/sell volumes from the directional tuple)
+    dcl = out["ref_dollar_ohlcv_close"]
+    bret = np.full(len(dcl), np.nan)
+    bret[1:] = np.log(dcl[1:] / dcl[:-1])
+    if len(bret) > 12:
+        bret[[5, 11]] = np.nan
+    out["in_bar_ret"] = bret
+    for w, smp in [(5, True), (20, False)]:
+        out[f"ref_rv_{w}_{int(smp)}"] = realized_vol(bret, w, smp)
+    out["ref_ewms_10"] = ewms(bret, 10)
+    vb, vs = out["ref_dollar_dir_2"].astype(np.float64), out["ref_dollar_dir_3"].astype(np.float64)
+    if len(vb) > 9:
+        vb[7] = np.nan
+    out["in_vpin_vb"], out["in_vpin_vs"] = vb, vs
+    out["ref_vpin_8"] = vpin(vb, vs, 8)
+    out["ref_flow_acc_20_5"] = comp_flow_acceleration(out["ref_dollar_ohlcv_volume"].astype(np.float64), 20, 5)
     if tbm:
         # events: dollar-bar closes with a finite sigma, excluding those too close to the end
         ev = out["ref_dollar_idx"][1:]
@@ -198,6 +215,12 @@ def crosscheck():
     b = oracle.triple_barrier(ts, px, ev, tg, (2.0, 2.0), 300.0, 1.0, None, 0.0)
     for k in range(4):
         chk(f"tbm[{k}]", a[k], b[k])
+    g = dict(np.load(os.path.join(HERE, "synth_20k.npz")))
+    chk("a15 realized_vol", g["ref_rv_5_1"], oracle.realized_vol(g["in_bar_ret"], 5, True))
+    chk("a15 realized_vol pop", g["ref_rv_20_0"], oracle.realized_vol(g["in_bar_ret"], 20, False))
+    chk("a15 ewms", g["ref_ewms_10"], oracle.ewms(g["in_bar_ret"], 10))
+    chk("a15 vpin", g["ref_vpin_8"], oracle.vpin(g["in_vpin_vb"], g["in_vpin_vs"], 8))
+    chk("a15 flow acc", g["ref_flow_acc_20_5"], oracle.comp_flow_acceleration(g["ref_dollar_ohlcv_volume"].astype(np.float64), 20, 5))
     print("CROSSCHECK", "PASSED" if ok else "FAILED")
 
 

@@ -119,3 +119,17 @@ def test_triple_barrier(case):
     assert_exact(tch[~skipped], g["ref_tbm_meta_touch"][~skipped], f"{name}.tbm.meta.touch")
     assert_f64(rets, g["ref_tbm_meta_rets"], f"{name}.tbm.meta.rets", rtol=1e-9, atol=1e-15)
     assert_f64(rat, g["ref_tbm_meta_ratios"], f"{name}.tbm.meta.ratios", rtol=1e-9, atol=1e-15)
+
+
+def test_bar_level_features(ctx):
+    """a15: realized_vol / ewms / vpin / comp_flow_acceleration on the dollar bars of the synthetic fixture."""
+    from finmlkit_b200.feature.core.volatility import ewms, realized_vol
+    from finmlkit_b200.feature.core.volume import comp_flow_acceleration, vpin
+    g = load_case("synth_20k")
+    assert_exact(realized_vol(g["in_bar_ret"], 5, True, ctx=ctx), g["ref_rv_5_1"], "rv sample")     # same summation order
+    assert_exact(realized_vol(g["in_bar_ret"], 20, False, ctx=ctx), g["ref_rv_20_0"], "rv population")
+    assert_f64(ewms(g["in_bar_ret"], 10, ctx=ctx), g["ref_ewms_10"], "ewms", rtol=1e-9, atol=1e-15)
+    from helpers import assert_f32_ulp
+    assert_f32_ulp(vpin(g["in_vpin_vb"], g["in_vpin_vs"], 8, ctx=ctx), g["ref_vpin_8"], "vpin", ulps=1, atol=1e-9)
+    assert_f64(comp_flow_acceleration(g["ref_dollar_ohlcv_volume"].astype(np.float64), 20, 5, ctx=ctx), g["ref_flow_acc_20_5"],
+               "flow acc", rtol=1e-9, atol=1e-12)

@@ -74,3 +74,12 @@ def test_series_and_labels(case):
         assert_exact(r[1][~sk], g["ref_tbm_meta_touch"][~sk], "meta touch")
         assert_exact(r[2], g["ref_tbm_meta_rets"], "meta rets")
         assert_exact(r[3], g["ref_tbm_meta_ratios"], "meta ratios")
+
+
+def test_bar_level_features():
+    g = load_case("synth_20k")
+    assert_exact(oracle.realized_vol(g["in_bar_ret"], 5, True), g["ref_rv_5_1"], "rv")
+    assert_exact(oracle.realized_vol(g["in_bar_ret"], 20, False), g["ref_rv_20_0"], "rv pop")
+    assert_exact(oracle.ewms(g["in_bar_ret"], 10), g["ref_ewms_10"], "ewms")
+    assert_exact(oracle.vpin(g["in_vpin_vb"], g["in_vpin_vs"], 8), g["ref_vpin_8"], "vpin")
+    assert_exact(oracle.comp_flow_acceleration(g["ref_dollar_ohlcv_volume"].astype(np.float64), 20, 5), g["ref_flow_acc_20_5"], "flow")
