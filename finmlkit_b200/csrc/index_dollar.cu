@@ -92,18 +92,28 @@ struct GuessOut {
 };
 
 // One lane per task; a warp's 32 tasks stream their ticks through a shared-memory tile that the warp fills with
-// coalesced loads (row r = the next DT_R ticks of lane r's task), so HBM sees full 128-byte requests even though
-// every task walks its own contiguous range sequentially.
+// coalesced asynchronous copies (cp.async: row r = the next DT_R ticks of lane r's task).  The tile is double
+// buffered: the copies of round k+1 are in flight while round k is replayed, so the HBM latency never sits on the
+// serial float chain.
 constexpr int DT_WARPS = 4;
-constexpr int DT_R = 16;
+constexpr int DT_R = 8;
+
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(DT_WARPS * 32) k_dollar_tasks(const double *__restrict__ p, const double *__restrict__ v,
                                                                 DollarParams P, int64_t nt,
                                                                 const int64_t *__restrict__ K_in,
                                                                 const double *__restrict__ carry,
                                                                 int64_t *__restrict__ out,
                                                                 DollarTaskRec *__restrict__ recs) {
-    __shared__ double sp[DT_WARPS][32][DT_R + 1];
-    __shared__ double sv[DT_WARPS][32][DT_R + 1];
+    __shared__ double sp[2][DT_WARPS][32][DT_R + 1];
+    __shared__ double sv[2][DT_WARPS][32][DT_R + 1];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t k = ((int64_t)blockIdx.x * DT_WARPS + w) * 32 + lane;
     const int64_t n = P.n;
@@ -111,33 +121,43 @@ __global__ void __launch_bounds__(DT_WARPS * 32) k_dollar_tasks(const double *__
     int64_t pos = 0;
     bool active = k < nt;
     if (active) pos = dollar_task_init(t, P, k, k > 0 ? carry[k] : 0.0, k > 0 ? K_in[k] : 0, k == 0 ? __dmul_rn(p[0], v[0]) : 0.0);
-    else { t.B = -1; t.K = 0; t.cnt = 0; t.end_idx = -2; t.nch = DC_NCH; t.start_units = 0; }
-    const int half = lane >> 4, col = lane & 15;
-    while (__any_sync(0xffffffffu, active)) {
-#pragma unroll 4
-        for (int q = 0; q < 16; q++) {
-            const int row = 2 * q + half;
-            const int64_t rp = __shfl_sync(0xffffffffu, pos, row);
-            const int ra = __shfl_sync(0xffffffffu, (int)active, row);
+    else { t.B = -1; t.K = 0; t.cnt = 0; t.end_idx = -2; t.nch = DC_NCH; t.start_units = 0; t.phase = 3; }
+    const int sub = lane >> 3, col = lane & 7;     // 8 lanes copy one 64-byte row; 4 rows per instruction
+    auto stage = [&](int buf, int64_t at, bool on) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int row = 4 * q + sub;
+            const int64_t rp = __shfl_sync(0xffffffffu, at, row);
+            const int ra = __shfl_sync(0xffffffffu, (int)on, row);
             const int64_t idx = rp + col;
-            double a = 0.0, b = 0.0;
-            if (ra && idx < n) { a = __ldg(p + idx); b = __ldg(v + idx); }
-            sp[w][row][col] = a;
-            sv[w][row][col] = b;
+            if (ra && idx < n) {
+                cp_async8(&sp[buf][w][row][col], p + idx);
+                cp_async8(&sv[buf][w][row][col], v + idx);
+            }
         }
+        cp_async_commit();
+    };
+    int buf = 0;
+    stage(0, pos, active);
+    while (__any_sync(0xffffffffu, active)) {
+        stage(buf ^ 1, pos + DT_R, active);          // prefetch the next round
+        cp_async_wait<1>();                           // the current round's copies have landed
         __syncwarp();
         if (active) {
+            int m = DT_R;
+            if (pos + DT_R > n) m = (int)(n - pos);
 #pragma unroll 1
-            for (int tt = 0; tt < DT_R; tt++) {
-                const int64_t i = pos + tt;
-                if (i >= n) { active = false; break; }
-                const double d = __dmul_rn(sp[w][lane][tt], sv[w][lane][tt]);
-                if (dollar_task_consume(t, P, i, d, out)) { active = false; break; }
+            for (int tt = 0; tt < m; tt++) {
+                const double d = __dmul_rn(sp[buf][w][lane][tt], sv[buf][w][lane][tt]);
+                if (dollar_task_consume(t, P, pos + tt, d, out)) { active = false; break; }
             }
             pos += DT_R;
+            if (pos >= n) active = false;
         }
         __syncwarp();
+        buf ^= 1;
     }
+    cp_async_wait<0>();
     if (k < nt) {
         DollarTaskRec rec;
         dollar_task_finish(t, P, &rec);

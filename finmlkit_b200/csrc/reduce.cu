@@ -161,24 +161,30 @@ __device__ void warp_select_two(const double *__restrict__ a, int64_t cnt, int64
     for (;;) {
         const unsigned long long hi_bound = prefix | ~mask;   // largest key of the selected range
         if (c <= 32) {
-            // gather the candidates (ballot compaction keeps tick order) and the smallest key above the range
+            // gather the (<= 32) candidates into shared memory -- unordered: equal keys are interchangeable for rank
+            // selection -- and, only when the (k+1)-th statistic may lie outside the bucket, the smallest key above it
+            const bool need_above = (kk + 1 >= c);
             unsigned long long amin = ~0ull;
-            int filled = 0;
-            for (int64_t j0 = 0; j0 < cnt; j0 += 32) {
-                const int64_t j = j0 + lane;
-                unsigned long long key = 0ull;
-                bool m = false;
-                if (j < cnt) {
-                    key = dkey(__ldg(a + j));
-                    m = (key & mask) == prefix;
-                    if (key > hi_bound && key < amin) amin = key;
+            unsigned *cnt_s = hist;             // hist[0] doubles as the append counter
+            if (lane == 0) *cnt_s = 0u;
+            __syncwarp();
+            int64_t j = lane;
+            for (; j + 96 < cnt; j += 128) {    // 4 independent loads in flight per lane
+                const double x0 = __ldg(a + j), x1 = __ldg(a + j + 32), x2 = __ldg(a + j + 64), x3 = __ldg(a + j + 96);
+                const unsigned long long ks[4] = {dkey(x0), dkey(x1), dkey(x2), dkey(x3)};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if ((ks[q] & mask) == prefix) cand[atomicAdd(cnt_s, 1u) & 31u] = ks[q];
+                    else if (need_above && ks[q] > hi_bound && ks[q] < amin) amin = ks[q];
                 }
-                const unsigned bal = __ballot_sync(FULL, m);
-                if (m) cand[filled + __popc(bal & ((1u << lane) - 1u))] = key;
-                filled += __popc(bal);
+            }
+            for (; j < cnt; j += 32) {
+                const unsigned long long key = dkey(__ldg(a + j));
+                if ((key & mask) == prefix) cand[atomicAdd(cnt_s, 1u) & 31u] = key;
+                else if (need_above && key > hi_bound && key < amin) amin = key;
             }
             __syncwarp();
-            amin = warp_min64(amin);
+            if (need_above) amin = warp_min64(amin);
             const unsigned long long mine = lane < c ? cand[lane] : ~0ull;
             int rank = 0;
             for (int q = 0; q < (int)c; q++) {
