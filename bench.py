@@ -31,7 +31,7 @@ METRIC = "ticks/sec bar+feature build"
 UNIT = "ticks/s"
 # algorithmic HBM bytes per tick of each streaming kernel
 ALGO_BYTES_PER_TICK = {"k_dollar_tasks": 16, "k_dollar_chunk_sums": 16, "k_bar_ohlcv_warp": 16, "k_bar_ohlcv_thread": 16,
-                       "k_bar_order_stats": 8, "k_dollar_fused": 16}
+                       "k_bar_order_stats": 8, "k_bar_ohlcv_median": 16}
 
 
 def env_int(name, default):
@@ -219,6 +219,30 @@ def main():
     ms_per_step = ms / args.steps
     value = world * n / (ms_per_step * 1e-3)
 
+    # ---- secondary: the north_star's single-GPU time-bar build (1-minute bars + OHLCV incl. median), same stream ------
+    time_bars = None
+    if world == 1:
+        def tstep(with_median):
+            tix = core.time_bar_index(tr, 60.0)
+            ctx.check(ctx._L.fmk_bar_ohlcv_device(ctx.h, tr.h, tix.h, with_median))
+            return tix.m - 1
+        time_bars = {}
+        for with_median in (1, 0):
+            tstep(with_median)
+            ctx.sync()
+            ctx.prof_enable(True)
+            ctx.timer_start()
+            for _ in range(args.steps):
+                nb_t = tstep(with_median)
+            tms = ctx.timer_stop() / args.steps
+            ctx.prof_enable(False)
+            pr = ctx.prof_report()
+            kname, (kc, kms) = max(pr.items(), key=lambda kv: kv[1][1])
+            time_bars["ohlcv+median" if with_median else "ohlcv"] = {
+                "ticks_per_s": n / (tms * 1e-3), "ms_per_step": tms, "bars": nb_t, "dominant_kernel": kname,
+                "kernel_GBps_on_16B_per_tick": 16 * n / (kms / kc * 1e-3) / 1e9,
+                "frac_of_peak": 16 * n / (kms / kc * 1e-3) / 1e9 / measured_peak()[0]}
+
     # ---- roofline of the dominant kernel (CUDA events around every launch of the timed region) ----------------------
     peak, peak_src = measured_peak()
     roofline = None
@@ -319,7 +343,7 @@ def main():
                            "l2": "inputs (16-24 GB/step) exceed the 126 MB L2; no flush needed" if n * 16 > 4e8 else "inputs fit L2: timing is warm-L2",
                            "parallelism": f"symbols x{world}", "index_stats": stats,
                            "gather_bytes_per_step": gather_bytes[0]},
-                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline}
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline, "time_bars_1min": time_bars}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

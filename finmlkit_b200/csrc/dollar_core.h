@@ -121,6 +121,7 @@ struct DollarTaskRec {
 struct DollarParams {
     double T, u, top_lim, sub_lim;  // u = ulp(T); top_lim = 4*2^e; sub_lim = 2*2^e
     double margin0;                 // 2^(e-35): distance guaranteed by the coarse per-tick tests
+    double inv_half_u;              // 2/u
     uint32_t hi_tiny, hi_near, hi_top, hi_sub;   // high words of 2^(e-24), 2^(e-34), top_lim, sub_lim
     uint32_t eTb;                                // biased exponent of T
     int64_t n, CH, cap;
@@ -137,6 +138,7 @@ DC_HD bool dollar_params_init(DollarParams *P, double T, int64_t n, int64_t CH, 
     P->top_lim = pow2 * 4.0;
     P->sub_lim = pow2 * 2.0;
     P->margin0 = pow2 * 2.9103830456733704e-11;             // 2^-35
+    P->inv_half_u = 2.0 / P->u;
     P->hi_tiny = dc_hi(pow2 * 5.9604644775390625e-08);      // 2^-24
     P->hi_near = dc_hi(pow2 * 5.820766091346741e-11);       // 2^-34
     P->hi_top = dc_hi(P->top_lim);
@@ -297,10 +299,12 @@ DC_HD bool dollar_virtual_tick(DollarTask &t, double d, const DollarParams &P) {
     const bool in_upper = eb > P.eTb;                     // r >= 2^(e+1)
     const bool in_top = eb == P.eTb;
     const bool crossing = ((hr ^ hcp) >> 20) != 0u;
-    const uint64_t db = dc_bits(d);
-    const uint32_t ed = (uint32_t)(db >> 52) & 0x7FFu;
-    const uint64_t md = (db & 0x000FFFFFFFFFFFFFull) | (ed ? 0x0010000000000000ull : 0ull);
-    const bool dtie = (uint32_t)dc_ffsll(md) + ed == P.eTb;   // fraction of d/u is exactly one half
+    // pre-filter for "d/u has fractional part exactly one half" (the only way an add inside T's binade can be a tie):
+    // t = 2d/u is then an odd integer.  For t < 2^52, t + 2^52 rounds t to an integer whose parity is the low mantissa
+    // bit.  Larger d (>= T/2-ish) simply take the rare branch, which decides exactly from the TwoSum error anyway.
+    const double tq = dc_mul(d, P.inv_half_u);
+    const double tm = dc_add(tq, 4503599627370496.0);
+    const bool dtie = ((dc_sub(tm, 4503599627370496.0) == tq) & ((uint32_t)dc_bits(tm) & 1u)) | !(tq < 4503599627370496.0);
     const bool sens = in_upper | (in_top & (dtie | crossing));
     if (rare_m | sens) {
         if (rare_m) {
@@ -327,6 +331,14 @@ DC_HD bool dollar_virtual_tick(DollarTask &t, double d, const DollarParams &P) {
     return false;
 }
 #endif
+
+// chain 0 emitted a boundary at tick i: record it; returns true when the task is finished
+DC_HD bool dollar_task_emit(DollarTask &t, const DollarParams &P, int64_t i, int64_t *out) {
+    t.cnt++;
+    if (t.K + t.cnt < P.cap) out[t.K + t.cnt] = i;   // speculative writes stay in bounds; cap bounds the true count
+    if (!t.last_chunk && i >= t.hi) { t.end_idx = i; t.phase = 3; return true; }
+    return false;
+}
 
 // Feed tick i (d = fl(p_i * v_i)).  Returns true when the task is finished.
 DC_HD bool dollar_task_consume(DollarTask &t, const DollarParams &P, int64_t i, double d, int64_t *out) {
@@ -364,11 +376,7 @@ DC_HD bool dollar_task_consume(DollarTask &t, const DollarParams &P, int64_t i, 
 #else
     const bool e0 = dollar_virtual_tick(t, d, P);
 #endif
-    if (e0) {
-        t.cnt++;
-        if (t.K + t.cnt < P.cap) out[t.K + t.cnt] = i;   // speculative writes stay in bounds; cap bounds the true count
-        if (!t.last_chunk && i >= t.hi) { t.end_idx = i; t.phase = 3; return true; }
-    }
+    if (e0) return dollar_task_emit(t, P, i, out);
     return false;
 }
 

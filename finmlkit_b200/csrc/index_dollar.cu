@@ -146,11 +146,30 @@ __global__ void __launch_bounds__(DT_WARPS * 32) k_dollar_tasks(const double *__
         if (active) {
             int m = DT_R;
             if (pos + DT_R > n) m = (int)(n - pos);
+            int tt = 0;
+            if (t.phase == 1) {   // approximate walk to the first boundary of the chunk
 #pragma unroll 1
-            for (int tt = 0; tt < m; tt++) {
-                const double d = __dmul_rn(sp[buf][w][lane][tt], sv[buf][w][lane][tt]);
-                if (dollar_task_consume(t, P, pos + tt, d, out)) { active = false; break; }
+                for (; tt < m && t.phase == 1; tt++) {
+                    const double d = __dmul_rn(sp[buf][w][lane][tt], sv[buf][w][lane][tt]);
+                    if (dollar_task_consume(t, P, pos + tt, d, out)) active = false;
+                }
             }
+#ifndef DC_EXPLICIT_CHAINS
+            if (t.phase == 2) {   // exact replay: the tight loop
+#pragma unroll 1
+                for (; tt < m; tt++) {
+                    const double d = __dmul_rn(sp[buf][w][lane][tt], sv[buf][w][lane][tt]);
+                    if (dollar_virtual_tick(t, d, P)) {
+                        if (dollar_task_emit(t, P, pos + tt, out)) { active = false; break; }
+                    }
+                }
+            }
+#else
+            for (; tt < m && active; tt++) {
+                const double d = __dmul_rn(sp[buf][w][lane][tt], sv[buf][w][lane][tt]);
+                if (dollar_task_consume(t, P, pos + tt, d, out)) active = false;
+            }
+#endif
             pos += DT_R;
             if (pos >= n) active = false;
         }
@@ -311,30 +330,46 @@ __global__ void k_dollar_chain_task0(const DollarTaskRec *__restrict__ recs, con
 
 __global__ void k_dollar_reset_ev(DollarStatus *st) { st->ev_min = ~0ull; }
 
-// single-thread exact repair from (pos, c, K); resync allowed at tasks >= kmin
-__global__ void k_dollar_serial(const double *__restrict__ p, const double *__restrict__ v, int64_t n, double T,
-                                double u, double sub_lim, int64_t CH, int64_t nt,
-                                const DollarTaskRec *__restrict__ recs, int64_t kmin, int64_t pos, double c, int64_t K,
-                                int c_from_first, int64_t *out, int64_t cap, DollarStatus *st) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// exact serial repair from (pos, c, K); resync allowed at tasks >= kmin.  One warp: the lanes fetch 32 ticks at a time
+// (coalesced) and every lane replays the same recurrence on the shuffled products, so the chain never waits on a
+// dependent global load.  Semantics are those of dollar_serial() in dollar_core.h.
+__global__ void __launch_bounds__(32) k_dollar_serial(const double *__restrict__ p, const double *__restrict__ v, int64_t n,
+                                                      double T, double u, double sub_lim, int64_t CH, int64_t nt,
+                                                      const DollarTaskRec *__restrict__ recs, int64_t kmin, int64_t pos,
+                                                      double c, int64_t K, int c_from_first, int64_t *out, int64_t cap,
+                                                      DollarStatus *st) {
+    const int lane = threadIdx.x;
     if (c_from_first) c = __dmul_rn(p[0], v[0]);   // logic.py:142 cum_dollar = prices[0] * volumes[0]
-    int overflow = 0;
-    double c_out;
-    int64_t pos_out;
-    auto stop = [&](int64_t i, int64_t Kafter, double cc) {
-        const int64_t kk = i / CH;
-        if (kk < kmin || kk >= nt) return false;
-        const DollarTaskRec &t = recs[kk];
-        if (t.start_idx != i || t.k_start != Kafter) return false;
-        const double eu = cc / u;
-        return (double)(int64_t)eu == eu && cc < sub_lim;
-    };
-    const int64_t cnt = dollar_serial(LdG{p}, LdG{v}, n, T, pos, c, K, out, cap, &overflow, stop, &c_out, &pos_out);
+    int64_t cnt = 0, pos_out = -2;
+    bool overflow = false;
+    for (int64_t base = pos + 1; base < n && pos_out == -2; base += 32) {
+        const int64_t i = base + lane;
+        const double d = i < n ? __dmul_rn(__ldg(p + i), __ldg(v + i)) : 0.0;
+        const int m = (n - base) < 32 ? (int)(n - base) : 32;
+        for (int q = 0; q < m; q++) {
+            c = __dadd_rn(c, __shfl_sync(0xffffffffu, d, q));
+            if (c >= T) {
+                c = __dadd_rn(c, -T);
+                cnt++;
+                const int64_t at = base + q;
+                if (K + cnt < cap) { if (lane == 0) out[K + cnt] = at; } else overflow = true;
+                const int64_t kk = at / CH;
+                if (kk >= kmin && kk < nt) {
+                    const DollarTaskRec &t = recs[kk];
+                    if (t.start_idx == at && t.k_start == K + cnt) {
+                        const double eu = c / u;
+                        if ((double)(int64_t)eu == eu && c < sub_lim) { pos_out = at; break; }
+                    }
+                }
+            }
+        }
+    }
+    if (lane != 0) return;
     if (overflow) { st->event = -1; return; }
     if (pos_out == -2) { st->event = 1; st->K_total = K + cnt; return; }
     st->event = 5;   // resynchronised
     st->k_ev = pos_out / CH;
-    st->s = (int64_t)(c_out / u);
+    st->s = (int64_t)(c / u);
     st->pos = pos_out;
     st->K = K + cnt;
     st->use_c = 0;
@@ -394,7 +429,7 @@ int fmk_dollar_index_impl(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index
     if (!fast) {
         // degenerate threshold (<= 0, inf, denormal): the recurrence is replayed serially on the device
         ctx->stats[1]++;
-        FMK_LAUNCH(ctx, k_dollar_serial, 1, 1, 0, t->price, t->amount, n, T, 1.0, 0.0, CH, (int64_t)0,
+        FMK_LAUNCH(ctx, k_dollar_serial, 1, 32, 0, t->price, t->amount, n, T, 1.0, 0.0, CH, (int64_t)0,
                    (const DollarTaskRec *)recs.p, (int64_t)0, (int64_t)0, 0.0, (int64_t)0, 1, idx, cap, st.p);
         FMK_CUDA(ctx, cudaMemcpyAsync(&hs, st.p, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
         FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -437,7 +472,7 @@ int fmk_dollar_index_impl(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index
         const int64_t kmin = hs.event == 4 ? hs.k_ev : (hs.event == 0 ? nt : hs.k_ev + 1);
         const double c = hs.use_c ? hs.c : (double)hs.s * P.u;
         ctx->stats[1]++;
-        FMK_LAUNCH(ctx, k_dollar_serial, 1, 1, 0, t->price, t->amount, n, T, P.u, P.sub_lim, CH, nt,
+        FMK_LAUNCH(ctx, k_dollar_serial, 1, 32, 0, t->price, t->amount, n, T, P.u, P.sub_lim, CH, nt,
                    (const DollarTaskRec *)recs.p, kmin, hs.pos, c, hs.K, 0, idx, cap, st.p);
         FMK_CUDA(ctx, cudaMemcpyAsync(&hs, st.p, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
         FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -153,8 +153,11 @@ __device__ __forceinline__ unsigned long long warp_min64(unsigned long long x) {
 
 // k-th (0-based) and (k+1)-th smallest of a[0..cnt): warp-cooperative.  hist: 256 words of this warp's shared memory,
 // cand: 32 u64 of this warp's shared memory.  If k+1 == cnt, *r1 = *r0.
+// have_first: the OR / AND of all keys is already known (the fused OHLCV pass computes it while streaming the bar),
+// which saves the first diff pass.
 __device__ void warp_select_two(const double *__restrict__ a, int64_t cnt, int64_t k, unsigned *hist,
-                                unsigned long long *cand, double *r0, double *r1) {
+                                unsigned long long *cand, double *r0, double *r1, bool have_first = false,
+                                unsigned long long orv0 = 0ull, unsigned long long andv0 = ~0ull) {
     const int lane = threadIdx.x & 31;
     unsigned long long mask = 0ull, prefix = 0ull;   // keys in play: (key & mask) == prefix
     int64_t kk = k, c = cnt;
@@ -202,7 +205,8 @@ __device__ void warp_select_two(const double *__restrict__ a, int64_t cnt, int64
         }
         // diff pass
         unsigned long long orv = 0ull, andv = ~0ull, amin = ~0ull;
-        {
+        if (have_first && mask == 0ull) { orv = orv0; andv = andv0; }
+        else {
             int64_t j = lane;
             for (; j + 96 < cnt; j += 128) {   // 4 independent loads in flight per lane
                 const double x0 = __ldg(a + j), x1 = __ldg(a + j + 32), x2 = __ldg(a + j + 64), x3 = __ldg(a + j + 96);
@@ -320,6 +324,60 @@ __global__ void __launch_bounds__(OS_WARPS * 32) k_bar_order_stats(const double 
     }
 }
 
+// Fused comp_bar_ohlcv: one warp streams the bar once from HBM (price + amount: O/H/L/C, sums, and the OR/AND of the
+// amount keys), then runs the radix select for the median on the amounts it has just pulled through L1/L2.
+__global__ void __launch_bounds__(OS_WARPS * 32) k_bar_ohlcv_median(const double *__restrict__ p,
+                                                                    const double *__restrict__ v,
+                                                                    const int64_t *__restrict__ ci, int64_t nb, int64_t n,
+                                                                    OhlcvOut o, double *__restrict__ median_out) {
+    __shared__ unsigned hist_s[OS_WARPS][256];
+    __shared__ unsigned long long cand_s[OS_WARPS][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nb; i += nwarps) {
+        const int64_t s = ci[i], e = ci[i + 1];
+        if (s == e) {
+            if (lane == 0) { ohlcv_empty(o, i, p, e, n); median_out[i] = 0.0; }
+            continue;
+        }
+        const int64_t start = s + 1;
+        double hi = -INFINITY, lo = INFINITY, sv = 0.0, sd = 0.0;
+        unsigned long long orv = 0ull, andv = ~0ull;
+        int64_t j = start + lane;
+        for (; j + 96 <= e; j += 128) {
+            double p0 = __ldg(p + j), p1 = __ldg(p + j + 32), p2 = __ldg(p + j + 64), p3 = __ldg(p + j + 96);
+            double v0 = __ldg(v + j), v1 = __ldg(v + j + 32), v2 = __ldg(v + j + 64), v3 = __ldg(v + j + 96);
+            hi = fmax(fmax(hi, fmax(p0, p1)), fmax(p2, p3));
+            lo = fmin(fmin(lo, fmin(p0, p1)), fmin(p2, p3));
+            sv += (v0 + v1) + (v2 + v3);
+            sd += (p0 * v0 + p1 * v1) + (p2 * v2 + p3 * v3);
+            const unsigned long long k0 = dkey(v0), k1 = dkey(v1), k2 = dkey(v2), k3 = dkey(v3);
+            orv |= (k0 | k1) | (k2 | k3);
+            andv &= (k0 & k1) & (k2 & k3);
+        }
+        for (; j <= e; j += 32) {
+            double pj = __ldg(p + j), vj = __ldg(v + j);
+            hi = fmax(hi, pj); lo = fmin(lo, pj);
+            sv += vj; sd += pj * vj;
+            const unsigned long long kj = dkey(vj);
+            orv |= kj; andv &= kj;
+        }
+        hi = warp_max(hi); lo = warp_min(lo); sv = warp_sum(sv); sd = warp_sum(sd);
+        orv = warp_or64(orv); andv = warp_and64(andv);
+        const int64_t cnt = e - start + 1;
+        if (lane == 0) {
+            o.open[i] = p[start]; o.close[i] = p[e]; o.high[i] = hi; o.low[i] = lo;
+            o.volume[i] = (float)sv;
+            o.vwap[i] = sv > 0 ? sd / sv : 0.0;
+            o.trades[i] = cnt;
+        }
+        const int64_t mk = (cnt & 1) ? (cnt >> 1) : (cnt >> 1) - 1;
+        double r0, r1;
+        warp_select_two(v + start, cnt, mk, hist_s[w], cand_s[w], &r0, &r1, true, orv, andv);
+        if (lane == 0) median_out[i] = (cnt & 1) ? r0 : (r0 + r1) / 2;
+    }
+}
+
 static int launch_order_stats(fmk_ctx *ctx, const double *a, const int64_t *ci, int64_t nb, int mode, double *med,
                               double *p95) {
     if (nb <= 0) return FMK_OK;
@@ -338,6 +396,13 @@ static int check_index(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix) {
 
 static int run_ohlcv(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, OhlcvOut o, double *median) {
     const int64_t nb = ix->m - 1;
+    if (median && t->n / nb >= 8) {
+        int64_t blocks = cdiv(nb, OS_WARPS);
+        const int64_t maxb = (int64_t)ctx->sm_count * 16;
+        if (blocks > maxb) blocks = maxb;
+        FMK_LAUNCH(ctx, k_bar_ohlcv_median, (unsigned)blocks, OS_WARPS * 32, 0, t->price, t->amount, ix->close_idx, nb, t->n, o, median);
+        return FMK_OK;
+    }
     if (t->n / nb >= 8) {
         int64_t warps = nb;
         int64_t blocks = cdiv(warps, 8);
