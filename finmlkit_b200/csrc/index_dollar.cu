@@ -12,7 +12,7 @@
 #include "dollar_core.h"
 #include "scan.cuh"
 
-constexpr int DOLLAR_CH = 2048;
+constexpr int DOLLAR_CH = 4096;
 constexpr int DOLLAR_A_THREADS = 256;
 
 struct LdG {

@@ -59,9 +59,12 @@ __device__ int64_t volume_replay(const double *__restrict__ v, int64_t n, int64_
     return n;
 }
 
+// Ambiguous starts (candidate inside the guard band) are not replayed inline -- that would stall the whole warp on one
+// lane's serial sum -- but appended to a work list that k_volume_replay drains with one thread per entry.
 __global__ void __launch_bounds__(VN_THREADS) k_volume_next(const double *__restrict__ P, const double *__restrict__ v,
                                                             int64_t n, double T, double guard,
-                                                            int32_t *__restrict__ next, int64_t *replays) {
+                                                            int32_t *__restrict__ next, int32_t *__restrict__ work,
+                                                            unsigned long long *nwork, int64_t work_cap) {
     __shared__ int64_t bracket[2];
     const int64_t i0 = (int64_t)blockIdx.x * VN_THREADS;
     const int64_t i = i0 + threadIdx.x;
@@ -82,10 +85,20 @@ __global__ void __launch_bounds__(VN_THREADS) k_volume_next(const double *__rest
     if (j >= n) r = n;                                            // even T - guard is never reached: no boundary
     else if (__ldg(P + j) >= __dadd_rn(base, thi)) r = j;        // clears T + guard: certain
     else {                                                       // within the guard band: the reference's own sum decides
-        r = volume_replay(v, n, i, T);
-        atomicAdd((unsigned long long *)replays, 1ull);
+        const unsigned long long slot = atomicAdd(nwork, 1ull);
+        if ((int64_t)slot < work_cap) { work[slot] = (int32_t)i; r = -1; }
+        else r = volume_replay(v, n, i, T);                      // list full: replay inline
     }
     next[i] = (int32_t)r;
+}
+
+__global__ void k_volume_replay(const double *__restrict__ v, int64_t n, double T, const int32_t *__restrict__ work,
+                                const unsigned long long *nwork, int64_t work_cap, int32_t *__restrict__ next) {
+    const int64_t m = (int64_t)(*nwork < (unsigned long long)work_cap ? *nwork : (unsigned long long)work_cap);
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < m; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = work[q];
+        next[i] = (int32_t)volume_replay(v, n, i, T);
+    }
 }
 
 // first boundary: cum = v[0]; for i >= 1: cum += v[i]; cum >= T -> i   (logic.py:106-111; tick 0 is never tested)
@@ -288,8 +301,13 @@ int fmk_volume_index_impl(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index
     FMK_CUDA(ctx, cudaMemsetAsync(entryS.p, 0xff, (size_t)nS * 8, ctx->stream));
     FMK_CUDA(ctx, cudaMemsetAsync(entryC.p, 0xff, (size_t)nC * 8, ctx->stream));
     FMK_CUDA(ctx, cudaMemsetAsync(off.p, 0, 8, ctx->stream));
+    const int64_t work_cap = n / 4 + 1024;
+    Scratch<int32_t> work(ctx);
+    FMK_TRY(work.alloc(work_cap));
     FMK_LAUNCH(ctx, k_volume_next, (unsigned)cdiv(n, VN_THREADS), VN_THREADS, 0, (const double *)P.p, t->amount, n, T, guard,
-               next.p, replays.p);
+               next.p, work.p, (unsigned long long *)replays.p, work_cap);
+    FMK_LAUNCH(ctx, k_volume_replay, (unsigned)(ctx->sm_count * 16), 128, 0, t->amount, n, T, (const int32_t *)work.p,
+               (const unsigned long long *)replays.p, work_cap, next.p);
     FMK_LAUNCH(ctx, k_volume_first, 1, 1, 0, t->amount, n, T, first.p);
     FMK_LAUNCH(ctx, k_volume_exit0, (unsigned)nC, 256, 0, (const int32_t *)next.p, n, exit0.p);
     FMK_LAUNCH(ctx, k_volume_exit1, (unsigned)nS, 256, 0, (const int32_t *)exit0.p, n, exit1.p);

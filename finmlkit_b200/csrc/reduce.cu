@@ -116,13 +116,16 @@ __global__ void __launch_bounds__(256) k_bar_ohlcv_thread(const double *__restri
 // One WARP per bar, adaptive MSB radix select on the order-preserving 64-bit key of each amount:
 //   diff pass  : OR/AND of the keys still in play -> first bit where they differ (common prefixes and all-equal
 //                groups -- heavy on exchange-quantised sizes -- cost one pass, not eight)
-//   hist pass  : 256-bin shared-memory histogram of the 8 bits below that bit, pick the bucket holding rank k
+//   hist pass  : 1024-bin shared-memory histogram of the 10 bits from that bit down, pick the bucket holding rank k
 //   gather     : once <= 32 candidates remain they are compacted into the lanes and ranked by counting
 // Every pass also tracks the smallest key ABOVE the selected range, which is the (k+1)-th order statistic when the
 // k-th is the largest candidate (median of an even count, percentile interpolation).  The bar's amounts are re-read
 // from L1/L2 on each pass (a 1000-tick bar is 8 KB); HBM sees them once.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int OS_WARPS = 8;
+constexpr int OS_RBITS = 10;                 // radix digit width
+constexpr int OS_NBIN = 1 << OS_RBITS;
+constexpr int OS_HIST = OS_NBIN + OS_NBIN / 32; // padded histogram words per warp
 
 __device__ __forceinline__ unsigned long long dkey(double x) {  // order-preserving map double -> uint64
     unsigned long long b = (unsigned long long)__double_as_longlong(x);
@@ -151,7 +154,7 @@ __device__ __forceinline__ unsigned long long warp_min64(unsigned long long x) {
     return x;
 }
 
-// k-th (0-based) and (k+1)-th smallest of a[0..cnt): warp-cooperative.  hist: 256 words of this warp's shared memory,
+// k-th (0-based) and (k+1)-th smallest of a[0..cnt): warp-cooperative.  hist: OS_HIST words of this warp's shared memory,
 // cand: 32 u64 of this warp's shared memory.  If k+1 == cnt, *r1 = *r0.
 // have_first: the OR / AND of all keys is already known (the fused OHLCV pass computes it while streaming the bar),
 // which saves the first diff pass.
@@ -232,9 +235,11 @@ __device__ void warp_select_two(const double *__restrict__ a, int64_t cnt, int64
             return;
         }
         const int hb = 63 - __clzll((long long)diff);
-        const int shift = hb >= 7 ? hb - 7 : 0;
-        for (int b = lane; b < 256; b += 32) hist[b] = 0u;
+        const int shift = hb >= OS_RBITS - 1 ? hb - (OS_RBITS - 1) : 0;
+        for (int b = lane; b < OS_HIST; b += 32) hist[b] = 0u;
         __syncwarp();
+        // bin d lives at hist[d + (d >> 5)] (one pad word per 32 bins) so that the per-lane group sums below are
+        // bank-conflict free
         {
             int64_t j = lane;
             for (; j + 96 < cnt; j += 128) {
@@ -242,19 +247,24 @@ __device__ void warp_select_two(const double *__restrict__ a, int64_t cnt, int64
                 const unsigned long long ks[4] = {dkey(x0), dkey(x1), dkey(x2), dkey(x3)};
 #pragma unroll
                 for (int q = 0; q < 4; q++)
-                    if ((ks[q] & mask) == prefix) atomicAdd(&hist[(unsigned)(ks[q] >> shift) & 255u], 1u);
+                    if ((ks[q] & mask) == prefix) {
+                        const unsigned d = (unsigned)(ks[q] >> shift) & (OS_NBIN - 1u);
+                        atomicAdd(&hist[d + (d >> 5)], 1u);
+                    }
             }
             for (; j < cnt; j += 32) {
                 const unsigned long long key = dkey(__ldg(a + j));
-                if ((key & mask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+                if ((key & mask) == prefix) {
+                    const unsigned d = (unsigned)(key >> shift) & (OS_NBIN - 1u);
+                    atomicAdd(&hist[d + (d >> 5)], 1u);
+                }
             }
         }
         __syncwarp();
-        // bucket holding rank kk: each lane owns 8 consecutive bins
-        unsigned loc[8];
+        // level 1: lane L sums bins [32L, 32L+32); level 2: the owner group's 32 bins, one per lane
         unsigned s = 0;
-#pragma unroll
-        for (int q = 0; q < 8; q++) { loc[q] = hist[lane * 8 + q]; s += loc[q]; }
+#pragma unroll 8
+        for (int q = 0; q < 32; q++) s += hist[33 * lane + q];
         unsigned inc = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -264,24 +274,25 @@ __device__ void warp_select_two(const double *__restrict__ a, int64_t cnt, int64
         const unsigned exc = inc - s;
         const bool mineb = (unsigned long long)kk >= exc && (unsigned long long)kk < inc;
         const int owner = __ffs(__ballot_sync(FULL, mineb)) - 1;
-        int bsel = 0;
-        unsigned below = 0, csel = 0;
-        if (lane == owner) {
-            unsigned run = exc;
+        const unsigned exc_owner = __shfl_sync(FULL, exc, owner);
+        const unsigned bv = hist[33 * owner + lane];
+        unsigned inc2 = bv;
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                if ((unsigned long long)kk >= run && (unsigned long long)kk < run + loc[q]) { bsel = lane * 8 + q; below = run; csel = loc[q]; }
-                run += loc[q];
-            }
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(FULL, inc2, o);
+            if (lane >= o) inc2 += y;
         }
-        bsel = __shfl_sync(FULL, bsel, owner);
-        below = __shfl_sync(FULL, below, owner);
-        csel = __shfl_sync(FULL, csel, owner);
+        const unsigned exc2 = inc2 - bv;
+        const unsigned long long k2 = (unsigned long long)kk - exc_owner;
+        const int sel = __ffs(__ballot_sync(FULL, k2 >= exc2 && k2 < inc2)) - 1;
+        const int bsel = owner * 32 + sel;
+        const unsigned below = exc_owner + __shfl_sync(FULL, exc2, sel);
+        const unsigned csel = __shfl_sync(FULL, bv, sel);
         kk -= below;
         c = csel;
         // new range: common bits above the digit come from any key in play (orv), the digit is bsel
-        const unsigned long long above_mask = (shift + 8 >= 64) ? 0ull : (~0ull << (shift + 8));
-        mask = above_mask | (255ull << shift);
+        const unsigned long long above_mask = (shift + OS_RBITS >= 64) ? 0ull : (~0ull << (shift + OS_RBITS));
+        mask = above_mask | ((unsigned long long)(OS_NBIN - 1) << shift);
         prefix = (orv & above_mask) | ((unsigned long long)bsel << shift);
         __syncwarp();
     }
@@ -292,7 +303,7 @@ __global__ void __launch_bounds__(OS_WARPS * 32) k_bar_order_stats(const double 
                                                                    const int64_t *__restrict__ ci, int64_t nb, int mode,
                                                                    double *__restrict__ median_out,
                                                                    double *__restrict__ p95_out) {
-    __shared__ unsigned hist_s[OS_WARPS][256];
+    __shared__ unsigned hist_s[OS_WARPS][OS_HIST];
     __shared__ unsigned long long cand_s[OS_WARPS][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -330,7 +341,7 @@ __global__ void __launch_bounds__(OS_WARPS * 32) k_bar_ohlcv_median(const double
                                                                     const double *__restrict__ v,
                                                                     const int64_t *__restrict__ ci, int64_t nb, int64_t n,
                                                                     OhlcvOut o, double *__restrict__ median_out) {
-    __shared__ unsigned hist_s[OS_WARPS][256];
+    __shared__ unsigned hist_s[OS_WARPS][OS_HIST];
     __shared__ unsigned long long cand_s[OS_WARPS][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;

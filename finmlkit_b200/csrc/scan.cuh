@@ -45,15 +45,41 @@ __device__ __forceinline__ T block_excl_scan_sum(T x, T *tot) {
     return r;
 }
 
+
+// Thread t of a block owns elements [8t, 8t+8) of its tile (blocked order keeps the scan operator's order).  Reading them
+// straight from global memory makes every lane touch its own 64-byte segment; for small element types the tile is
+// instead fetched with fully coalesced row loads and transposed through padded shared memory.
+template <typename T, typename InF>
+__device__ __forceinline__ void scan_load_items(InF &in, int64_t tile_base, int64_t n, T (&vals)[SCAN_ITEMS]) {
+    if constexpr (sizeof(T) <= 8) {
+        __shared__ __align__(16) unsigned char raw_in[(SCAN_TILE + SCAN_TILE / 8) * 8];
+        T *tile = reinterpret_cast<T *>(raw_in);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            const int e = threadIdx.x + k * SCAN_THREADS;
+            const int64_t i = tile_base + e;
+            tile[e + (e >> 3)] = (i < n) ? in(i) : T(0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) vals[k] = tile[threadIdx.x * (SCAN_ITEMS + 1) + k];
+        __syncthreads();
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            const int64_t i = tile_base + (int64_t)threadIdx.x * SCAN_ITEMS + k;
+            vals[k] = (i < n) ? in(i) : T(0);
+        }
+    }
+}
+
 template <typename T, typename InF>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(InF in, int64_t n, T *tile_sums) {
-    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    T vals[SCAN_ITEMS];
+    scan_load_items<T>(in, (int64_t)blockIdx.x * SCAN_TILE, n, vals);
     T s = T(0);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        int64_t i = base + k;
-        if (i < n) s = s + in(i);
-    }
+    for (int k = 0; k < SCAN_ITEMS; k++) s = s + vals[k];
     T tot;
     block_excl_scan_sum(s, &tot);
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
@@ -94,21 +120,36 @@ template <typename T, typename InF, typename OutF>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(InF in, OutF out, int64_t n, const T *tile_offsets) {
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     T vals[SCAN_ITEMS];
+    scan_load_items<T>(in, (int64_t)blockIdx.x * SCAN_TILE, n, vals);
     T s = T(0);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        int64_t i = base + k;
-        vals[k] = (i < n) ? in(i) : T(0);
-        s = s + vals[k];
-    }
+    for (int k = 0; k < SCAN_ITEMS; k++) s = s + vals[k];
     T tot;
     T ex = block_excl_scan_sum(s, &tot);
     T run = tile_offsets[blockIdx.x] + ex;
+    if constexpr (sizeof(T) <= 8) {
+        // transpose the results back so that out() is called in coalesced order
+        __shared__ __align__(16) unsigned char raw_out[(SCAN_TILE + SCAN_TILE / 8) * 8];
+        T *otile = reinterpret_cast<T *>(raw_out);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        int64_t i = base + k;
-        run = run + vals[k];
-        if (i < n) out(i, run);
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            run = run + vals[k];
+            otile[threadIdx.x * (SCAN_ITEMS + 1) + k] = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            const int e = threadIdx.x + k * SCAN_THREADS;
+            const int64_t i = (int64_t)blockIdx.x * SCAN_TILE + e;
+            if (i < n) out(i, otile[e + (e >> 3)]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            int64_t i = base + k;
+            run = run + vals[k];
+            if (i < n) out(i, run);
+        }
     }
 }
 

@@ -1,0 +1,94 @@
+"""BASELINE configs 3 and 4 at full size on one GPU (device-resident timings + prefix parity vs the oracle).
+   python scripts/gpu_configs.py [N=1e9]"""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+import ctypes as C
+import numpy as np
+from finmlkit_b200 import core
+import oracle
+from helpers import assert_f64, check_directional, check_footprint_csr
+
+N = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000_000
+PRE = min(N, 20_000_000)
+ctx = core.default_context(0)
+tr = core.DeviceTrades.synth(N, seed=42, ctx=ctx)
+ts = np.empty(N, np.int64); px = np.empty(N); qty = np.empty(N); side = np.empty(N, np.int8)
+tr.download(out=(ts, px, qty, side))
+res = {"ticks": N}
+
+def timed(fn, reps=2):
+    best, out = 1e18, None
+    for _ in range(reps):
+        ctx.sync(); ctx.prof_enable(True); ctx.timer_start(); out = fn(); ms = ctx.timer_stop(); ctx.prof_enable(False)
+        pr = ctx.prof_report()
+        if ms < best: best, prof = ms, pr
+    return out, best, {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
+
+# ---- config 3: volume bars + directional + footprints --------------------------------------------------------------
+VT = 50.0
+vix, ms, pr = timed(lambda: core.volume_bar_index(tr, VT))
+res["volume_index"] = {"ms": ms, "ticks_per_s": N / ms * 1e3, "bars": vix.m - 1, "stats": ctx.index_stats(), "kernels_ms": pr}
+vidx = vix.download()[1]
+ref = oracle.volume_bar_indexer(qty[:PRE], VT)
+assert np.array_equal(vidx[vidx < PRE], ref), "volume prefix parity"
+t0 = time.time(); oracle.volume_bar_indexer(qty[:PRE * 5 if PRE * 5 <= N else N], VT); res["volume_index"]["cpu_ticks_per_s"] = min(PRE * 5, N) / (time.time() - t0)
+
+L = ctx._L
+def directional_dev():
+    return core.bar_directional(tr, vix)
+d, ms, pr = timed(directional_dev)
+res["directional"] = {"ms_incl_d2h": ms, "kernels_ms": pr}
+o = core.bar_ohlcv(tr, vix)
+def fp_dev():
+    h = C.c_void_p()
+    lo, hi = np.ascontiguousarray(o[2]), np.ascontiguousarray(o[1])
+    ctx.check(L.fmk_bar_footprints(ctx.h, tr.h, vix.h, 0.1, lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), 3.0, C.byref(h)))
+    nl = L.fmk_footprint_levels(h); L.fmk_footprint_free(ctx.h, h); return nl
+nl, ms, pr = timed(fp_dev)
+res["footprints"] = {"ms_device_build": ms, "levels": int(nl), "kernels_ms": pr}
+# prefix parity for directional / footprints
+k = len(ref) - 1
+dr = oracle.comp_bar_directional_features(px[:PRE], qty[:PRE], ref, side[:PRE])
+check_directional([x[:k] for x in d], dr, "dir prefix")
+trp = core.DeviceTrades.upload(ts[:PRE], px[:PRE], qty[:PRE], side[:PRE], ctx=ctx)
+ixp = core.DeviceIndex.from_host(trp, ref)
+op = core.bar_ohlcv(trp, ixp)
+fg = core.bar_footprints_csr(trp, ixp, 0.1, op[2], op[1], 3.0)
+fo = oracle.comp_bar_footprints_csr(px[:PRE], qty[:PRE], ref, side[:PRE], 0.1, op[2], op[1], 3.0)
+check_footprint_csr(fg, fo[0], list(fo[1:]), float(np.max(np.abs(fo[1]))), "fp prefix")
+res["config3_parity_prefix_ticks"] = PRE
+print("config3", json.dumps(res), flush=True)
+
+# ---- config 4: sigma pipeline + CUSUM bars + triple barrier -----------------------------------------------------------
+h = C.c_void_p()
+def sigma_dev():
+    r = C.c_void_p(); s = C.c_void_p()
+    ctx.check(L.fmk_lagged_returns_dev(ctx.h, tr.h, 3600.0, 1, C.byref(r)))
+    ctx.check(L.fmk_ewmst_dev(ctx.h, tr.h, r, 3600.0, 1e-12, C.byref(s)))
+    L.fmk_buf_free(ctx.h, r)
+    return s
+s_h, ms, pr = timed(sigma_dev, reps=1)
+res4 = {"sigma_pipeline": {"ms": ms, "ticks_per_s": N / ms * 1e3, "kernels_ms": pr}}
+sig = core.DeviceBuf(ctx, s_h)
+sigma = sig.download(np.float64, N)
+rr = oracle.comp_lagged_returns(ts[:PRE], px[:PRE], 3600.0, True)
+assert_f64(sigma[:PRE], oracle.ewmst(ts[:PRE], rr, 3600.0), "sigma prefix", rtol=1e-9, atol=1e-18)
+def cusum_dev():
+    sb = core.DeviceBuf.upload(ctx, sigma)     # cusum forward-fills in place: fresh copy per run
+    return core.cusum_bar_index(tr, sb, 5e-4, 2.0)
+cix, ms, pr = timed(cusum_dev, reps=1)
+res4["cusum_index"] = {"ms_incl_sigma_h2d": ms, "bars": cix.m - 1, "stats": ctx.index_stats(), "kernels_ms": pr}
+cidx = cix.download()[1]
+sp = sigma[:PRE].copy()
+cref = oracle.cusum_bar_indexer(ts[:PRE], px[:PRE], sp, 5e-4, 2.0)
+assert np.array_equal(cidx[cidx < PRE], cref), "cusum prefix parity"
+ev = cidx[1:]; ev = ev[np.isfinite(sigma[ev])]; ev = ev[ts[ev] + 3600 * 10**9 <= ts[-1]]
+tg = sigma[ev]
+lab, ms, pr = timed(lambda: core.triple_barrier_dev(tr, ev, tg, (2.0, 2.0), 3600.0, 1.0, None, 0.0), reps=1)
+res4["triple_barrier"] = {"ms": ms, "events": int(len(ev)), "mean_path_ticks": float(np.mean(lab[1] - ev)), "kernels_ms": pr}
+evp = ev[ev < PRE // 2]
+if len(evp):
+    lr = oracle.triple_barrier(ts[:PRE], px[:PRE], evp, sigma[evp], (2.0, 2.0), 3600.0, 1.0, None, 0.0)
+    assert np.array_equal(lab[0][:len(evp)], lr[0]) and np.array_equal(lab[1][:len(evp)], lr[1]), "tbm prefix parity"
+print("config4", json.dumps(res4), flush=True)
