@@ -42,14 +42,47 @@ def env_int(name, default):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML polled every 2 ms from a thread (nvidia-smi -lms
+    needs ~0.5 s to start, longer than a 10-step timed region); falls back to `nvidia-smi -lms 100` without pynvml."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.rows, self.proc, self.nv = gpu_index, [], None, None
+        self.sm, self.smax, self.reasons, self.power = [], None, set(), []
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, b in bits.items():
+                    if r & b:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nv is not None:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -63,6 +96,11 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nv is not None:
+            self._stop.set()
+            self.t.join(timeout=1.0)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax, "reasons": sorted(self.reasons),
+                    "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None, "source": "nvml, 2 ms poll during the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -79,7 +117,8 @@ class ClockSampler:
             for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi -lms 100"}
 
 
 def measured_peak():
@@ -94,7 +133,7 @@ def ncu_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full summary, if one exists for this workload."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return t.get(kernel)
+        return float(t[kernel]["dram_bytes_per_launch"]) if kernel in t else None
     except Exception:
         return None
 

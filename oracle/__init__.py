@@ -258,3 +258,27 @@ def comp_flow_acceleration(volumes, window, recent_periods):
     out = np.empty(len(v))
     lib().fmko_flow_acceleration(_p(v), C.c_int64(len(v)), C.c_int64(int(window)), C.c_int64(int(recent_periods)), _p(out))
     return out
+
+
+def average_uniqueness(timestamps, event_idxs, touch_idxs):
+    """label/weights.py:7-49 -> (weights f64[E], concurrency i16[n])."""
+    ev, tc = _i64(event_idxs), _i64(touch_idxs)
+    n = len(timestamps)
+    w = np.zeros(len(ev))
+    conc = np.zeros(n, np.int16)
+    rc = lib().fmko_average_uniqueness(C.c_int64(n), _p(ev), _p(tc), C.c_int64(len(ev)), C.c_int64(len(tc)), _p(w), _p(conc))
+    if rc:
+        raise ValueError("Timestamps and lookahead indices must have the same length.")
+    return w, conc
+
+
+def return_attribution(event_idxs, touch_idxs, close, concurrency, normalize):
+    """label/weights.py:52-103."""
+    ev, tc, c = _i64(event_idxs), _i64(touch_idxs), _f64(close)
+    cc = np.ascontiguousarray(concurrency, dtype=np.int16)
+    w = np.zeros(len(ev))
+    rc = lib().fmko_return_attribution(_p(ev), _p(tc), C.c_int64(len(ev)), _p(c), _p(cc), C.c_int64(len(c)),
+                                       C.c_int(bool(normalize)), _p(w))
+    if rc == 1:
+        raise ValueError("Sum of weights is zero or negative, cannot normalize.")
+    return w

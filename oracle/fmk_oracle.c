@@ -659,3 +659,60 @@ int fmko_flow_acceleration(const double *vol, int64_t n, int64_t window, int64_t
     free(S);
     return FMKO_OK;
 }
+
+/* ---- sample weights on ticks (label/weights.py) ------------------------------------------------------ */
+/* Python slice a[start:stop] normalisation for a length-n array */
+static void py_slice(int64_t start, int64_t stop, int64_t n, int64_t *s, int64_t *e) {
+    if (start < 0) { start += n; if (start < 0) start = 0; } else if (start > n) start = n;
+    if (stop < 0) { stop += n; if (stop < 0) stop = 0; } else if (stop > n) stop = n;
+    *s = start; *e = stop > start ? stop : start;
+}
+
+/* label/weights.py:7-49 average_uniqueness.  concurrency is int16 and wraps silently like the reference's
+ * `concurrency[start:end+1] += 1`; the weight is np.mean(1.0 / slice) = sequential sum / size (inf on a zero entry,
+ * NaN for an empty slice where Numba's python error model would raise ZeroDivisionError). */
+int fmko_average_uniqueness(int64_t n, const int64_t *ev, const int64_t *touch, int64_t ne, int64_t ntouch,
+                            double *weights, int16_t *conc) {
+    if (ne != ntouch) return FMKO_ERR_LEN;
+    memset(conc, 0, sizeof(int16_t) * (size_t)n);
+    for (int64_t i = 0; i < ne; i++) {
+        int64_t s, e;
+        py_slice(ev[i], touch[i] + 1, n, &s, &e);
+        for (int64_t j = s; j < e; j++) conc[j] = (int16_t)(uint16_t)((uint16_t)conc[j] + 1u);
+    }
+    #pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < ne; i++) {
+        int64_t s, e;
+        py_slice(ev[i], touch[i] + 1, n, &s, &e);
+        double c = 0.0;
+        for (int64_t j = s; j < e; j++) c += 1.0 / (double)conc[j];
+        weights[i] = (e > s) ? c / (double)(e - s) : NAN;
+    }
+    return FMKO_OK;
+}
+
+/* label/weights.py:52-103 return_attribution.  Returns 1 when normalize is set and the sum of weights is <= 0
+ * (the reference raises ValueError("Sum of weights is zero or negative, cannot normalize.")). */
+int fmko_return_attribution(const int64_t *ev, const int64_t *touch, int64_t ne, const double *close, const int16_t *conc,
+                            int64_t n, int normalize, double *weights) {
+    double *lr = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    if (n > 0) lr[0] = NAN;
+    #pragma omp parallel for schedule(static)
+    for (int64_t i = 1; i < n; i++) lr[i] = close[i - 1] != 0.0 ? log(close[i] / close[i - 1]) : NAN;
+    #pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < ne; i++) {
+        double w = 0.0;
+        for (int64_t j = ev[i]; j <= touch[i]; j++)
+            if (conc[j] > 0 && !isnan(lr[j])) w += lr[j] / (double)conc[j];
+        weights[i] = fabs(w);
+    }
+    free(lr);
+    if (normalize) {
+        double s = 0.0;
+        for (int64_t i = 0; i < ne; i++) s += weights[i];
+        if (s <= 0.) return 1;
+        double f = (double)ne / s;
+        for (int64_t i = 0; i < ne; i++) weights[i] *= f;
+    }
+    return FMKO_OK;
+}

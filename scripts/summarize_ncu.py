@@ -41,7 +41,8 @@ for r in rows[2:]:
         lines.append(f"| algorithmic bytes ({algo} B/tick) | {algo * ticks / 1e9:.3f} GB |")
         lines.append(f"| measured DRAM traffic / algorithmic | {(rd + wr) / (algo * ticks):.3f} |")
         lines.append(f"| algorithmic GB/s under ncu (cold, serialised) | {algo * ticks / dur_s / 1e9:.0f} |")
-        traffic[name] = {"dram_bytes_per_launch": rd + wr, "ticks_per_launch": ticks, "bytes_per_tick": (rd + wr) / ticks}
+        traffic.setdefault(name, {})
+        if not traffic[name]: traffic[name] = {"dram_bytes_per_launch": rd + wr, "ticks_per_launch": ticks, "bytes_per_tick": (rd + wr) / ticks}
     top = sorted(((num(r[col[s]]) or 0, s) for s in stalls), reverse=True)[:4]
     lines.append("| top stall reasons (warps per issue) | " + ", ".join(f"{s.split('stalled_')[1].split('_per_')[0]} {v:.2f}" for v, s in top) + " |")
     lines.append("")
