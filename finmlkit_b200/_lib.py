@@ -69,6 +69,9 @@ SIGNATURES = {
     "fmk_ewms": (INT, [P, P, I64, I64, P]),
     "fmk_vpin": (INT, [P, P, P, I64, I64, P]),
     "fmk_flow_acceleration": (INT, [P, P, I64, I64, I64, P]),
+    "fmk_average_uniqueness": (INT, [P, I64, P, P, I64, I64, P, P]),
+    "fmk_return_attribution": (INT, [P, P, P, I64, P, P, I64, INT, P]),
+    "fmk_sample_weights": (INT, [P, P, P, P, I64, INT, P, P, P]),
     "fmk_triple_barrier": (INT, [P, P, P, P, I64, I64, F64, F64, F64, F64, P, I64, F64, P, P, P, P]),
 }
 

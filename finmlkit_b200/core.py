@@ -353,3 +353,36 @@ def flow_acceleration_series(volumes, window, recent_periods, ctx: Context = Non
     out = np.empty(len(v))
     ctx.check(ctx._L.fmk_flow_acceleration(ctx.h, _ptr(v), len(v), int(window), int(recent_periods), _ptr(out)))
     return out
+
+
+# ---- sample weights on ticks (label/weights.py) ----------------------------------------------------------------------
+def average_uniqueness_dev(n, event_idxs, touch_idxs, ctx: Context = None):
+    ctx = ctx or default_context()
+    ev, tc = _c(event_idxs, np.int64), _c(touch_idxs, np.int64)
+    w = np.zeros(len(ev))
+    conc = np.zeros(int(n), np.int16)
+    ctx.check(ctx._L.fmk_average_uniqueness(ctx.h, int(n), _ptr(ev), _ptr(tc), len(ev), len(tc), _ptr(w), _ptr(conc)))
+    return w, conc
+
+
+def return_attribution_dev(event_idxs, touch_idxs, close, concurrency, normalize, ctx: Context = None):
+    ctx = ctx or default_context()
+    ev, tc = _c(event_idxs, np.int64), _c(touch_idxs, np.int64)
+    c, cc = _c(close, np.float64), _c(concurrency, np.int16)
+    if len(cc) != len(c) or len(ev) != len(tc):
+        raise ValueError("close / concurrency and event / touch arrays must have matching lengths")
+    w = np.zeros(len(ev))
+    ctx.check(ctx._L.fmk_return_attribution(ctx.h, _ptr(ev), _ptr(tc), len(ev), _ptr(c), _ptr(cc), len(c), int(bool(normalize)), _ptr(w)))
+    return w
+
+
+def sample_weights_dev(trades: DeviceTrades, event_idxs, touch_idxs, normalize=False, want_concurrency=False):
+    """(avg_uniqueness, return_attribution[, concurrency]) in one pass over the device-resident price column."""
+    ev, tc = _c(event_idxs, np.int64), _c(touch_idxs, np.int64)
+    if len(ev) != len(tc):
+        raise ValueError("Timestamps and lookahead indices must have the same length.")
+    u, r = np.zeros(len(ev)), np.zeros(len(ev))
+    conc = np.zeros(trades.n, np.int16) if want_concurrency else None
+    ctx = trades.ctx
+    ctx.check(ctx._L.fmk_sample_weights(ctx.h, trades.h, _ptr(ev), _ptr(tc), len(ev), int(bool(normalize)), _ptr(u), _ptr(r), _ptr(conc)))
+    return (u, r, conc) if want_concurrency else (u, r)

@@ -97,3 +97,69 @@ class TBMLabel:
         self._out = pd.DataFrame({'touch_time': pd.to_datetime(ts[touch_idx]), 'event_idx': event_idx, 'touch_idx': touch_idx,
                                   'labels': labels, 'returns': rets, 'vertical_touch_weights': ratios}, index=self.features.index)
         return self.features, self.full_output
+
+    def compute_weights(self, trades, normalized: bool = False) -> pd.DataFrame:
+        """label/kit.py:315-322."""
+        return SampleWeights.compute_info_weights(trades, self._out, normalized)
+
+
+class SampleWeights:
+    """label/kit.py:325-477: average uniqueness + return attribution (GPU, one pass over the price column), then the
+    O(n_events) time-decay / class-balance combination."""
+
+    @staticmethod
+    def compute_info_weights(trades, labels: pd.DataFrame, normalize: bool = False) -> pd.DataFrame:
+        if not hasattr(trades, "data"):
+            raise ValueError("Trades must be an instance of TradesData.")
+        if not isinstance(labels, pd.DataFrame):
+            raise ValueError("Events must be a pandas DataFrame.")
+        if 'event_idx' not in labels.columns or 'touch_idx' not in labels.columns:
+            raise ValueError("Events DataFrame must contain 'event_idx' and 'touch_idxs' columns.")
+        from .. import core
+        px = trades.data.price.values
+        tr = core.DeviceTrades.upload(None, px, px)            # only the price column is read
+        avg_u, info_w = core.sample_weights_dev(tr, labels.event_idx.values, labels.touch_idx.values, normalize=normalize)
+        out_df = pd.DataFrame({'avg_uniqueness': avg_u}, index=labels.index)
+        out_df["return_attribution"] = info_w
+        return out_df
+
+    @staticmethod
+    def compute_final_weights(avg_uniqueness: pd.Series, time_decay_intercept: float = 1., return_attribution: pd.Series = None,
+                              vertical_touch_weights: pd.Series = None, labels: pd.Series = None) -> pd.DataFrame:
+        from .weights import time_decay, class_balance_weights
+        if not isinstance(avg_uniqueness, pd.Series):
+            raise ValueError("avg_uniqueness must be a pandas Series.")
+        if not isinstance(time_decay_intercept, (int, float)):
+            raise ValueError("time_decay_intercept must be a numeric value.")
+        if not -1.0 <= time_decay_intercept <= 1.0:
+            raise ValueError("time_decay_intercept must lie in [-1, 1]")
+        for name, s in (("return_attribution", return_attribution), ("vertical_touch_weights", vertical_touch_weights), ("labels", labels)):
+            if s is not None and not isinstance(s, pd.Series):
+                raise ValueError(f"{name} must be a pandas Series.")
+        for name, s in (("return_attribution", return_attribution), ("vertical_touch_weights", vertical_touch_weights), ("labels", labels)):
+            if s is not None and not avg_uniqueness.index.equals(s.index):
+                raise ValueError(f"avg_uniqueness and {name} must have the same index.")
+        n_events = len(avg_uniqueness)
+        time_decay_weights = time_decay(avg_uniqueness.values, time_decay_intercept)
+        out_df = pd.DataFrame({'time_decay_weights': time_decay_weights}, index=avg_uniqueness.index)
+        if return_attribution is not None:
+            if return_attribution.sum() <= 0:
+                raise ValueError("Return attribution sum is zero or negative, cannot normalize.")
+            ra = return_attribution.values * n_events / return_attribution.sum()
+            out_df["return_attribution"] = ra
+            combined = time_decay_weights * ra
+        else:
+            combined = time_decay_weights * avg_uniqueness.values
+        if vertical_touch_weights is not None:
+            out_df["vertical_touch_weights"] = vertical_touch_weights.values
+            combined = combined * vertical_touch_weights.values
+        mean_combined = combined.mean()
+        if mean_combined <= 0:
+            raise ValueError("Mean of combined weights is zero or negative, cannot normalize.")
+        base_weights = combined / mean_combined
+        if labels is not None:
+            _, _, _, final_weights = class_balance_weights(labels.values, base_weights)
+        else:
+            final_weights = base_weights
+        out_df["weights"] = final_weights
+        return out_df

@@ -151,6 +151,19 @@ int fmk_triple_barrier(fmk_ctx *ctx, const fmk_trades *t, const int64_t *event_i
                        double vertical_barrier_s, double min_close_time_s, const int8_t *side, int64_t n_side,
                        double min_ret, int8_t *labels, int64_t *touch_idx, double *rets, double *max_rb_ratios);
 
+/* ---- sample weights on ticks (label/weights.py) ----------------------------------------------------------
+ * Indices must lie in [0, n).  concurrency is int16 with the reference's silent wrap-around. */
+/* average_uniqueness, label/weights.py:7-49: weights f64[n_events], concurrency i16[n] (either may be NULL) */
+int fmk_average_uniqueness(fmk_ctx *ctx, int64_t n, const int64_t *event_idx, const int64_t *touch_idx, int64_t n_events,
+                           int64_t n_touch, double *weights, int16_t *concurrency);
+/* return_attribution, label/weights.py:52-103 (host close / concurrency arrays, as the reference passes them) */
+int fmk_return_attribution(fmk_ctx *ctx, const int64_t *event_idx, const int64_t *touch_idx, int64_t n_events,
+                           const double *close, const int16_t *concurrency, int64_t n, int normalize, double *weights);
+/* both in one pass over the device-resident price column (SampleWeights.compute_info_weights, label/kit.py:329-366) */
+int fmk_sample_weights(fmk_ctx *ctx, const fmk_trades *t, const int64_t *event_idx, const int64_t *touch_idx,
+                       int64_t n_events, int normalize, double *avg_uniqueness, double *return_attribution,
+                       int16_t *concurrency);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,7 +127,52 @@ def case_stream(name, ts, px, qty, side, *, interval=60.0, tick_thr=100, vol_thr
     print(f"{name}: n={len(ts)} bars={nb} events={len(out.get('in_tbm_events', []))}")
 
 
+def weights_cases():
+    """SURVEY 8f-1 sample weights: reference outputs on the synth_20k TBM events, an int16 wrap-around case and a series
+    with a zero close (infinite log return)."""
+    from finmlkit.label.weights import average_uniqueness, return_attribution, time_decay, class_balance_weights
+    g = dict(np.load(os.path.join(HERE, "synth_20k.npz")))
+    out = {}
+    ts, px = g["in_ts"], g["in_px"]
+    ev, tc = g["in_tbm_events"], g["ref_tbm_touch"]
+    out["a_ts"], out["a_px"], out["a_ev"], out["a_touch"] = ts, px, ev, tc
+    w, c = average_uniqueness(ts, ev, tc)
+    out["a_ref_avg_u"], out["a_ref_conc"] = w, c
+    out["a_ref_ra"] = return_attribution(ev, tc, px, c, False)
+    out["a_ref_ra_norm"] = return_attribution(ev, tc, px, c, True)
+    out["a_ref_decay_05"] = time_decay(w, 0.5)
+    out["a_ref_decay_m03"] = time_decay(w, -0.3)
+    lab = g["ref_tbm_labels"]
+    cb = class_balance_weights(lab, w)
+    out["a_labels"] = lab
+    for k in range(4):
+        out[f"a_ref_cb_{k}"] = cb[k]
+    # int16 wrap: 70 000 identical labels over ticks 10..20 plus a few ordinary ones; a zero close inside a label
+    n = 400
+    rng = np.random.default_rng(3)
+    ts2 = np.arange(n, dtype=np.int64)
+    px2 = np.round(100 + np.cumsum(rng.normal(0, 0.05, n)), 2)
+    px2[300] = 0.0
+    ev2 = np.concatenate([np.full(70000, 10), np.array([0, 5, 15, 100, 250, 290, 310, 399])]).astype(np.int64)
+    tc2 = np.concatenate([np.full(70000, 20), np.array([30, 5, 18, 260, 299, 305, 398, 399])]).astype(np.int64)
+    w2, c2 = average_uniqueness(ts2, ev2, tc2)
+    out["b_ts"], out["b_px"], out["b_ev"], out["b_touch"] = ts2, px2, ev2, tc2
+    out["b_ref_avg_u"], out["b_ref_conc"] = w2, c2
+    out["b_ref_ra"] = return_attribution(ev2, tc2, px2, c2, False)
+    # 65 536 identical labels: the wrapped concurrency is exactly 0 inside the labels -> inf uniqueness
+    ev3 = np.concatenate([np.full(65536, 10), np.array([12, 50])]).astype(np.int64)
+    tc3 = np.concatenate([np.full(65536, 20), np.array([60, 70])]).astype(np.int64)
+    w3, c3 = average_uniqueness(ts2, ev3, tc3)
+    out["c_ev"], out["c_touch"], out["c_ref_avg_u"], out["c_ref_conc"] = ev3, tc3, w3, c3
+    out["c_ref_ra"] = return_attribution(ev3, tc3, px2, c3, False)
+    np.savez_compressed(os.path.join(HERE, "weights.npz"), **out)
+    print("weights: events", len(ev), "max concurrency", int(c.max()), "wrap conc", int(c2[15]), "zero-wrap", int(c3[15]), w3[:1])
+
+
 def main():
+    if "--only-weights" in sys.argv:
+        weights_cases()
+        return
     # 1. plain synthetic stream (same generator the bench uses)
     ts, px, qty, side = synth_trades(20000, seed=42)
     case_stream("synth_20k", ts, px, qty, side)
@@ -164,6 +209,7 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"clock_{iv}.npz"), in_ts=ts, in_interval=np.array([iv]),
                             ref_time_clock=clock, ref_time_idx=idx)
 
+    weights_cases()
     crosscheck()
 
 
