@@ -295,6 +295,9 @@ extern "C" int fmk_index_from_host(fmk_ctx *ctx, const fmk_trades *t, const int6
     memset(ix, 0, sizeof(*ix));
     ix->m = m;
     ix->n_ticks = t->n;
+    ix->sorted = 1;     // caller-provided indices: verify (the tiled OHLCV kernel needs monotone in-range indices)
+    for (int64_t k = 0; k < m; k++)
+        if (close_idx[k] < -1 || close_idx[k] >= t->n || (k > 0 && close_idx[k] < close_idx[k - 1])) { ix->sorted = 0; break; }
     int rc = fmk_dalloc(ctx, &ix->close_idx, m);
     if (rc) { delete ix; return rc; }
     if (m > 0) {
@@ -363,6 +366,7 @@ extern "C" int fmk_time_bar_index(fmk_ctx *ctx, const fmk_trades *t, double inte
     memset(ix, 0, sizeof(*ix));
     ix->m = m;
     ix->n_ticks = t->n;
+    ix->sorted = 1;
     int rc = fmk_dalloc(ctx, &ix->close_ts, m);
     if (!rc) rc = fmk_dalloc(ctx, &ix->close_idx, m);
     if (rc) { fmk_index_free(ctx, ix); return rc; }
@@ -396,6 +400,7 @@ extern "C" int fmk_tick_bar_index(fmk_ctx *ctx, const fmk_trades *t, int64_t thr
     memset(ix, 0, sizeof(*ix));
     ix->m = m;
     ix->n_ticks = n;
+    ix->sorted = 1;
     int rc = fmk_dalloc(ctx, &ix->close_idx, m);
     if (rc) { fmk_index_free(ctx, ix); return rc; }
     k_tick_bar<<<(unsigned)cdiv(m, 256), 256, 0, ctx->stream>>>(m, threshold, ix->close_idx);

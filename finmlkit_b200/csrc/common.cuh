@@ -51,6 +51,7 @@ struct fmk_index {
     int64_t n_ticks;    // length of the trade arrays it indexes
     int64_t *close_ts;  // may be null for fmk_index_from_host without timestamps
     int64_t *close_idx;
+    int sorted;         // close_idx is non-decreasing and within [-1, n_ticks): always true for device-built indices
 };
 
 struct fmk_buf {

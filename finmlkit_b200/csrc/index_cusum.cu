@@ -274,6 +274,7 @@ int fmk_cusum_index_impl(fmk_ctx *ctx, const fmk_trades *t, fmk_buf *sigma, doub
     memset(ix, 0, sizeof(*ix));
     ix->m = total + 1;
     ix->n_ticks = n;
+    ix->sorted = 1;
     ix->close_idx = idx;
     int rc = fmk_gather_close_ts(ctx, t, ix);
     if (rc) { fmk_index_free(ctx, ix); return rc; }

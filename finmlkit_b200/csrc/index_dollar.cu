@@ -488,6 +488,7 @@ int fmk_dollar_index_impl(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index
     memset(ix, 0, sizeof(*ix));
     ix->m = K_total + 1;
     ix->n_ticks = n;
+    ix->sorted = 1;
     ix->close_idx = idx;
     idx = nullptr;  // ownership moved
     int rc = fmk_gather_close_ts(ctx, t, ix);

@@ -249,6 +249,7 @@ static int finish_index(fmk_ctx *ctx, const fmk_trades *t, int64_t *idx, int64_t
     memset(ix, 0, sizeof(*ix));
     ix->m = m;
     ix->n_ticks = t->n;
+    ix->sorted = 1;
     ix->close_idx = idx;
     int rc = fmk_gather_close_ts(ctx, t, ix);
     if (rc) { fmk_index_free(ctx, ix); return rc; }

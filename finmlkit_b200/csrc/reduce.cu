@@ -6,6 +6,7 @@
 // deterministic.  When bars are very short (avg < 8 ticks) a thread-per-bar variant is used instead.
 // HBM traffic: price + amount read once (16 B/tick) for OHLCV; amount once more (8 B/tick) for the median.
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 #include "common.cuh"
 #include "scan.cuh"
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(OS_WARPS * 32) k_bar_order_stats(const double 
 
 // Fused comp_bar_ohlcv: one warp streams the bar once from HBM (price + amount: O/H/L/C, sums, and the OR/AND of the
 // amount keys), then runs the radix select for the median on the amounts it has just pulled through L1/L2.
-__global__ void __launch_bounds__(OS_WARPS * 32) k_bar_ohlcv_median(const double *__restrict__ p,
+__global__ void __launch_bounds__(OS_WARPS * 32) k_bar_ohlcv_median_v1(const double *__restrict__ p,
                                                                     const double *__restrict__ v,
                                                                     const int64_t *__restrict__ ci, int64_t nb, int64_t n,
                                                                     OhlcvOut o, double *__restrict__ median_out) {
@@ -389,6 +390,242 @@ __global__ void __launch_bounds__(OS_WARPS * 32) k_bar_ohlcv_median(const double
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Order statistics on RAW bit patterns.  Trade sizes are never negative, and for non-negative doubles the IEEE bit
+// pattern orders like the value, so the per-element key transform (14 % of the fused kernel's instructions) can be
+// dropped; the histogram passes then only need the HIGH 32-bit word of each amount (LDG.32, 32-bit integer ops), and
+// full 64-bit values are touched only for the <= 32 final candidates.  A bar that holds a negative size / -0.0 (sign
+// bit in the OR of the patterns) or whose sizes differ only below the high word takes warp_select_two instead.
+//   h1  1024-bin histogram (two 16-bit counters per word, bank-transposed for a conflict-free two-level scan) of the
+//       10 bits below the highest differing high-word bit; repeated on the selected bucket while it holds > 32 distinct
+//       candidates
+//   h2  bucket of <= 32: members fetched by index and ranked in registers; bucket of > 32: OR/AND of the members --
+//       exchange-quantised sizes make them identical, which ends the search
+//   h3  (k+1)-th statistic above the bucket, when needed: min over the members of the higher buckets
+// Returns false when the caller has to fall back to the generic select.  cnt < 65536 (packed counters).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int RS_WORDS = 512;
+__device__ __forceinline__ unsigned rs_word(unsigned d) {   // lane L of the scan owns bins [32L, 32L+32) = words q*32 + L
+    const unsigned w = d >> 1;
+    return ((w & 15u) << 5) | (w >> 4);
+}
+
+__device__ bool warp_select_raw(const double *__restrict__ seg, int ncnt, int kk, bool want1, unsigned long long ro,
+                                unsigned long long ra, unsigned *hist, double *r0, double *r1) {
+    const int lane = threadIdx.x & 31;
+    const unsigned *segw = reinterpret_cast<const unsigned *>(seg);   // high word of element q: segw[2q + 1]
+    unsigned *cidx = hist + RS_WORDS;          // 32 candidate indices
+    unsigned *ccnt = hist + RS_WORDS + 32;     // append counter
+    unsigned diff_hi = (unsigned)((ro ^ ra) >> 32);
+    if (diff_hi == 0u) return false;
+    unsigned mask = 0u, prefix = 0u, upper = (unsigned)(ra >> 32);
+    for (;;) {
+        const int hb = 31 - __clz(diff_hi);
+        const int shift = hb >= 9 ? hb - 9 : 0;
+#pragma unroll
+        for (int q = 0; q < RS_WORDS / 32; q++) hist[q * 32 + lane] = 0u;
+        __syncwarp();
+        {
+            int q = lane;
+            if (mask == 0u) {                  // first level: every element is in play
+                for (; q + 96 < ncnt; q += 128) {
+                    const unsigned h0 = __ldg(segw + 2 * q + 1), h1 = __ldg(segw + 2 * q + 65),
+                                   h2 = __ldg(segw + 2 * q + 129), h3 = __ldg(segw + 2 * q + 193);
+                    const unsigned d0 = (h0 >> shift) & 1023u, d1 = (h1 >> shift) & 1023u, d2 = (h2 >> shift) & 1023u,
+                                   d3 = (h3 >> shift) & 1023u;
+                    atomicAdd(&hist[rs_word(d0)], (d0 & 1u) ? 65536u : 1u);
+                    atomicAdd(&hist[rs_word(d1)], (d1 & 1u) ? 65536u : 1u);
+                    atomicAdd(&hist[rs_word(d2)], (d2 & 1u) ? 65536u : 1u);
+                    atomicAdd(&hist[rs_word(d3)], (d3 & 1u) ? 65536u : 1u);
+                }
+                for (; q < ncnt; q += 32) {
+                    const unsigned d = (__ldg(segw + 2 * q + 1) >> shift) & 1023u;
+                    atomicAdd(&hist[rs_word(d)], (d & 1u) ? 65536u : 1u);
+                }
+            } else {
+#pragma unroll 4
+                for (; q < ncnt; q += 32) {
+                    const unsigned h = __ldg(segw + 2 * q + 1);
+                    if ((h & mask) == prefix) {
+                        const unsigned d = (h >> shift) & 1023u;
+                        atomicAdd(&hist[rs_word(d)], (d & 1u) ? 65536u : 1u);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        unsigned ps = 0;
+#pragma unroll
+        for (int q = 0; q < RS_WORDS / 32; q++) ps += hist[q * 32 + lane];
+        const unsigned ssum = (ps & 0xffffu) + (ps >> 16);
+        unsigned inc = ssum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned y = __shfl_up_sync(FULL, inc, d);
+            if (lane >= d) inc += y;
+        }
+        const unsigned exc = inc - ssum;
+        const unsigned kq = (unsigned)kk;
+        const int owner = __ffs(__ballot_sync(FULL, kq >= exc && kq < inc)) - 1;
+        const unsigned exc_owner = __shfl_sync(FULL, exc, owner);
+        const unsigned wv = hist[((lane >> 1) << 5) | owner];
+        const unsigned bv = (lane & 1) ? (wv >> 16) : (wv & 0xffffu);
+        unsigned inc2 = bv;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned y = __shfl_up_sync(FULL, inc2, d);
+            if (lane >= d) inc2 += y;
+        }
+        const unsigned exc2 = inc2 - bv;
+        const unsigned k2 = kq - exc_owner;
+        const int sel = __ffs(__ballot_sync(FULL, k2 >= exc2 && k2 < inc2)) - 1;
+        const unsigned bsel = (unsigned)(owner * 32 + sel);
+        const int c1 = (int)__shfl_sync(FULL, bv, sel);
+        kk = (int)(k2 - __shfl_sync(FULL, exc2, sel));          // rank inside the bucket
+        const unsigned above_mask = (shift + 10 >= 32) ? 0u : (~0u << (shift + 10));
+        mask = above_mask | (1023u << shift);
+        prefix = (upper & above_mask) | (bsel << shift);
+        const bool inside1 = kk + 1 < c1;
+        unsigned long long key0 = 0ull, key1 = 0ull;
+        bool resolved = false;
+        if (c1 <= 32) {
+            if (lane == 0) *ccnt = 0u;
+            __syncwarp();
+            {
+                int q = lane;
+                for (; q + 96 < ncnt; q += 128) {
+                    const unsigned h0 = __ldg(segw + 2 * q + 1), h1 = __ldg(segw + 2 * q + 65),
+                                   h2 = __ldg(segw + 2 * q + 129), h3 = __ldg(segw + 2 * q + 193);
+                    if ((h0 & mask) == prefix) cidx[atomicAdd(ccnt, 1u) & 31u] = (unsigned)q;
+                    if ((h1 & mask) == prefix) cidx[atomicAdd(ccnt, 1u) & 31u] = (unsigned)(q + 32);
+                    if ((h2 & mask) == prefix) cidx[atomicAdd(ccnt, 1u) & 31u] = (unsigned)(q + 64);
+                    if ((h3 & mask) == prefix) cidx[atomicAdd(ccnt, 1u) & 31u] = (unsigned)(q + 96);
+                }
+                for (; q < ncnt; q += 32)
+                    if ((__ldg(segw + 2 * q + 1) & mask) == prefix) cidx[atomicAdd(ccnt, 1u) & 31u] = (unsigned)q;
+            }
+            __syncwarp();
+            const unsigned long long mine =
+                lane < c1 ? (unsigned long long)__double_as_longlong(__ldg(seg + cidx[lane])) : ~0ull;
+            int rank = 0;
+            for (int q = 0; q < c1; q++) {
+                const unsigned long long x = __shfl_sync(FULL, mine, q);
+                rank += (x < mine) || (x == mine && q < lane);
+            }
+            const unsigned b0 = __ballot_sync(FULL, lane < c1 && rank == kk);
+            key0 = __shfl_sync(FULL, mine, __ffs(b0) - 1);
+            if (want1 && inside1) {
+                const unsigned b1 = __ballot_sync(FULL, lane < c1 && rank == kk + 1);
+                key1 = __shfl_sync(FULL, mine, __ffs(b1) - 1);
+            }
+            resolved = true;
+        } else {
+            unsigned long long bo = 0ull, ba = ~0ull;
+#pragma unroll 4
+            for (int q = lane; q < ncnt; q += 32)
+                if ((__ldg(segw + 2 * q + 1) & mask) == prefix) {
+                    const unsigned long long key = (unsigned long long)__double_as_longlong(__ldg(seg + q));
+                    bo |= key; ba &= key;
+                }
+            bo = warp_or64(bo); ba = warp_and64(ba);
+            if (bo == ba) { key0 = bo; key1 = bo; resolved = true; }
+            else {
+                upper = (unsigned)(ba >> 32);                   // common bits of the members
+                diff_hi = (unsigned)((bo ^ ba) >> 32);
+                if (diff_hi == 0u || shift == 0) return false;  // members differ only below the high word
+            }
+        }
+        if (resolved) {
+            if (want1 && !inside1) {              // the (k+1)-th statistic is the smallest value above the bucket
+                const unsigned hi_bound = prefix | ~mask;
+                unsigned long long amin = ~0ull;
+#pragma unroll 4
+                for (int q = lane; q < ncnt; q += 32)
+                    if (__ldg(segw + 2 * q + 1) > hi_bound) {
+                        const unsigned long long key = (unsigned long long)__double_as_longlong(__ldg(seg + q));
+                        amin = key < amin ? key : amin;
+                    }
+                key1 = warp_min64(amin);
+            }
+            *r0 = __longlong_as_double((long long)key0);
+            *r1 = __longlong_as_double((long long)key1);
+            return true;
+        }
+    }
+}
+
+// Fused comp_bar_ohlcv (the kernel run_ohlcv launches): one warp streams its bar once from HBM (O/H/L/C, sums, OR/AND
+// of the raw size patterns), then selects the median on the sizes it has just pulled through L1/L2.
+__global__ void __launch_bounds__(OS_WARPS * 32) k_bar_ohlcv_median(const double *__restrict__ p,
+                                                                    const double *__restrict__ v,
+                                                                    const int64_t *__restrict__ ci, int64_t nb, int64_t n,
+                                                                    OhlcvOut o, double *__restrict__ median_out) {
+    __shared__ unsigned hist_s[OS_WARPS][OS_HIST];
+    __shared__ unsigned long long cand_s[OS_WARPS][32];
+    static_assert(RS_WORDS + 33 <= OS_HIST, "raw-select scratch must fit the generic histogram");
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nb; i += nwarps) {
+        const int64_t s = ci[i], e = ci[i + 1];
+        if (s == e) {
+            if (lane == 0) { ohlcv_empty(o, i, p, e, n); median_out[i] = 0.0; }
+            continue;
+        }
+        const int64_t start = s + 1;
+        double hi = -INFINITY, lo = INFINITY, sv = 0.0, sd = 0.0;
+        unsigned long long ro = 0ull, ra = ~0ull;
+        int64_t j = start + lane;
+        for (; j + 96 <= e; j += 128) {
+            const double p0 = __ldg(p + j), p1 = __ldg(p + j + 32), p2 = __ldg(p + j + 64), p3 = __ldg(p + j + 96);
+            const double v0 = __ldg(v + j), v1 = __ldg(v + j + 32), v2 = __ldg(v + j + 64), v3 = __ldg(v + j + 96);
+            // strict compares like the reference (base.py:381-384): a NaN price never replaces the running high / low
+            hi = p0 > hi ? p0 : hi; hi = p1 > hi ? p1 : hi; hi = p2 > hi ? p2 : hi; hi = p3 > hi ? p3 : hi;
+            lo = p0 < lo ? p0 : lo; lo = p1 < lo ? p1 : lo; lo = p2 < lo ? p2 : lo; lo = p3 < lo ? p3 : lo;
+            sv += (v0 + v1) + (v2 + v3);
+            sd += (p0 * v0 + p1 * v1) + (p2 * v2 + p3 * v3);
+            const unsigned long long k0 = (unsigned long long)__double_as_longlong(v0), k1 = (unsigned long long)__double_as_longlong(v1),
+                                     k2 = (unsigned long long)__double_as_longlong(v2), k3 = (unsigned long long)__double_as_longlong(v3);
+            ro |= (k0 | k1) | (k2 | k3);
+            ra &= (k0 & k1) & (k2 & k3);
+        }
+        for (; j <= e; j += 32) {
+            const double pj = __ldg(p + j), vj = __ldg(v + j);
+            hi = pj > hi ? pj : hi; lo = pj < lo ? pj : lo;
+            sv += vj; sd += pj * vj;
+            const unsigned long long kj = (unsigned long long)__double_as_longlong(vj);
+            ro |= kj; ra &= kj;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const double h2 = __shfl_xor_sync(FULL, hi, d), l2 = __shfl_xor_sync(FULL, lo, d);
+            hi = h2 > hi ? h2 : hi;
+            lo = l2 < lo ? l2 : lo;
+        }
+        sv = warp_sum(sv); sd = warp_sum(sd);
+        ro = warp_or64(ro); ra = warp_and64(ra);
+        const int64_t cnt = e - start + 1;
+        if (lane == 0) {
+            o.open[i] = p[start]; o.close[i] = p[e]; o.high[i] = hi; o.low[i] = lo;
+            o.volume[i] = (float)sv;
+            o.vwap[i] = sv > 0 ? sd / sv : 0.0;
+            o.trades[i] = cnt;
+        }
+        const bool odd = cnt & 1;
+        const int64_t mk = odd ? (cnt >> 1) : (cnt >> 1) - 1;
+        double r0, r1;
+        bool done = false;
+        if (ro == ra) { r0 = r1 = __longlong_as_double((long long)ro); done = true; }      // all sizes identical
+        else if (!(ro >> 63) && cnt < 65536) done = warp_select_raw(v + start, (int)cnt, (int)mk, !odd, ro, ra, hist_s[w], &r0, &r1);
+        if (!done) {
+            __syncwarp();
+            warp_select_two(v + start, cnt, mk, hist_s[w], cand_s[w], &r0, &r1);
+        }
+        if (lane == 0) median_out[i] = odd ? r0 : (r0 + r1) / 2;
+    }
+}
+
+#include "ohlcv_conveyor.cuh"
+
 static int launch_order_stats(fmk_ctx *ctx, const double *a, const int64_t *ci, int64_t nb, int mode, double *med,
                               double *p95) {
     if (nb <= 0) return FMK_OK;
@@ -411,6 +648,18 @@ static int run_ohlcv(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, Ohl
         int64_t blocks = cdiv(nb, OS_WARPS);
         const int64_t maxb = (int64_t)ctx->sm_count * 16;
         if (blocks > maxb) blocks = maxb;
+        // FMK_MEDIAN_KERNEL=v1|conveyor selects the earlier variants for A/B profiling
+        static const char *variant = getenv("FMK_MEDIAN_KERNEL");
+        if (variant && variant[0] == 'c' && ix->sorted && ((((uintptr_t)t->price | (uintptr_t)t->amount) & 15u) == 0) && t->n / nb <= 1536) {
+            const size_t smem = sizeof(CvShared);
+            FMK_CUDA(ctx, cudaFuncSetAttribute(k_bar_ohlcv_conveyor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FMK_LAUNCH(ctx, k_bar_ohlcv_conveyor, (unsigned)ctx->sm_count, CV_THREADS, smem, t->price, t->amount, ix->close_idx, nb, t->n, o, median);
+            return FMK_OK;
+        }
+        if (variant && variant[0] == 'v') {
+            FMK_LAUNCH(ctx, k_bar_ohlcv_median_v1, (unsigned)blocks, OS_WARPS * 32, 0, t->price, t->amount, ix->close_idx, nb, t->n, o, median);
+            return FMK_OK;
+        }
         FMK_LAUNCH(ctx, k_bar_ohlcv_median, (unsigned)blocks, OS_WARPS * 32, 0, t->price, t->amount, ix->close_idx, nb, t->n, o, median);
         return FMK_OK;
     }

@@ -2,7 +2,7 @@
    ncu -i X.ncu-rep --page raw --csv > raw.csv ; python scripts/summarize_ncu.py raw.csv <ticks> profiles/NAME.md"""
 import csv, json, os, sys
 
-ALGO = {"k_dollar_tasks": 16, "k_dollar_chunk_sums": 16, "k_bar_ohlcv_median": 16, "k_bar_ohlcv_warp": 16, "k_bar_order_stats": 8}
+ALGO = {"k_dollar_tasks": 16, "k_dollar_chunk_sums": 16, "k_bar_ohlcv_median": 16, "k_bar_ohlcv_warp": 16, "k_bar_ohlcv_conveyor": 16, "k_bar_ohlcv_median_v1": 16, "k_bar_order_stats": 8}
 rows = list(csv.reader(open(sys.argv[1])))
 ticks = float(sys.argv[2])
 out = sys.argv[3]
