@@ -7,12 +7,13 @@
 //   C   k_dollar_chain      : single-block parallel composition of the per-task integer transfer functions,
 //                             certification of every task against the true carried state
 //   S   k_dollar_serial     : exact serial replay from the last certified state (repair path only)
+#include <stdlib.h>
 #include <new>
 #include "common.cuh"
 #include "dollar_core.h"
 #include "scan.cuh"
 
-constexpr int DOLLAR_CH = 4096;
+constexpr int DOLLAR_CH = 4096;          // default ticks per task; large inputs pick a wave-filling size (dollar_pick_chunk)
 constexpr int DOLLAR_A_THREADS = 256;
 
 struct LdG {
@@ -22,12 +23,12 @@ struct LdG {
 
 __global__ void __launch_bounds__(DOLLAR_A_THREADS) k_dollar_chunk_sums(const double *__restrict__ p,
                                                                         const double *__restrict__ v, int64_t n,
-                                                                        dd_t *__restrict__ sums) {
+                                                                        int CH, dd_t *__restrict__ sums) {
     __shared__ dd_t sm[DOLLAR_A_THREADS / 32];
-    const int64_t base = (int64_t)blockIdx.x * DOLLAR_CH;
+    const int64_t base = (int64_t)blockIdx.x * CH;
     dd_t s = {0.0, 0.0};
-#pragma unroll
-    for (int k = 0; k < DOLLAR_CH / DOLLAR_A_THREADS; k++) {
+#pragma unroll 8
+    for (int k = 0; k < CH / DOLLAR_A_THREADS; k++) {
         const int64_t i = base + threadIdx.x + (int64_t)k * DOLLAR_A_THREADS;
         if (i < n) s = dd_add_d(s, __dmul_rn(__ldg(p + i), __ldg(v + i)));
     }
@@ -377,12 +378,36 @@ __global__ void __launch_bounds__(32) k_dollar_serial(const double *__restrict__
 
 __global__ void k_set_i64(int64_t *p, int64_t v) { *p = v; }
 
+// Every task (one lane) replays its chunk plus about one bar, and all tasks take the same time, so the task kernel's
+// duration is (number of waves) x (chunk + overlap).  With the default 4096-tick chunks 1e9 ticks are 2.6 waves of the
+// resident lanes, i.e. three rounds with the last one mostly idle.  For inputs of at least one full wave the chunk is
+// sized so that the tasks fill an integer number of waves (multiple of 256 ticks, 4096..16384).
+static int64_t dollar_pick_chunk(fmk_ctx *ctx, int64_t n) {
+    int bps = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_dollar_tasks, DT_WARPS * 32, 0) != cudaSuccess || bps <= 0)
+        return DOLLAR_CH;
+    const int64_t resident = (int64_t)bps * ctx->sm_count * DT_WARPS * 32;
+    if (n < resident * DOLLAR_CH) return DOLLAR_CH;
+    int64_t best = DOLLAR_CH;
+    double best_cost = 1e300;
+    for (int64_t W = 1; W <= 64; W++) {
+        int64_t ch = cdiv(cdiv(n, W * resident), DOLLAR_A_THREADS) * DOLLAR_A_THREADS;
+        if (ch > 16384) continue;
+        if (ch < DOLLAR_CH) break;
+        const int64_t waves = cdiv(cdiv(n, ch), resident);
+        const double cost = (double)waves * (double)(ch + 768);     // 768: a typical bar of overlap
+        if (cost < best_cost) { best_cost = cost; best = ch; }
+    }
+    return best;
+}
+
 int fmk_dollar_index_impl(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index **out_ix) {
     *out_ix = nullptr;
     const int64_t n = t->n;
     if (n <= 0) return fmk_fail(ctx, FMK_ERR_ARG, "empty trades");
     if (T != T) return fmk_fail(ctx, FMK_ERR_ARG, "threshold is NaN");
-    const int64_t CH = DOLLAR_CH;
+    static const char *ch_env = getenv("FMK_DOLLAR_CH");            // profiling override (multiple of 256)
+    const int64_t CH = ch_env ? (int64_t)atoll(ch_env) : dollar_pick_chunk(ctx, n);
     const int64_t nt = cdiv(n, CH);
     ctx->stats[0] = nt; ctx->stats[1] = 0; ctx->stats[2] = 0;
 
@@ -401,7 +426,7 @@ int fmk_dollar_index_impl(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index
     const bool fast = dollar_params_init(&P, T, n, CH, 0);
     int64_t cap = n + 1;
     if (fast) {
-        FMK_LAUNCH(ctx, k_dollar_chunk_sums, (unsigned)nt, DOLLAR_A_THREADS, 0, t->price, t->amount, n, sums.p);
+        FMK_LAUNCH(ctx, k_dollar_chunk_sums, (unsigned)nt, DOLLAR_A_THREADS, 0, t->price, t->amount, n, (int)CH, sums.p);
         Scratch<DD> dtot(ctx);
         FMK_TRY(dtot.alloc(1));
         FMK_TRY((device_inclusive_scan<DD>(ctx, SumIn{sums.p}, GuessOut{K_in.p, carry.p, nt, T}, nt, dtot.p)));
