@@ -10,12 +10,17 @@
 //                                     "may close" flag (fully parallel; the libm calls live here)
 //   C2  k_cusum_tasks   : one lane per chunk; warm-up over the PREVIOUS chunk from the zero state, record the state
 //                         reached at the chunk start (speculative), then replay the chunk marking closes in a bitmap
-//   C3  k_cusum_verify  : single thread walks the chunks with the TRUE state; a chunk whose speculative start state
-//                         is bit-identical to the true one is accepted as is, otherwise it is replayed exactly
+//   C3  k_cusum_check / k_cusum_tasks(work list) : parallel fix-point.  Chunk k is consistent when the state it started
+//                         from is bit-identical to the end state of chunk k-1; every inconsistent chunk is replayed (all of
+//                         them in parallel, one lane each) from its predecessor's current end state, and the check is
+//                         repeated until nothing changes.  Chunk 0 starts from the true initial state, so by induction the
+//                         fixed point is the sequential trajectory; the number of rounds is the longest run of chunks
+//                         over which the state fails to coalesce (a handful on market data; n_chunks in the worst case)
 //   C4  bitmap -> index list (popcount scan + ordered write)
 // Given identical r_i the result is the reference's, bit for bit; r_i itself uses CUDA's log (<= 1 ulp from glibc's),
 // which can only matter at an exact tie of a ~1e-19-wide band (documented in DESIGN.md).
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 #include "common.cuh"
 #include "scan.cuh"
@@ -48,7 +53,10 @@ struct FFOut {
 
 __global__ void k_cusum_first(const double *__restrict__ sigma, int64_t n, unsigned long long *first) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && sigma[i] == sigma[i]) atomicMin(first, (unsigned long long)i);
+    // one atomic per warp at most, and none once a smaller index is already recorded
+    const unsigned ok = __ballot_sync(0xffffffffu, i < n && sigma[i] == sigma[i]);
+    if (ok && (threadIdx.x & 31) == (unsigned)(__ffs(ok) - 1) && (unsigned long long)i < *(volatile unsigned long long *)first)
+        atomicMin(first, (unsigned long long)i);
 }
 
 __global__ void k_cusum_prep(const int64_t *__restrict__ ts, const double *__restrict__ p,
@@ -85,12 +93,17 @@ __global__ void __launch_bounds__(CT_WARPS * 32) k_cusum_tasks(const double *__r
                                                                int64_t first, int64_t CH, int64_t nchunks,
                                                                unsigned *__restrict__ bitmap,
                                                                CusumState *__restrict__ spec_start,
-                                                               CusumState *__restrict__ spec_end) {
+                                                               CusumState *__restrict__ spec_end,
+                                                               const int64_t *__restrict__ work, int64_t nwork,
+                                                               const CusumState *__restrict__ prev_end) {
     __shared__ double sr[CT_WARPS][32][CT_R + 1];
     __shared__ double sl[CT_WARPS][32][CT_R + 1];
     __shared__ uint8_t sa[CT_WARPS][32][CT_R];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t k = ((int64_t)blockIdx.x * CT_WARPS + w) * 32 + lane;
+    const int64_t tid = ((int64_t)blockIdx.x * CT_WARPS + w) * 32 + lane;
+    // work == nullptr: speculative pass over every chunk; otherwise replay of the listed chunks from prev_end[k-1]
+    int64_t k = tid;
+    if (work) k = tid < nwork ? work[tid] : nchunks;
     const int64_t lo = first + 1 + k * CH;              // first tick of the chunk (ticks <= first are never tested)
     int64_t hi = lo + CH;
     if (hi > n) hi = n;
@@ -98,6 +111,7 @@ __global__ void __launch_bounds__(CT_WARPS * 32) k_cusum_tasks(const double *__r
     int64_t pos = lo - CH;                              // warm-up over the previous chunk
     if (pos < first + 1) pos = first + 1;
     CusumState s{0.0, 0.0};
+    if (work && active) { pos = lo; s = prev_end[k - 1]; }   // listed chunks have k >= 1
     unsigned word = 0;
     const int half = lane >> 4, col = lane & 15;
     if (active && pos == lo) spec_start[k] = s;        // chunk 0: the true initial state
@@ -135,50 +149,19 @@ __global__ void __launch_bounds__(CT_WARPS * 32) k_cusum_tasks(const double *__r
     if (k < nchunks && lo < n) spec_end[k] = s;
 }
 
-// C3: accept or repair, chunk by chunk, with the true state.  One block: the speculative states are staged through
-// shared memory in tiles so the serial walk of thread 0 never waits on a dependent global load.
-constexpr int CV_TILE = 1024;
-__global__ void __launch_bounds__(256) k_cusum_verify(const double *__restrict__ r, const double *__restrict__ lam,
-                                                      const uint8_t *__restrict__ allowed, int64_t n, int64_t first,
-                                                      int64_t CH, int64_t nchunks, unsigned *bitmap,
-                                                      const CusumState *__restrict__ spec_start,
-                                                      const CusumState *__restrict__ spec_end, int64_t *repairs) {
-    __shared__ CusumState ss[CV_TILE], se[CV_TILE];
-    __shared__ CusumState cur;
-    __shared__ long long rep_s;
-    if (threadIdx.x == 0) { cur.sp = 0.0; cur.sn = 0.0; rep_s = 0; }
-    for (int64_t k0 = 0; k0 < nchunks; k0 += CV_TILE) {
-        __syncthreads();
-        for (int q = threadIdx.x; q < CV_TILE && k0 + q < nchunks; q += 256) { ss[q] = spec_start[k0 + q]; se[q] = spec_end[k0 + q]; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            CusumState s = cur;
-            for (int q = 0; q < CV_TILE && k0 + q < nchunks; q++) {
-                const int64_t k = k0 + q;
-                const int64_t lo = first + 1 + k * CH;
-                if (lo >= n) break;
-                int64_t hi = lo + CH;
-                if (hi > n) hi = n;
-                const CusumState g = ss[q];
-                if (__double_as_longlong(g.sp) == __double_as_longlong(s.sp) &&
-                    __double_as_longlong(g.sn) == __double_as_longlong(s.sn)) {
-                    s = se[q];
-                    continue;
-                }
-                rep_s++;
-                unsigned word = 0;
-                for (int64_t i = lo; i < hi; i++) {
-                    const bool close = cusum_step(s, r[i], lam[i], allowed[i] != 0);
-                    const int64_t rel = i - (first + 1);
-                    if (close) word |= 1u << (rel & 31);
-                    if ((rel & 31) == 31 || i + 1 == hi) { bitmap[rel >> 5] = word; word = 0; }
-                }
-            }
-            cur = s;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) *repairs = rep_s;
+// C3: consistency check of the chunk chain; inconsistent chunks are appended to the work list
+__global__ void k_cusum_check(const CusumState *__restrict__ start, const CusumState *__restrict__ end, int64_t nchunks,
+                              int64_t *__restrict__ work, unsigned long long *count) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (k >= nchunks) return;
+    const CusumState a = start[k], b = end[k - 1];
+    if (__double_as_longlong(a.sp) != __double_as_longlong(b.sp) || __double_as_longlong(a.sn) != __double_as_longlong(b.sn))
+        work[atomicAdd(count, 1ull)] = k;
+}
+__global__ void k_cusum_commit(const int64_t *__restrict__ work, int64_t nwork, const CusumState *__restrict__ end_next,
+                               CusumState *__restrict__ end) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nwork) end[work[t]] = end_next[work[t]];
 }
 
 // C4: bitmap -> ordered index list
@@ -238,29 +221,49 @@ int fmk_cusum_index_impl(fmk_ctx *ctx, const fmk_trades *t, fmk_buf *sigma, doub
     int64_t total = 0;
     int64_t *idx = nullptr;
     if (m_ticks > 0) {
-        int64_t CH = cdiv(m_ticks, 8192);
+        // ~64k chunks keep every SM busy in the speculative pass and make a repair round cheap; chunks are multiples of 32
+        // ticks so that bitmap words are never shared between lanes
+        int64_t CH = cdiv(m_ticks, 65536);
         if (CH < 4096) CH = 4096;
+        if (const char *e = getenv("FMK_CUSUM_CH")) CH = atoll(e) > 0 ? atoll(e) : CH;   // test hook: tiny chunks, many rounds
         CH = cdiv(CH, 32) * 32;
         const int64_t nchunks = cdiv(m_ticks, CH);
         const int64_t nwords = cdiv(m_ticks, 32);
         Scratch<unsigned> bitmap(ctx);
-        Scratch<CusumState> ss(ctx), se(ctx);
-        Scratch<int64_t> rep(ctx), dtotal(ctx);
-        FMK_TRY(bitmap.alloc(nwords)); FMK_TRY(ss.alloc(nchunks)); FMK_TRY(se.alloc(nchunks)); FMK_TRY(rep.alloc(1));
+        Scratch<CusumState> ss(ctx), se(ctx), se_next(ctx);
+        Scratch<int64_t> work(ctx), dtotal(ctx);
+        Scratch<unsigned long long> dcount(ctx);
+        FMK_TRY(bitmap.alloc(nwords)); FMK_TRY(ss.alloc(nchunks)); FMK_TRY(se.alloc(nchunks)); FMK_TRY(se_next.alloc(nchunks));
+        FMK_TRY(work.alloc(nchunks)); FMK_TRY(dcount.alloc(1));
         FMK_TRY(dtotal.alloc(1));
         FMK_LAUNCH(ctx, k_cusum_tasks, (unsigned)cdiv(nchunks, CT_WARPS * 32), CT_WARPS * 32, 0, (const double *)r.p,
-                   (const double *)lam.p, (const uint8_t *)allowed.p, n, first, CH, nchunks, bitmap.p, ss.p, se.p);
-        FMK_LAUNCH(ctx, k_cusum_verify, 1, 256, 0, (const double *)r.p, (const double *)lam.p, (const uint8_t *)allowed.p, n,
-                   first, CH, nchunks, bitmap.p, (const CusumState *)ss.p, (const CusumState *)se.p, rep.p);
+                   (const double *)lam.p, (const uint8_t *)allowed.p, n, first, CH, nchunks, bitmap.p, ss.p, se.p,
+                   (const int64_t *)nullptr, (int64_t)0, (const CusumState *)nullptr);
+        int64_t hrep = 0, rounds = 0;
+        for (;;) {
+            unsigned long long hcount = 0;
+            FMK_CUDA(ctx, cudaMemsetAsync(dcount.p, 0, 8, ctx->stream));
+            if (nchunks > 1)
+                FMK_LAUNCH(ctx, k_cusum_check, (unsigned)cdiv(nchunks - 1, 256), 256, 0, (const CusumState *)ss.p,
+                           (const CusumState *)se.p, nchunks, work.p, dcount.p);
+            FMK_CUDA(ctx, cudaMemcpyAsync(&hcount, dcount.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (hcount == 0) break;
+            const int64_t nw = (int64_t)hcount;
+            FMK_LAUNCH(ctx, k_cusum_tasks, (unsigned)cdiv(nw, CT_WARPS * 32), CT_WARPS * 32, 0, (const double *)r.p,
+                       (const double *)lam.p, (const uint8_t *)allowed.p, n, first, CH, nchunks, bitmap.p, ss.p, se_next.p,
+                       (const int64_t *)work.p, nw, (const CusumState *)se.p);
+            FMK_LAUNCH(ctx, k_cusum_commit, (unsigned)cdiv(nw, 256), 256, 0, (const int64_t *)work.p, nw,
+                       (const CusumState *)se_next.p, se.p);
+            hrep += nw; rounds++;
+        }
         // count, allocate, write
         Scratch<int64_t> wsum(ctx);
         FMK_TRY(wsum.alloc(1));
         FMK_TRY((device_inclusive_scan<int64_t>(ctx, PopIn{bitmap.p}, CountOut{}, nwords, dtotal.p)));
-        int64_t hrep = 0;
-        FMK_CUDA(ctx, cudaMemcpyAsync(&hrep, rep.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
         FMK_CUDA(ctx, cudaMemcpyAsync(&total, dtotal.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
         FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        ctx->stats[0] = nchunks; ctx->stats[1] = hrep; ctx->stats[2] = 1;
+        ctx->stats[0] = nchunks; ctx->stats[1] = hrep; ctx->stats[2] = rounds;
         FMK_TRY(fmk_dalloc(ctx, &idx, total + 1));
         int rc = device_inclusive_scan<int64_t>(ctx, PopIn{bitmap.p}, PopOut{bitmap.p, idx, first + 1}, nwords, (int64_t *)nullptr);
         if (rc) { fmk_dfree(ctx, idx); return rc; }

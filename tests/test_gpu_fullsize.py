@@ -75,3 +75,42 @@ def test_time_and_volume_bars_1e8(ctx):
     assert np.array_equal(vidx, oracle.volume_bar_indexer(qty, 50.0))
     tk = core.tick_bar_index(tr, 1000).download()[1]
     assert np.array_equal(tk, oracle.tick_bar_indexer(ts, 1000))
+
+
+def test_cusum_fixpoint_small_chunks(ctx, monkeypatch):
+    """CUSUM chunk chain with 32/96-tick chunks: hundreds of chunks whose state does not coalesce within one chunk, so the
+    parallel fix-point needs many rounds -- the result must still be the sequential trajectory (golden reference)."""
+    from finmlkit_b200 import core
+    from helpers import STREAM_CASES, load_case
+    for ch in ("32", "96"):
+        monkeypatch.setenv("FMK_CUSUM_CH", ch)
+        for name in STREAM_CASES:
+            g = load_case(name)
+            tr = core.DeviceTrades.upload(g["in_ts"], g["in_px"], g["in_qty"], g["in_side"], ctx=ctx)
+            sig = core.DeviceBuf.upload(ctx, g["in_cusum_sigma"])
+            idx = core.cusum_bar_index(tr, sig, 5e-4, 2.0).download()[1]
+            assert np.array_equal(idx, g["ref_cusum_idx"]), f"{name} CH={ch}"
+            st = ctx.index_stats()
+            assert st["tasks"] > 30
+    monkeypatch.delenv("FMK_CUSUM_CH")
+
+
+def test_cusum_1e7_vs_oracle(ctx):
+    """1-hour sigma pipeline + CUSUM bars on 1e7 ticks (2441 chunks, multi-round repair) against the oracle given the same
+    sigma; a low threshold variant closes bars every few hundred ticks."""
+    import ctypes as C
+    from finmlkit_b200 import core
+    n = 10_000_000
+    tr = core.DeviceTrades.synth(n, seed=44, ctx=ctx)
+    ts, px, qty, side = tr.download()
+    L = ctx._L
+    r, s = C.c_void_p(), C.c_void_p()
+    ctx.check(L.fmk_lagged_returns_dev(ctx.h, tr.h, 3600.0, 1, C.byref(r)))
+    ctx.check(L.fmk_ewmst_dev(ctx.h, tr.h, r, 3600.0, 1e-12, C.byref(s)))
+    L.fmk_buf_free(ctx.h, r)
+    sigma = core.DeviceBuf(ctx, s).download(np.float64, n)
+    for floor, mult in ((5e-4, 2.0), (1e-5, 0.05)):
+        sb = core.DeviceBuf.upload(ctx, sigma)
+        idx = core.cusum_bar_index(tr, sb, floor, mult).download()[1]
+        ref = oracle.cusum_bar_indexer(ts, px, sigma.copy(), floor, mult)
+        assert np.array_equal(idx, ref), (floor, mult, len(idx), len(ref))
