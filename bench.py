@@ -148,6 +148,11 @@ def run_reference(args):
         return
     sample = int(min(args.ticks, args.cpu_sample))
     ts, px, qty, side = synth_trades(sample, seed=42)
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is supposed to use every host core it can
+    try:
+        oracle.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        oracle.set_num_threads(os.cpu_count() or 1)
     cores = oracle.num_threads()
 
     def step():
@@ -357,6 +362,10 @@ def main():
         # ---- CPU baseline beside it (rank 0, N=1 only): oracle port on a bounded sample of the same arrays ----------
         if world == 1 and rank == 0:
             import oracle
+            try:
+                oracle.set_num_threads(len(os.sched_getaffinity(0)))
+            except Exception:
+                pass
             s = int(min(n_e, args.cpu_sample))
             px, qty = np.array(h_px[:s]), np.array(h_qty[:s])
             oracle.comp_bar_ohlcv(px[:1000], qty[:1000], np.array([0, 999], np.int64))
