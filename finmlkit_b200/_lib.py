@@ -72,6 +72,9 @@ SIGNATURES = {
     "fmk_average_uniqueness": (INT, [P, I64, P, P, I64, I64, P, P]),
     "fmk_return_attribution": (INT, [P, P, P, I64, P, P, I64, INT, P]),
     "fmk_sample_weights": (INT, [P, P, P, P, I64, INT, P, P, P]),
+    "fmk_cusum_filter": (INT, [P, P, I64, P, I64, C.POINTER(P), C.POINTER(I64)]),
+    "fmk_trade_side_vector": (INT, [P, P, I64, P]),
+    "fmk_merge_split_trades": (INT, [P, P, P, P, P, I64, P, P, P, P, C.POINTER(I64)]),
     "fmk_triple_barrier": (INT, [P, P, P, P, I64, I64, F64, F64, F64, F64, P, I64, F64, P, P, P, P]),
 }
 

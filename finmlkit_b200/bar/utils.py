@@ -52,3 +52,16 @@ def footprint_to_dataframe(bar_timestamps, price_levels, buy_volumes, sell_volum
     df['price_level'] = df['price_level'] * price_tick
     df = df.sort_values(by=['bar_datetime_idx', 'price_level'], ascending=[True, False])
     return df
+
+
+def comp_trade_side_vector(prices, ctx=None):
+    """bar/utils.py:26-46 of the reference (tick rule) on the GPU: int8 sides, ``sides[0] == 0``."""
+    from .. import core
+    return core.trade_side_vector_dev(prices, ctx=ctx)
+
+
+def merge_split_trades(timestamps, prices, amounts, is_buyer_maker, ctx=None):
+    """bar/utils.py:263-329 of the reference on the GPU.  Inputs must already be ordered by (timestamp, price, side);
+    returns ``(timestamps i64, prices f64, amounts f32, sides i8 or empty)``."""
+    from .. import core
+    return core.merge_split_trades_dev(timestamps, prices, amounts, is_buyer_maker, ctx=ctx)

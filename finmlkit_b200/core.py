@@ -386,3 +386,35 @@ def sample_weights_dev(trades: DeviceTrades, event_idxs, touch_idxs, normalize=F
     ctx = trades.ctx
     ctx.check(ctx._L.fmk_sample_weights(ctx.h, trades.h, _ptr(ev), _ptr(tc), len(ev), int(bool(normalize)), _ptr(u), _ptr(r), _ptr(conc)))
     return (u, r, conc) if want_concurrency else (u, r)
+
+
+# ---- event sampler and ingest scans ------------------------------------------------------------------------------------
+def cusum_filter_dev(raw_time_series, threshold, ctx: Context = None):
+    ctx = ctx or default_context()
+    x, th = _c(raw_time_series, np.float64), _c(threshold, np.float64)
+    h, m = C.c_void_p(), C.c_int64()
+    ctx.check(ctx._L.fmk_cusum_filter(ctx.h, _ptr(x), len(x), _ptr(th), len(th), C.byref(h), C.byref(m)))
+    return DeviceBuf(ctx, h).download(np.int64, int(m.value))
+
+
+def trade_side_vector_dev(prices, ctx: Context = None):
+    ctx = ctx or default_context()
+    p = _c(prices, np.float64)
+    out = np.zeros(len(p), np.int8)
+    ctx.check(ctx._L.fmk_trade_side_vector(ctx.h, _ptr(p), len(p), _ptr(out)))
+    return out
+
+
+def merge_split_trades_dev(timestamps, prices, amounts, is_buyer_maker, ctx: Context = None):
+    ctx = ctx or default_context()
+    ts, p, a = _c(timestamps, np.int64), _c(prices, np.float64), _c(amounts, np.float32)
+    if not (len(ts) == len(p) == len(a)):
+        raise ValueError("timestamps, prices and amounts must have the same length")
+    ibm = _c(is_buyer_maker, np.uint8) if is_buyer_maker is not None else None
+    n = len(ts)
+    ots, op, oa = np.empty(n, np.int64), np.empty(n), np.empty(n, np.float32)
+    osd = np.empty(n, np.int8) if ibm is not None else None
+    m = C.c_int64()
+    ctx.check(ctx._L.fmk_merge_split_trades(ctx.h, _ptr(ts), _ptr(p), _ptr(a), _ptr(ibm), n, _ptr(ots), _ptr(op), _ptr(oa), _ptr(osd), C.byref(m)))
+    m = int(m.value)
+    return ots[:m], op[:m], oa[:m], (osd[:m] if osd is not None else np.empty(0, np.int8))

@@ -70,16 +70,34 @@ __global__ void k_cusum_prep(const int64_t *__restrict__ ts, const double *__res
     allowed[i] = !(i + 1 < n && ts[i] == ts[i + 1]);
 }
 
+// cusum_filter inputs: r_i = log(x_i / x_{i-1}), thr_i (constant or per element); every tick may fire
+__global__ void k_cusum_filter_prep(const double *__restrict__ x, const double *__restrict__ thr, int64_t nthr, int64_t n,
+                                    double *__restrict__ r, double *__restrict__ lam, uint8_t *__restrict__ allowed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    r[i] = i > 0 ? log(__ddiv_rn(x[i], x[i - 1])) : 0.0;
+    lam[i] = nthr == 1 ? thr[0] : thr[i];
+    allowed[i] = 1;
+}
+
 struct CusumState { double sp, sn; };
 
-// one reference step; returns true when the bar closes at this tick
+// one reference step; returns true when the bar closes / the event fires at this tick.
+// MODE 0: _cusum_bar_indexer (bar/logic.py:203-218): s+ >= lam first, then s- <= -lam, only where `allowed`.
+// MODE 1: cusum_filter (sampling/filters.py:54-67): s- < -thr first, then s+ > thr (strict), every tick.
+template <int MODE>
 __device__ __forceinline__ bool cusum_step(CusumState &s, double r, double lam, bool allowed) {
     const double a = __dadd_rn(s.sp, r), b = __dadd_rn(s.sn, r);
     s.sp = (a > 0.0) ? a : 0.0;      // python max(0.0, a): a only if a > 0.0 (NaN -> 0.0)
     s.sn = (b < 0.0) ? b : 0.0;
-    if (!allowed) return false;
-    if (s.sp >= lam) { s.sp = 0.0; return true; }
-    if (s.sn <= -lam) { s.sn = 0.0; return true; }
+    if (MODE == 0) {
+        if (!allowed) return false;
+        if (s.sp >= lam) { s.sp = 0.0; return true; }
+        if (s.sn <= -lam) { s.sn = 0.0; return true; }
+    } else {
+        if (s.sn < -lam) { s.sn = 0.0; return true; }
+        if (s.sp > lam) { s.sp = 0.0; return true; }
+    }
     return false;
 }
 
@@ -88,6 +106,7 @@ constexpr int CT_R = 16;
 
 // lane = chunk.  Replay [warm_start, chunk_start) silently from the zero state, then [chunk_start, chunk_end) with
 // closes recorded in the bitmap (chunk bounds are multiples of 32 ticks, so words are never shared between lanes).
+template <int MODE>
 __global__ void __launch_bounds__(CT_WARPS * 32) k_cusum_tasks(const double *__restrict__ r, const double *__restrict__ lam,
                                                                const uint8_t *__restrict__ allowed, int64_t n,
                                                                int64_t first, int64_t CH, int64_t nchunks,
@@ -134,7 +153,7 @@ __global__ void __launch_bounds__(CT_WARPS * 32) k_cusum_tasks(const double *__r
                 const int64_t i = pos + tt;
                 if (i >= hi) { active = false; break; }
                 if (i == lo) spec_start[k] = s;
-                const bool close = cusum_step(s, sr[w][lane][tt], sl[w][lane][tt], sa[w][lane][tt] != 0);
+                const bool close = cusum_step<MODE>(s, sr[w][lane][tt], sl[w][lane][tt], sa[w][lane][tt] != 0);
                 if (i >= lo) {
                     const int64_t rel = i - (first + 1);
                     if (close) word |= 1u << (rel & 31);
@@ -190,6 +209,74 @@ struct CountOut {
 
 __global__ void k_set_first(int64_t *out, int64_t v) { out[0] = v; }
 
+// Shared driver of the chunk chain: speculative pass, parallel fix-point, bitmap -> ordered index list.
+// idx_out[0] is left for the caller (open marker); idx_out[1..total] are the closing / event ticks.
+#define CUSUM_TASKS(grid, block, smem, ...)                                                      \
+    do {                                                                                         \
+        if (mode == 0) FMK_LAUNCH(ctx, k_cusum_tasks<0>, grid, block, smem, __VA_ARGS__);        \
+        else FMK_LAUNCH(ctx, k_cusum_tasks<1>, grid, block, smem, __VA_ARGS__);                  \
+    } while (0)
+
+static int cusum_chain(fmk_ctx *ctx, const Scratch<double> &r, const Scratch<double> &lam, const Scratch<uint8_t> &allowed,
+                       int64_t n, int64_t first, int mode, int64_t **idx_out, int64_t *total_out) {
+    const int64_t m_ticks = n - (first + 1);   // ticks that can close a bar
+    int64_t total = 0;
+    int64_t *idx = nullptr;
+    if (m_ticks > 0) {
+        // ~64k chunks keep every SM busy in the speculative pass and make a repair round cheap; chunks are multiples of 32
+        // ticks so that bitmap words are never shared between lanes
+        int64_t CH = cdiv(m_ticks, 65536);
+        if (CH < 4096) CH = 4096;
+        if (const char *e = getenv("FMK_CUSUM_CH")) CH = atoll(e) > 0 ? atoll(e) : CH;   // test hook: tiny chunks, many rounds
+        CH = cdiv(CH, 32) * 32;
+        const int64_t nchunks = cdiv(m_ticks, CH);
+        const int64_t nwords = cdiv(m_ticks, 32);
+        Scratch<unsigned> bitmap(ctx);
+        Scratch<CusumState> ss(ctx), se(ctx), se_next(ctx);
+        Scratch<int64_t> work(ctx), dtotal(ctx);
+        Scratch<unsigned long long> dcount(ctx);
+        FMK_TRY(bitmap.alloc(nwords)); FMK_TRY(ss.alloc(nchunks)); FMK_TRY(se.alloc(nchunks)); FMK_TRY(se_next.alloc(nchunks));
+        FMK_TRY(work.alloc(nchunks)); FMK_TRY(dcount.alloc(1));
+        FMK_TRY(dtotal.alloc(1));
+        CUSUM_TASKS( (unsigned)cdiv(nchunks, CT_WARPS * 32), CT_WARPS * 32, 0, (const double *)r.p,
+                   (const double *)lam.p, (const uint8_t *)allowed.p, n, first, CH, nchunks, bitmap.p, ss.p, se.p,
+                   (const int64_t *)nullptr, (int64_t)0, (const CusumState *)nullptr);
+        int64_t hrep = 0, rounds = 0;
+        for (;;) {
+            unsigned long long hcount = 0;
+            FMK_CUDA(ctx, cudaMemsetAsync(dcount.p, 0, 8, ctx->stream));
+            if (nchunks > 1)
+                FMK_LAUNCH(ctx, k_cusum_check, (unsigned)cdiv(nchunks - 1, 256), 256, 0, (const CusumState *)ss.p,
+                           (const CusumState *)se.p, nchunks, work.p, dcount.p);
+            FMK_CUDA(ctx, cudaMemcpyAsync(&hcount, dcount.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (hcount == 0) break;
+            const int64_t nw = (int64_t)hcount;
+            CUSUM_TASKS( (unsigned)cdiv(nw, CT_WARPS * 32), CT_WARPS * 32, 0, (const double *)r.p,
+                       (const double *)lam.p, (const uint8_t *)allowed.p, n, first, CH, nchunks, bitmap.p, ss.p, se_next.p,
+                       (const int64_t *)work.p, nw, (const CusumState *)se.p);
+            FMK_LAUNCH(ctx, k_cusum_commit, (unsigned)cdiv(nw, 256), 256, 0, (const int64_t *)work.p, nw,
+                       (const CusumState *)se_next.p, se.p);
+            hrep += nw; rounds++;
+        }
+        // count, allocate, write
+        Scratch<int64_t> wsum(ctx);
+        FMK_TRY(wsum.alloc(1));
+        FMK_TRY((device_inclusive_scan<int64_t>(ctx, PopIn{bitmap.p}, CountOut{}, nwords, dtotal.p)));
+        FMK_CUDA(ctx, cudaMemcpyAsync(&total, dtotal.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->stats[0] = nchunks; ctx->stats[1] = hrep; ctx->stats[2] = rounds;
+        FMK_TRY(fmk_dalloc(ctx, &idx, total + 1));
+        int rc = device_inclusive_scan<int64_t>(ctx, PopIn{bitmap.p}, PopOut{bitmap.p, idx, first + 1}, nwords, (int64_t *)nullptr);
+        if (rc) { fmk_dfree(ctx, idx); return rc; }
+    } else {
+        FMK_TRY(fmk_dalloc(ctx, &idx, 1));
+    }
+    *idx_out = idx;
+    *total_out = total;
+    return FMK_OK;
+}
+
 int fmk_cusum_index_impl(fmk_ctx *ctx, const fmk_trades *t, fmk_buf *sigma, double sigma_floor, double sigma_mult,
                          fmk_index **out_ix) {
     *out_ix = nullptr;
@@ -217,59 +304,9 @@ int fmk_cusum_index_impl(fmk_ctx *ctx, const fmk_trades *t, fmk_buf *sigma, doub
     FMK_LAUNCH(ctx, k_cusum_prep, (unsigned)cdiv(n, 256), 256, 0, (const int64_t *)t->ts, (const double *)t->price,
                (const double *)sg, n, sigma_floor, sigma_mult, r.p, lam.p, allowed.p);
 
-    const int64_t m_ticks = n - (first + 1);   // ticks that can close a bar
     int64_t total = 0;
     int64_t *idx = nullptr;
-    if (m_ticks > 0) {
-        // ~64k chunks keep every SM busy in the speculative pass and make a repair round cheap; chunks are multiples of 32
-        // ticks so that bitmap words are never shared between lanes
-        int64_t CH = cdiv(m_ticks, 65536);
-        if (CH < 4096) CH = 4096;
-        if (const char *e = getenv("FMK_CUSUM_CH")) CH = atoll(e) > 0 ? atoll(e) : CH;   // test hook: tiny chunks, many rounds
-        CH = cdiv(CH, 32) * 32;
-        const int64_t nchunks = cdiv(m_ticks, CH);
-        const int64_t nwords = cdiv(m_ticks, 32);
-        Scratch<unsigned> bitmap(ctx);
-        Scratch<CusumState> ss(ctx), se(ctx), se_next(ctx);
-        Scratch<int64_t> work(ctx), dtotal(ctx);
-        Scratch<unsigned long long> dcount(ctx);
-        FMK_TRY(bitmap.alloc(nwords)); FMK_TRY(ss.alloc(nchunks)); FMK_TRY(se.alloc(nchunks)); FMK_TRY(se_next.alloc(nchunks));
-        FMK_TRY(work.alloc(nchunks)); FMK_TRY(dcount.alloc(1));
-        FMK_TRY(dtotal.alloc(1));
-        FMK_LAUNCH(ctx, k_cusum_tasks, (unsigned)cdiv(nchunks, CT_WARPS * 32), CT_WARPS * 32, 0, (const double *)r.p,
-                   (const double *)lam.p, (const uint8_t *)allowed.p, n, first, CH, nchunks, bitmap.p, ss.p, se.p,
-                   (const int64_t *)nullptr, (int64_t)0, (const CusumState *)nullptr);
-        int64_t hrep = 0, rounds = 0;
-        for (;;) {
-            unsigned long long hcount = 0;
-            FMK_CUDA(ctx, cudaMemsetAsync(dcount.p, 0, 8, ctx->stream));
-            if (nchunks > 1)
-                FMK_LAUNCH(ctx, k_cusum_check, (unsigned)cdiv(nchunks - 1, 256), 256, 0, (const CusumState *)ss.p,
-                           (const CusumState *)se.p, nchunks, work.p, dcount.p);
-            FMK_CUDA(ctx, cudaMemcpyAsync(&hcount, dcount.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            if (hcount == 0) break;
-            const int64_t nw = (int64_t)hcount;
-            FMK_LAUNCH(ctx, k_cusum_tasks, (unsigned)cdiv(nw, CT_WARPS * 32), CT_WARPS * 32, 0, (const double *)r.p,
-                       (const double *)lam.p, (const uint8_t *)allowed.p, n, first, CH, nchunks, bitmap.p, ss.p, se_next.p,
-                       (const int64_t *)work.p, nw, (const CusumState *)se.p);
-            FMK_LAUNCH(ctx, k_cusum_commit, (unsigned)cdiv(nw, 256), 256, 0, (const int64_t *)work.p, nw,
-                       (const CusumState *)se_next.p, se.p);
-            hrep += nw; rounds++;
-        }
-        // count, allocate, write
-        Scratch<int64_t> wsum(ctx);
-        FMK_TRY(wsum.alloc(1));
-        FMK_TRY((device_inclusive_scan<int64_t>(ctx, PopIn{bitmap.p}, CountOut{}, nwords, dtotal.p)));
-        FMK_CUDA(ctx, cudaMemcpyAsync(&total, dtotal.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        ctx->stats[0] = nchunks; ctx->stats[1] = hrep; ctx->stats[2] = rounds;
-        FMK_TRY(fmk_dalloc(ctx, &idx, total + 1));
-        int rc = device_inclusive_scan<int64_t>(ctx, PopIn{bitmap.p}, PopOut{bitmap.p, idx, first + 1}, nwords, (int64_t *)nullptr);
-        if (rc) { fmk_dfree(ctx, idx); return rc; }
-    } else {
-        FMK_TRY(fmk_dalloc(ctx, &idx, 1));
-    }
+    FMK_TRY(cusum_chain(ctx, r, lam, allowed, n, first, 0, &idx, &total));
     k_set_first<<<1, 1, 0, ctx->stream>>>(idx, first);
     ctx->launches++;
     fmk_index *ix = new (std::nothrow) fmk_index();
@@ -282,5 +319,36 @@ int fmk_cusum_index_impl(fmk_ctx *ctx, const fmk_trades *t, fmk_buf *sigma, doub
     int rc = fmk_gather_close_ts(ctx, t, ix);
     if (rc) { fmk_index_free(ctx, ix); return rc; }
     *out_ix = ix;
+    return FMK_OK;
+}
+
+
+// cusum_filter (sampling/filters.py:6-70): host series / thresholds in, device buffer of int64 event indices out.
+extern "C" int fmk_cusum_filter(fmk_ctx *ctx, const double *series, int64_t n, const double *threshold, int64_t n_thr,
+                                fmk_buf **events_out, int64_t *n_events) {
+    *events_out = nullptr; *n_events = 0;
+    if (n <= 1) return fmk_fail(ctx, FMK_ERR_ARG, "Input time series must have at least 2 elements.");
+    if (n_thr != 1 && n_thr != n)
+        return fmk_fail(ctx, FMK_ERR_ARG, "Threshold array must either contain 1 const. element or len(raw_time_series) elements.");
+    Scratch<double> x(ctx), th(ctx), r(ctx), lam(ctx);
+    Scratch<uint8_t> allowed(ctx);
+    FMK_TRY(x.alloc(n)); FMK_TRY(th.alloc(n_thr)); FMK_TRY(r.alloc(n)); FMK_TRY(lam.alloc(n)); FMK_TRY(allowed.alloc(n));
+    FMK_CUDA(ctx, cudaMemcpyAsync(x.p, series, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FMK_CUDA(ctx, cudaMemcpyAsync(th.p, threshold, (size_t)n_thr * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FMK_LAUNCH(ctx, k_cusum_filter_prep, (unsigned)cdiv(n, 256), 256, 0, (const double *)x.p, (const double *)th.p, n_thr, n,
+               r.p, lam.p, allowed.p);
+    int64_t *idx = nullptr, total = 0;
+    FMK_TRY(cusum_chain(ctx, r, lam, allowed, n, 0, 1, &idx, &total));
+    fmk_buf *b = new (std::nothrow) fmk_buf();
+    if (!b) { fmk_dfree(ctx, idx); return FMK_ERR_ALLOC; }
+    // hand out the events without the leading marker slot: copy down by one element (stream ordered)
+    b->bytes = total * 8;
+    int rc = fmk_dalloc(ctx, (int64_t **)&b->ptr, total);
+    if (rc) { delete b; fmk_dfree(ctx, idx); return rc; }
+    if (total > 0) FMK_CUDA(ctx, cudaMemcpyAsync(b->ptr, idx + 1, (size_t)total * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    fmk_dfree(ctx, idx);
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *events_out = b;
+    *n_events = total;
     return FMK_OK;
 }

@@ -164,6 +164,19 @@ int fmk_sample_weights(fmk_ctx *ctx, const fmk_trades *t, const int64_t *event_i
                        int64_t n_events, int normalize, double *avg_uniqueness, double *return_attribution,
                        int16_t *concurrency);
 
+/* ---- event sampler and ingest scans ------------------------------------------------------------------- */
+/* cusum_filter, sampling/filters.py:6-70: threshold has 1 or n elements; *events_out is a device buffer of n_events int64
+ * indices (fmk_buf_download / fmk_buf_free). */
+int fmk_cusum_filter(fmk_ctx *ctx, const double *series, int64_t n, const double *threshold, int64_t n_thr,
+                     fmk_buf **events_out, int64_t *n_events);
+/* comp_trade_side_vector (tick rule), bar/utils.py:12-46 */
+int fmk_trade_side_vector(fmk_ctx *ctx, const double *prices, int64_t n, int8_t *sides_out);
+/* merge_split_trades, bar/utils.py:263-329: inputs ordered by (timestamp, price, side); outputs are caller-allocated with
+ * n elements (the reference allocates n and trims); is_buyer_maker / sides_out may be NULL. */
+int fmk_merge_split_trades(fmk_ctx *ctx, const int64_t *ts, const double *prices, const float *amounts,
+                           const uint8_t *is_buyer_maker, int64_t n, int64_t *ts_out, double *prices_out,
+                           float *amounts_out, int8_t *sides_out, int64_t *n_out);
+
 #ifdef __cplusplus
 }
 #endif

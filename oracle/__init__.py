@@ -39,6 +39,8 @@ def lib():
         _lib.fmko_dollar_bar_indexer.restype = C.c_int64
         _lib.fmko_cusum_bar_indexer.restype = C.c_int64
         _lib.fmko_bar_footprints.restype = C.c_int64
+        _lib.fmko_cusum_filter.restype = C.c_int64
+        _lib.fmko_merge_split_trades.restype = C.c_int64
     return _lib
 
 
@@ -282,3 +284,37 @@ def return_attribution(event_idxs, touch_idxs, close, concurrency, normalize):
     if rc == 1:
         raise ValueError("Sum of weights is zero or negative, cannot normalize.")
     return w
+
+
+def cusum_filter(raw_time_series, threshold):
+    """sampling/filters.py:6-70 -> event indices int64."""
+    x, t = _f64(raw_time_series), _f64(threshold)
+    args = (_p(x), C.c_int64(len(x)), _p(t), C.c_int64(len(t)))
+    m = lib().fmko_cusum_filter(*args, None, C.c_int64(0))
+    if m == -1:
+        raise ValueError("Input time series must have at least 2 elements.")
+    if m == -2:
+        raise ValueError("Threshold array must either contain 1 const. element or len(raw_time_series) elements.")
+    out = np.empty(m, np.int64)
+    lib().fmko_cusum_filter(*args, _p(out), C.c_int64(m))
+    return out
+
+
+def comp_trade_side_vector(prices):
+    """bar/utils.py:26-46 (tick rule) -> int8 sides."""
+    p = _f64(prices)
+    out = np.zeros(len(p), np.int8)
+    lib().fmko_trade_side_vector(_p(p), C.c_int64(len(p)), _p(out))
+    return out
+
+
+def merge_split_trades(timestamps, prices, amounts, is_buyer_maker):
+    """bar/utils.py:263-329 -> (ts i64, price f64, amount f32, side i8 or empty)."""
+    ts, p = _i64(timestamps), _f64(prices)
+    a = np.ascontiguousarray(amounts, dtype=np.float32)
+    ibm = np.ascontiguousarray(is_buyer_maker, dtype=np.uint8) if is_buyer_maker is not None else None
+    n = len(ts)
+    ots, op, oa = np.empty(n, np.int64), np.empty(n), np.empty(n, np.float32)
+    osd = np.empty(n, np.int8) if ibm is not None else None
+    m = lib().fmko_merge_split_trades(_p(ts), _p(p), _p(a), _p(ibm), C.c_int64(n), _p(ots), _p(op), _p(oa), _p(osd))
+    return ots[:m], op[:m], oa[:m], (osd[:m] if osd is not None else np.empty(0, np.int8))

@@ -716,3 +716,58 @@ int fmko_return_attribution(const int64_t *ev, const int64_t *touch, int64_t ne,
     }
     return FMKO_OK;
 }
+
+/* ---- event sampler and ingest scans ------------------------------------------------------------------- */
+/* sampling/filters.py:6-70 cusum_filter.  thr has 1 or n elements.  Two-phase (out == NULL counts).  Returns -1 / -2 for
+ * the reference's two ValueErrors. */
+int64_t fmko_cusum_filter(const double *x, int64_t n, const double *thr, int64_t nthr, int64_t *out, int64_t cap) {
+    if (n <= 1) return -1;
+    if (nthr != 1 && nthr != n) return -2;
+    double sp = 0.0, sn = 0.0;
+    int64_t m = 0;
+    for (int64_t i = 1; i < n; i++) {
+        double ret = log(x[i] / x[i - 1]);
+        double t = nthr == 1 ? thr[0] : thr[i];
+        double a = sp + ret, b = sn + ret;
+        sp = (a > 0.0) ? a : 0.0;            /* python max(0.0, a) */
+        sn = (b < 0.0) ? b : 0.0;            /* python min(0.0, b) */
+        if (sn < -t) { sn = 0.0; if (out && m < cap) out[m] = i; m++; }
+        else if (sp > t) { sp = 0.0; if (out && m < cap) out[m] = i; m++; }
+    }
+    return m;
+}
+
+/* bar/utils.py:12-46 comp_trade_side / comp_trade_side_vector (tick rule) */
+int fmko_trade_side_vector(const double *p, int64_t n, int8_t *out) {
+    if (n <= 0) return FMKO_OK;
+    out[0] = 0;
+    int prev = 0;
+    double pp = p[0];
+    for (int64_t i = 1; i < n; i++) {
+        double dp = p[i] - pp;
+        if (fabs(dp) > 1e-12) prev = dp > 0 ? 1 : (dp < 0 ? -1 : 0);
+        out[i] = (int8_t)prev;
+        pp = p[i];
+    }
+    return FMKO_OK;
+}
+
+/* bar/utils.py:263-329 merge_split_trades: inputs ordered by (timestamp, price, side); returns the merged count */
+int64_t fmko_merge_split_trades(const int64_t *ts, const double *p, const float *a, const uint8_t *ibm, int64_t n,
+                                int64_t *ots, double *op, float *oa, int8_t *oside) {
+    if (n <= 0) return 0;
+    int64_t m = 0;
+    ots[0] = ts[0]; op[0] = p[0]; oa[0] = a[0];
+    if (ibm) oside[0] = ibm[0] ? -1 : 1;
+    for (int64_t i = 1; i < n; i++) {
+        int same = ts[i] == ots[m] && fabs(p[i] - op[m]) < 1e-8;
+        if (ibm) same = same && ((ibm[i] != 0) == (oside[m] == -1));
+        if (same) oa[m] = oa[m] + a[i];       /* float32 accumulation in arrival order */
+        else {
+            m++;
+            ots[m] = ts[i]; op[m] = p[i]; oa[m] = a[i];
+            if (ibm) oside[m] = ibm[i] ? -1 : 1;
+        }
+    }
+    return m + 1;
+}

@@ -78,3 +78,19 @@ def check_tbm(api):
     for kind, msg in V.TBM_ERRORS:
         with pytest.raises(ValueError, match=msg.replace(".", r"\.")):
             api.triple_barrier(*V.tbm_error_args(kind))
+
+
+def check_weights(api):
+    for c in V.AVG_UNIQUENESS:
+        w, conc = api.average_uniqueness(np.arange(c["n"], dtype=np.int64), np.array(c["ev"], np.int64), np.array(c["touch"], np.int64))
+        np.testing.assert_allclose(w, np.array(c["w"]), rtol=1e-12)
+        np.testing.assert_array_equal(conc, np.array(c["conc"], np.int16))
+        assert conc.dtype == np.int16 and w.dtype == np.float64
+    c = V.RETURN_ATTRIBUTION
+    w = api.return_attribution(np.array(c["ev"], np.int64), np.array(c["touch"], np.int64), np.array(c["close"]), np.array(c["conc"], np.int16), False)
+    np.testing.assert_allclose(w, [abs(np.log(102 / 100) + np.log(104 / 102) + np.log(106 / 104))], rtol=1e-12)
+    c = V.RETURN_ATTRIBUTION_ZERO
+    with pytest.raises(ValueError, match="Sum of weights is zero or negative, cannot normalize"):
+        api.return_attribution(np.array(c["ev"], np.int64), np.array(c["touch"], np.int64), np.array(c["close"]), np.array(c["conc"], np.int16), True)
+    w = api.return_attribution(np.zeros(0, np.int64), np.zeros(0, np.int64), np.array([100., 101., 102.]), np.ones(3, np.int16), False)
+    assert len(w) == 0 and w.dtype == np.float64

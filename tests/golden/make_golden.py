@@ -169,9 +169,51 @@ def weights_cases():
     print("weights: events", len(ev), "max concurrency", int(c.max()), "wrap conc", int(c2[15]), "zero-wrap", int(c3[15]), w3[:1])
 
 
+def ingest_cases():
+    """cusum_filter (constant and per-tick thresholds, NaN threshold stretch), tick rule, split-trade merging."""
+    from finmlkit.sampling.filters import cusum_filter
+    from finmlkit.bar.utils import comp_trade_side_vector, merge_split_trades
+    out = {}
+    ts, px, qty, side = synth_trades(50000, seed=21)
+    out["f_px"] = px
+    out["f_thr_const"] = np.array([2e-4])
+    out["f_ref_const"] = cusum_filter(px, out["f_thr_const"])
+    rng = np.random.default_rng(5)
+    thr = np.abs(rng.normal(3e-4, 1e-4, len(px)))
+    thr[1000:1200] = np.nan
+    out["f_thr_arr"] = thr
+    out["f_ref_arr"] = cusum_filter(px, thr)
+    # tick rule: flat stretches, sub-epsilon moves
+    p2 = px.copy()
+    p2[100:140] = p2[100]
+    p2[200] = p2[199] + 5e-13
+    out["s_px"] = p2
+    out["s_ref"] = comp_trade_side_vector(p2)
+    # merging: duplicate timestamps with split fills; prices within / beyond 1e-8 of the head; both sides
+    n = 20000
+    ts3 = 1_700_000_000_000_000_000 + np.cumsum(rng.integers(0, 3, n) * (rng.random(n) < 0.4)).astype(np.int64) * 1_000_000
+    px3 = np.round(100 + rng.integers(0, 3, n) * 0.5, 1) + rng.choice([0.0, 4e-9, 9e-9, 2e-8], n)
+    ibm = rng.random(n) < 0.5
+    order = np.lexsort((ibm, px3, ts3))
+    ts3, px3, ibm = ts3[order], px3[order], ibm[order]
+    am3 = np.round(rng.lognormal(-3, 1, n), 3).astype(np.float32)
+    out["m_ts"], out["m_px"], out["m_am"], out["m_ibm"] = ts3, px3, am3, ibm
+    r = merge_split_trades(ts3, px3, am3, ibm)
+    for k in range(4):
+        out[f"m_ref_{k}"] = np.asarray(r[k])
+    r = merge_split_trades(ts3, px3, am3, None)
+    for k in range(3):
+        out[f"m_ref_noside_{k}"] = np.asarray(r[k])
+    np.savez_compressed(os.path.join(HERE, "ingest.npz"), **out)
+    print("ingest: events", len(out["f_ref_const"]), len(out["f_ref_arr"]), "merged", len(out["m_ref_0"]), "of", n, "/", len(out["m_ref_noside_0"]))
+
+
 def main():
     if "--only-weights" in sys.argv:
         weights_cases()
+        return
+    if "--only-ingest" in sys.argv:
+        ingest_cases()
         return
     # 1. plain synthetic stream (same generator the bench uses)
     ts, px, qty, side = synth_trades(20000, seed=42)
@@ -210,6 +252,7 @@ def main():
                             ref_time_clock=clock, ref_time_idx=idx)
 
     weights_cases()
+    ingest_cases()
     crosscheck()
 
 

@@ -79,3 +79,16 @@ def tbm_error_args(kind):
     if kind.get("bad_side"):
         side = np.ones(1, np.int8)
     return ts, close, ev, tg, (1.0, 1.0), vert, 0.0, side, min_ret
+
+
+# average_uniqueness -- reference tests/labels/test_average_uniqueness.py:7-62 (hand-computed concurrency / weights)
+AVG_UNIQUENESS = [
+    dict(n=10, ev=[0, 4, 8], touch=[2, 6, 9], w=[1.0, 1.0, 1.0], conc=[1, 1, 1, 0, 1, 1, 1, 0, 1, 1]),
+    dict(n=5, ev=[0, 0, 0], touch=[4, 4, 4], w=[1 / 3, 1 / 3, 1 / 3], conc=[3, 3, 3, 3, 3]),
+    dict(n=8, ev=[0, 2, 4], touch=[3, 5, 7], w=[0.75, 0.5, 0.75], conc=[1, 1, 2, 2, 2, 2, 1, 1]),
+]
+# return_attribution -- reference tests/labels/test_return_attribution.py:26-75
+RETURN_ATTRIBUTION = dict(close=[100., 102., 104., 106.], ev=[0], touch=[3], conc=[1, 1, 1, 1])
+RETURN_ATTRIBUTION_ZERO = dict(close=[100., 100., 100., 100.], ev=[0, 2], touch=[1, 3], conc=[1, 1, 1, 1])
+# time_decay -- reference tests/labels/test_time_decay.py:22-47
+TIME_DECAY = [([0.5, 0.5, 0.5, 0.5], 1.0, [1.0, 1.0, 1.0, 1.0]), ([0.5, 0.5, 0.5, 0.5], 0.4, [0.55, 0.7, 0.85, 1.0])]

@@ -11,10 +11,11 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def api():
     from finmlkit_b200.bar import base, logic
-    from finmlkit_b200.label import tbm
+    from finmlkit_b200.label import tbm, weights
     return types.SimpleNamespace(comp_bar_ohlcv=base.comp_bar_ohlcv, time_bar_indexer=logic._time_bar_indexer,
                                  comp_bar_directional_features=base.comp_bar_directional_features,
-                                 comp_bar_footprints=base.comp_bar_footprints, triple_barrier=tbm.triple_barrier)
+                                 comp_bar_footprints=base.comp_bar_footprints, triple_barrier=tbm.triple_barrier,
+                                 average_uniqueness=weights.average_uniqueness, return_attribution=weights.return_attribution)
 
 
 def test_ohlcv(api):
@@ -35,3 +36,7 @@ def test_footprint(api):
 
 def test_tbm(api):
     chk.check_tbm(api)
+
+
+def test_weights(api):
+    chk.check_weights(api)

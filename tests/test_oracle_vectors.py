@@ -10,7 +10,8 @@ import ref_vectors as V
 
 API = types.SimpleNamespace(comp_bar_ohlcv=oracle.comp_bar_ohlcv, time_bar_indexer=oracle.time_bar_indexer,
                             comp_bar_directional_features=oracle.comp_bar_directional_features,
-                            comp_bar_footprints=oracle.comp_bar_footprints, triple_barrier=oracle.triple_barrier)
+                            comp_bar_footprints=oracle.comp_bar_footprints, triple_barrier=oracle.triple_barrier,
+                            average_uniqueness=oracle.average_uniqueness, return_attribution=oracle.return_attribution)
 
 
 def test_ohlcv():
@@ -43,3 +44,13 @@ def test_tick_size_empty_raises():
     from finmlkit_b200.bar.utils import comp_price_tick_size
     with pytest.raises(ValueError):
         comp_price_tick_size(np.array([]))
+
+
+def test_weights():
+    chk.check_weights(API)
+
+
+@pytest.mark.parametrize("u,last,want", V.TIME_DECAY)
+def test_time_decay_host(u, last, want):
+    from finmlkit_b200.label.weights import time_decay
+    np.testing.assert_allclose(time_decay(np.array(u), last), np.array(want), rtol=1e-12)
