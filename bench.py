@@ -32,7 +32,7 @@ UNIT = "ticks/s"
 # algorithmic HBM bytes per tick of each streaming kernel
 ALGO_BYTES_PER_TICK = {"k_dollar_tasks": 16, "k_dollar_chunk_sums": 16, "k_bar_ohlcv_warp": 16, "k_bar_ohlcv_thread": 16,
                        "k_bar_order_stats": 8, "k_bar_ohlcv_median": 16, "k_bar_ohlcv_conveyor": 16,
-                       "k_bar_ohlcv_median_v1": 16}
+                       "k_bar_ohlcv_median_v1": 16, "k_bar_ohlcv_median<true>": 16, "k_bar_ohlcv_median<false>": 16}
 
 
 def env_int(name, default):

@@ -556,7 +556,9 @@ __device__ bool warp_select_raw(const double *__restrict__ seg, int ncnt, int kk
 
 // Fused comp_bar_ohlcv (the kernel run_ohlcv launches): one warp streams its bar once from HBM (O/H/L/C, sums, OR/AND
 // of the raw size patterns), then selects the median on the sizes it has just pulled through L1/L2.
-__global__ void __launch_bounds__(OS_WARPS * 32) k_bar_ohlcv_median(const double *__restrict__ p,
+// Occupancy: measured on B200 at 1e9 ticks -- 3 / 4-5 / 6 resident blocks per SM give 5.06 / 4.01 / 4.95 ms: fewer warps
+// cannot hide the L2 latency of the select passes, more warps shrink L1 (shared-memory carve-out) and thrash it.
+__global__ void __launch_bounds__(OS_WARPS * 32, 4) k_bar_ohlcv_median(const double *__restrict__ p,
                                                                     const double *__restrict__ v,
                                                                     const int64_t *__restrict__ ci, int64_t nb, int64_t n,
                                                                     OhlcvOut o, double *__restrict__ median_out) {

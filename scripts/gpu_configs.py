@@ -91,4 +91,23 @@ evp = ev[ev < PRE // 2]
 if len(evp):
     lr = oracle.triple_barrier(ts[:PRE], px[:PRE], evp, sigma[evp], (2.0, 2.0), 3600.0, 1.0, None, 0.0)
     assert np.array_equal(lab[0][:len(evp)], lr[0]) and np.array_equal(lab[1][:len(evp)], lr[1]), "tbm prefix parity"
+# ---- widened rows: sample weights on the TBM output, cusum_filter, tick rule ------------------------------------
+def weights_dev():
+    return core.sample_weights_dev(tr, ev, lab[1], want_concurrency=False)
+(wu, wr), ms, pr = timed(weights_dev, reps=2)
+res4["sample_weights"] = {"ms_incl_event_h2d_d2h": ms, "events": int(len(ev)), "kernels_ms": pr}
+evp = ev[ev < PRE // 4]
+if len(evp):
+    tp = np.minimum(lab[1][:len(evp)], PRE - 1)
+    ow, oc = oracle.average_uniqueness(ts[:PRE], evp, tp)
+    gu, gr, gc = core.sample_weights_dev(core.DeviceTrades.upload(None, px[:PRE], qty[:PRE], ctx=ctx), evp, tp, want_concurrency=True)
+    assert np.array_equal(gc, oc), "concurrency prefix parity"
+    assert_f64(gu, ow, "avg_u prefix"); assert_f64(gr, oracle.return_attribution(evp, tp, px[:PRE], oc, False), "ra prefix", atol=1e-11)
+NF = min(N, 200_000_000)
+t0 = time.time(); fe = core.cusum_filter_dev(px[:NF], np.array([5e-3]), ctx=ctx); dt = time.time() - t0
+res4["cusum_filter"] = {"ticks": NF, "wall_ms_incl_h2d": dt * 1e3, "events": int(len(fe)), "stats": ctx.index_stats()}
+assert np.array_equal(fe[fe < PRE], oracle.cusum_filter(px[:PRE], np.array([5e-3]))), "cusum_filter prefix parity"
+t0 = time.time(); sd = core.trade_side_vector_dev(px[:NF], ctx=ctx); dt = time.time() - t0
+res4["tick_rule"] = {"ticks": NF, "wall_ms_incl_h2d_d2h": dt * 1e3}
+assert np.array_equal(sd[:PRE], oracle.comp_trade_side_vector(px[:PRE]))
 print("config4", json.dumps(res4), flush=True)
