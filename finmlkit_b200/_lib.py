@@ -75,6 +75,8 @@ SIGNATURES = {
     "fmk_cusum_filter": (INT, [P, P, I64, P, I64, C.POINTER(P), C.POINTER(I64)]),
     "fmk_trade_side_vector": (INT, [P, P, I64, P]),
     "fmk_merge_split_trades": (INT, [P, P, P, P, P, I64, P, P, P, P, C.POINTER(I64)]),
+    "fmk_volume_profile_rolling": (INT, [P, P, P, P, P, I64, P, P, P, F64, I64, F64, F64, P, P, P, P]),
+    "fmk_volume_profile_rolling_fp": (INT, [P, P, P, P, P, F64, I64, F64, F64, P, P, P, P]),
     "fmk_triple_barrier": (INT, [P, P, P, P, I64, I64, F64, F64, F64, F64, P, I64, F64, P, P, P, P]),
 }
 

@@ -418,3 +418,22 @@ def merge_split_trades_dev(timestamps, prices, amounts, is_buyer_maker, ctx: Con
     ctx.check(ctx._L.fmk_merge_split_trades(ctx.h, _ptr(ts), _ptr(p), _ptr(a), _ptr(ibm), n, _ptr(ots), _ptr(op), _ptr(oa), _ptr(osd), C.byref(m)))
     m = int(m.value)
     return ots[:m], op[:m], oa[:m], (osd[:m] if osd is not None else np.empty(0, np.int8))
+
+
+# ---- rolling volume profile (feature/core/volume.py) --------------------------------------------------------------------
+def volume_profile_rolling_csr(ts, highs, lows, level_offsets, price_levels, buy_volumes, sell_volumes, window_size_sec,
+                               n_bins, price_tick, va_pct=68.34, ctx: Context = None):
+    """(poc i32, hva i32, lva i32, vp_pct_abv_poc f32) from a host CSR footprint."""
+    ctx = ctx or default_context()
+    t, h, l = _c(ts, np.int64), _c(highs, np.float64), _c(lows, np.float64)
+    off, lv = _c(level_offsets, np.int64), _c(price_levels, np.int32)
+    b, s = _c(buy_volumes, np.float32), _c(sell_volumes, np.float32)
+    nb = len(t)
+    if not (len(h) == len(l) == nb == len(off) - 1) or nb == 0:
+        raise AssertionError("Input arrays should have the same length and be non-empty.")
+    poc, hva, lva = (np.zeros(nb, np.int32) for _ in range(3))
+    pct = np.zeros(nb, np.float32)
+    ctx.check(ctx._L.fmk_volume_profile_rolling(ctx.h, _ptr(off), _ptr(lv), _ptr(b), _ptr(s), nb, _ptr(t), _ptr(h), _ptr(l),
+                                                float(window_size_sec), int(n_bins) if n_bins else 0, float(price_tick),
+                                                float(va_pct), _ptr(poc), _ptr(hva), _ptr(lva), _ptr(pct)))
+    return poc, hva, lva, pct

@@ -177,6 +177,19 @@ int fmk_merge_split_trades(fmk_ctx *ctx, const int64_t *ts, const double *prices
                            const uint8_t *is_buyer_maker, int64_t n, int64_t *ts_out, double *prices_out,
                            float *amounts_out, int8_t *sides_out, int64_t *n_out);
 
+/* ---- rolling volume profile (feature/core/volume.py:133-456) --------------------------------------------
+ * n_bins <= 0 means None (no bucketing).  Outputs have n_bars elements (zeros before the first full window, like the
+ * reference): POC / HVA / LVA in integer price-tick units, fraction of the volume above the POC as float32. */
+int fmk_volume_profile_rolling(fmk_ctx *ctx, const int64_t *level_offsets, const int32_t *price_levels,
+                               const float *buy_volumes, const float *sell_volumes, int64_t n_bars, const int64_t *bar_ts,
+                               const double *highs, const double *lows, double window_sec, int64_t n_bins,
+                               double price_tick, double va_pct, int32_t *poc, int32_t *hva, int32_t *lva,
+                               float *pct_above_poc);
+/* same on the device-resident CSR footprint of fmk_bar_footprints */
+int fmk_volume_profile_rolling_fp(fmk_ctx *ctx, const fmk_footprint *fp, const int64_t *bar_ts, const double *highs,
+                                  const double *lows, double window_sec, int64_t n_bins, double price_tick, double va_pct,
+                                  int32_t *poc, int32_t *hva, int32_t *lva, float *pct_above_poc);
+
 #ifdef __cplusplus
 }
 #endif

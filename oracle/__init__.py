@@ -318,3 +318,19 @@ def merge_split_trades(timestamps, prices, amounts, is_buyer_maker):
     osd = np.empty(n, np.int8) if ibm is not None else None
     m = lib().fmko_merge_split_trades(_p(ts), _p(p), _p(a), _p(ibm), C.c_int64(n), _p(ots), _p(op), _p(oa), _p(osd))
     return ots[:m], op[:m], oa[:m], (osd[:m] if osd is not None else np.empty(0, np.int8))
+
+
+def volume_profile_rolling_csr(ts, highs, lows, level_offsets, price_levels, buy_volumes, sell_volumes, window_size_sec,
+                               n_bins, price_tick, va_pct=68.34):
+    """feature/core/volume.py:396-456 on a CSR footprint -> (poc i32, hva i32, lva i32, vp_pct_abv_poc f32)."""
+    t, h, l = _i64(ts), _f64(highs), _f64(lows)
+    off = _i64(level_offsets)
+    lv = np.ascontiguousarray(price_levels, dtype=np.int32)
+    b, s_ = np.ascontiguousarray(buy_volumes, dtype=np.float32), np.ascontiguousarray(sell_volumes, dtype=np.float32)
+    nb = len(t)
+    poc, hva, lva = (np.zeros(nb, np.int32) for _ in range(3))
+    pct = np.zeros(nb, np.float32)
+    lib().fmko_volume_profile_rolling(_p(t), _p(h), _p(l), C.c_int64(nb), _p(off), _p(lv), _p(b), _p(s_), C.c_double(window_size_sec),
+                                      C.c_int64(int(n_bins) if n_bins else 0), C.c_double(price_tick), C.c_double(va_pct),
+                                      _p(poc), _p(hva), _p(lva), _p(pct))
+    return poc, hva, lva, pct

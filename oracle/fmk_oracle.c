@@ -771,3 +771,130 @@ int64_t fmko_merge_split_trades(const int64_t *ts, const double *p, const float 
     }
     return m + 1;
 }
+
+/* ---- rolling volume profile (feature/core/volume.py:133-456) on the CSR footprint ---------------------- */
+static int64_t ss_i64(const int64_t *a, int64_t n, int64_t key, int right) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = lo + ((hi - lo) >> 1);
+        if (right ? (a[mid] <= key) : (a[mid] < key)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+/* comp_poc_hva_lva (volume.py:283-366) + calc_volume_percentage_above_poc (:369-393) on one profile */
+static void poc_hva_lva(const int32_t *lv, const float *vol, int64_t n, double va_pct, int32_t *poc_o, int32_t *hva_o,
+                        int32_t *lva_o, float *pct_o) {
+    float total = 0.0f;                               /* np.sum of a float32 array under Numba: float32 accumulator */
+    for (int64_t i = 0; i < n; i++) total += vol[i];
+    int64_t pi = 0;
+    for (int64_t i = 1; i < n; i++) if (vol[i] > vol[pi]) pi = i;      /* np.argmax: first maximum */
+    int32_t poc = lv[pi], hva = poc, lva = poc;
+    double va_thrs = (double)total * (va_pct / 100.0);
+    double cum = vol[pi];
+    int64_t up = pi + 1, dn = pi - 1;
+    /* Numba types each re-assignment separately (SSA): the two-level sums are float32 + float32 = float32 and only the
+     * merged variable is float64, so the up/down comparison sees float32-rounded sums (measured against the JIT). */
+    double cu = 0.0, cd = 0.0;
+    if (up < n) { cu = vol[up]; if (up + 1 < n) cu = (float)(vol[up] + vol[up + 1]); }
+    if (dn >= 0) { cd = vol[dn]; if (dn - 1 >= 0) cd = (float)(vol[dn] + vol[dn - 1]); }
+    while (cum < va_thrs) {
+        if (cu > cd) {
+            cum += cu; hva = lv[up + 1 < n - 1 ? up + 1 : n - 1]; up += 2;
+            cu = -1.0;
+            if (up < n) { cu = vol[up]; if (up + 1 < n) cu = (float)(vol[up] + vol[up + 1]); }
+        } else if (cu < cd) {
+            cum += cd; lva = lv[dn - 1 > 0 ? dn - 1 : 0]; dn -= 2;
+            cd = -1.0;
+            if (dn >= 0) { cd = vol[dn]; if (dn - 1 >= 0) cd = (float)(vol[dn] + vol[dn - 1]); }
+        } else if (cu == cd && cd != -1.0) {
+            cum += cu + cd;
+            hva = lv[up + 1 < n - 1 ? up + 1 : n - 1]; lva = lv[dn - 1 > 0 ? dn - 1 : 0];
+            up += 2; dn -= 2;
+            cu = -1.0;
+            if (up < n) { cu = vol[up]; if (up + 1 < n) cu = (float)(vol[up] + vol[up + 1]); }
+            cd = -1.0;
+            if (dn >= 0) { cd = vol[dn]; if (dn - 1 >= 0) cd = (float)(vol[dn] + vol[dn - 1]); }
+        } else break;                                   /* "BUG! Stuck in loop" branch of the reference */
+    }
+    *poc_o = poc; *hva_o = hva; *lva_o = lva;
+    double above = 0.0;
+    if (!(total <= 0)) {
+        for (int64_t i = 0; i < n; i++) if (lv[i] > poc) above += vol[i];
+        *pct_o = (above <= 0.0) ? 0.0f : (float)(above / (double)total);
+    } else *pct_o = 0.0f;
+}
+
+/* volume_profile_rolling (volume.py:396-456).  n_bins <= 0 means None (no bucketing). */
+int fmko_volume_profile_rolling(const int64_t *ts, const double *highs, const double *lows, int64_t nb,
+                                const int64_t *off, const int32_t *levels, const float *buy, const float *sell,
+                                double window_sec, int64_t n_bins, double tick, double va_pct,
+                                int32_t *poc, int32_t *hva, int32_t *lva, float *pct) {
+    for (int64_t i = 0; i < nb; i++) { poc[i] = hva[i] = lva[i] = 0; pct[i] = 0.0f; }
+    if (nb <= 0) return FMKO_OK;
+    const int64_t win = (int64_t)(window_sec * 1e9);
+    const int64_t first = ss_i64(ts, nb, ts[0] + win, 0);
+    #pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = first; i < nb; i++) {
+        const int64_t end_ts = ts[i], start_ts = end_ts - win;
+        int64_t s = ss_i64(ts, nb, start_ts, 0), e = ss_i64(ts, nb, end_ts, 1);
+        if (s == e) s = s - 1 > 0 ? s - 1 : 0;
+        double mn = lows[s], mx = highs[s];
+        for (int64_t t = s; t < e; t++) { if (lows[t] < mn) mn = lows[t]; if (highs[t] > mx) mx = highs[t]; }
+        const int64_t lo = (int64_t)rint(mn / tick), hi = (int64_t)rint(mx / tick);
+        const int64_t L = hi - lo + 1;
+        if (L <= 0) continue;
+        float *ab = (float *)calloc((size_t)L, sizeof(float)), *as = (float *)calloc((size_t)L, sizeof(float));
+        int32_t *lv = (int32_t *)malloc(sizeof(int32_t) * (size_t)L);
+        for (int64_t k = 0; k < L; k++) lv[k] = (int32_t)(lo + k);
+        for (int64_t t = s; t < e; t++)
+            for (int64_t k = off[t]; k < off[t + 1]; k++) {
+                const int64_t q = (int64_t)levels[k] - lo;      /* searchsorted on the complete integer grid */
+                if (q < 0 || q >= L) continue;
+                ab[q] = ab[q] + buy[k]; as[q] = as[q] + sell[k];
+            }
+        float *tot = ab;
+        for (int64_t k = 0; k < L; k++) tot[k] = ab[k] + as[k];
+        int64_t n = L;
+        int32_t *plv = lv; float *pv = tot;
+        int32_t *blv = NULL; float *bv = NULL;
+        if (n_bins > 0) {
+            /* bucket_price_levels (volume.py:208-280) */
+            const int64_t range = hi - lo;
+            int64_t bw = range / n_bins; if (bw < 1) bw = 1;
+            if (bw % 2 == 0) bw += 1;
+            int64_t nedges = 0;
+            for (int64_t x = lo; x < hi + bw; x += bw) nedges++;
+            int64_t nbin = nedges - 1;
+            int64_t e0 = lo, e_last = lo + (nedges - 1) * bw;
+            int single = 0;
+            if (nedges < 2) { single = 1; e_last = hi + 1; }   /* edges = [min, max + 1], n_bins stays len - 1 = 0 */
+            /* digitize(max) - 1: leftovers iff the last level falls at/after the last edge */
+            int64_t last_idx;
+            if (single) last_idx = (hi >= e_last) ? 1 : 0;
+            else last_idx = (hi >= e_last) ? nbin : (hi - e0) / bw;
+            const int left = last_idx == nbin;
+            const int64_t nout = nbin + (left ? 1 : 0);
+            blv = (int32_t *)calloc((size_t)(nout > 0 ? nout : 1), sizeof(int32_t));
+            bv = (float *)calloc((size_t)(nout > 0 ? nout : 1), sizeof(float));
+            for (int64_t b = 0; b < nbin; b++) {
+                const int64_t a = e0 + b * bw, c = e0 + (b + 1) * bw;
+                int64_t m2 = a + c - 1;                          /* python floor division by 2 */
+                blv[b] = (int32_t)(m2 >= 0 ? m2 / 2 : -((-m2 + 1) / 2));
+            }
+            if (left) blv[nbin] = (int32_t)hi;
+            for (int64_t k = 0; k < L; k++) {
+                const int64_t x = lo + k;
+                int64_t bi;
+                if (single) bi = (x >= e_last) ? 1 : (x >= e0 ? 0 : -1);
+                else bi = (x >= e_last) ? nbin : (x - e0) / bw;
+                if (bi >= 0 && bi < nbin) bv[bi] = bv[bi] + tot[k];
+                else if (bi == nbin) bv[nbin] = bv[nbin] + tot[k];
+            }
+            n = nout; plv = blv; pv = bv;
+        }
+        if (n > 0) poc_hva_lva(plv, pv, n, va_pct, &poc[i], &hva[i], &lva[i], &pct[i]);
+        free(ab); free(as); free(lv); free(blv); free(bv);
+    }
+    return FMKO_OK;
+}

@@ -208,7 +208,42 @@ def ingest_cases():
     print("ingest: events", len(out["f_ref_const"]), len(out["f_ref_arr"]), "merged", len(out["m_ref_0"]), "of", n, "/", len(out["m_ref_noside_0"]))
 
 
+def volprofile_cases():
+    """volume_profile_rolling of the reference on dollar-bar footprints of a 150k-tick stream (tick 0.1)."""
+    from numba.typed import List as NL
+    from finmlkit.feature.core.volume import volume_profile_rolling
+    ts, px, qty, side = synth_trades(150000, seed=8)
+    idx = np.array(_dollar_bar_indexer(px, qty, 3e4), dtype=np.int64)
+    o = comp_bar_ohlcv(px, qty, idx)
+    f = comp_bar_footprints(px, qty, idx, side, 0.1, o[2], o[1], 3.0)
+    off, lv = csr(list(f[0]), np.int32)
+    _, bv = csr(list(f[1]), np.float32)
+    _, sv = csr(list(f[2]), np.float32)
+    bts = ts[idx[1:]]
+    out = {"ts": bts, "high": o[1], "low": o[2], "off": off, "levels": lv, "buy": bv, "sell": sv}
+    cases = [(60.0, 27), (300.0, 0), (20.0, 5), (600.0, 27), (5.0, 27), (120.0, 3), (60.0, 200)]
+    out["cases"] = np.array(cases)
+    for k, (w, nbins) in enumerate(cases):
+        r = volume_profile_rolling(bts, o[1], o[2], f[0], f[1], f[2], w, int(nbins) if nbins else None, 0.1, 68.34)
+        for q in range(4):
+            out[f"ref_{k}_{q}"] = r[q]
+    # single-level windows (constant price) and a one-bar series
+    n = 64
+    ts2 = np.arange(n, dtype=np.int64) * 1_000_000_000
+    pl, bl, sl = NL(), NL(), NL()
+    for i in range(n):
+        pl.append(np.array([1000], np.int32)); bl.append(np.array([1.0 + i], np.float32)); sl.append(np.array([0.5], np.float32))
+    r = volume_profile_rolling(ts2, np.full(n, 100.0), np.full(n, 100.0), pl, bl, sl, 5.0, 27, 0.1, 68.34)
+    for q in range(4):
+        out[f"flat_ref_{q}"] = r[q]
+    np.savez_compressed(os.path.join(HERE, "volprofile.npz"), **out)
+    print("volprofile: bars", len(bts), "levels", len(lv), "flat poc", r[0][:8])
+
+
 def main():
+    if "--only-volprofile" in sys.argv:
+        volprofile_cases()
+        return
     if "--only-weights" in sys.argv:
         weights_cases()
         return
@@ -253,6 +288,7 @@ def main():
 
     weights_cases()
     ingest_cases()
+    volprofile_cases()
     crosscheck()
 
 
