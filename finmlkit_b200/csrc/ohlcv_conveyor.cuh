@@ -305,6 +305,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_bar_ohlcv_conveyor(const doub
                 for (;;) {
                     const int hb = 31 - __clz(diff_hi);
                     const int shift = hb >= 9 ? hb - 9 : 0;
+                    __syncwarp();
 #pragma unroll
                     for (int q = 0; q < CV_WORDS / 32; q++) W->hist[q * 32 + lane] = 0u;
                     __syncwarp();
@@ -465,6 +466,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_bar_ohlcv_conveyor(const doub
             for (;;) {
                 const int hb = 31 - __clz(diff_hi);
                 const int shift = hb >= 9 ? hb - 9 : 0;
+                __syncwarp();
 #pragma unroll
                 for (int q = 0; q < CV_WORDS / 32; q++) W->hist[q * 32 + lane] = 0u;
                 __syncwarp();

@@ -422,6 +422,7 @@ __device__ bool warp_select_raw(const double *__restrict__ seg, int ncnt, int kk
     for (;;) {
         const int hb = 31 - __clz(diff_hi);
         const int shift = hb >= 9 ? hb - 9 : 0;
+        __syncwarp();                          // earlier readers of the histogram (previous level / previous bar) are done
 #pragma unroll
         for (int q = 0; q < RS_WORDS / 32; q++) hist[q * 32 + lane] = 0u;
         __syncwarp();
