@@ -59,45 +59,155 @@ __device__ int64_t volume_replay(const double *__restrict__ v, int64_t n, int64_
     return n;
 }
 
+// Block-cooperative lower bound: first index in [lo, n) with P[idx] >= key, found with two rounds of 256 probes (a 65536
+// window; bars are far shorter) instead of a 30-step dependent binary search by one thread while 255 threads wait.
+__device__ int64_t block_lower_bound(const double *__restrict__ P, int64_t lo, int64_t n, double key, int64_t *slot) {
+    const int t = threadIdx.x;
+    int64_t hi = lo + (int64_t)VN_THREADS * VN_THREADS;
+    if (hi > n) hi = n;
+    const int64_t p1 = lo + (int64_t)t * VN_THREADS;
+    const int c1 = __syncthreads_count(p1 < hi && __ldg(P + p1) < key);       // probes below the key form a prefix
+    if (c1 == 0) return lo;
+    const int64_t seg = lo + (int64_t)(c1 - 1) * VN_THREADS;                  // P[seg] < key <= P[seg + 256] (or window end)
+    const int64_t p2 = seg + 1 + t;
+    const int c2 = __syncthreads_count(p2 < hi && __ldg(P + p2) < key);
+    int64_t r = seg + 1 + c2;
+    if (r >= hi && hi < n) {                                                   // beyond the window: plain search (rare)
+        if (t == 0) *slot = lower_bound_f64(P, hi, n, key);
+        __syncthreads();
+        r = *slot;
+        __syncthreads();
+    }
+    return r;
+}
+
 // Ambiguous starts (candidate inside the guard band) are not replayed inline -- that would stall the whole warp on one
-// lane's serial sum -- but appended to a work list that k_volume_replay drains with one thread per entry.
+// lane's serial sum -- but marked with -1 for k_volume_replay_seg.
+constexpr int VN_STAGE = 1536;      // prefix values staged in shared memory for the per-tick searches
 __global__ void __launch_bounds__(VN_THREADS) k_volume_next(const double *__restrict__ P, const double *__restrict__ v,
                                                             int64_t n, double T, double guard,
-                                                            int32_t *__restrict__ next, int32_t *__restrict__ work,
-                                                            unsigned long long *nwork, int64_t work_cap) {
-    __shared__ int64_t bracket[2];
+                                                            int32_t *__restrict__ next) {
+    __shared__ int64_t slot;
+    __shared__ double Ps[VN_STAGE];
     const int64_t i0 = (int64_t)blockIdx.x * VN_THREADS;
     const int64_t i = i0 + threadIdx.x;
     int64_t ilast = i0 + VN_THREADS - 1;
     if (ilast > n - 1) ilast = n - 1;
     const double tlo = __dadd_rn(T, -guard), thi = __dadd_rn(T, guard);
-    if (threadIdx.x == 0) bracket[0] = lower_bound_f64(P, i0 + 1, n, __dadd_rn(P[i0], tlo));
-    if (threadIdx.x == 32) bracket[1] = lower_bound_f64(P, ilast + 1, n, __dadd_rn(P[ilast], tlo));
+    // the candidates of the block's ticks are monotone in i: bracket them with the first and the last tick's candidates
+    const int64_t b0 = block_lower_bound(P, i0 + 1, n, __dadd_rn(P[i0], tlo), &slot);
+    const int64_t b1 = block_lower_bound(P, ilast + 1, n, __dadd_rn(P[ilast], tlo), &slot);
+    // stage P[b0 .. b1] (+1 for the certainty test) when it fits: the 256 searches then run on shared memory
+    const int64_t span = b1 - b0 + 2;
+    const bool staged = span <= VN_STAGE;
+    if (staged)
+        for (int64_t q = threadIdx.x; q < span; q += VN_THREADS) Ps[q] = b0 + q < n ? __ldg(P + b0 + q) : INFINITY;
     __syncthreads();
     if (i >= n) return;
     const double base = P[i];
-    int64_t lo = bracket[0], hi = bracket[1];
+    int64_t lo = b0, hi = b1;
     if (lo < i + 1) lo = i + 1;
     if (hi < lo) hi = lo;
-    // candidate: first j > i whose approximate bar volume reaches T - guard (monotone in i, bracketed by the block)
-    int64_t j = lower_bound_f64(P, lo, hi, __dadd_rn(base, tlo));
+    // candidate: first j > i whose approximate bar volume reaches T - guard
+    const double key = __dadd_rn(base, tlo);
+    int64_t j;
+    double pj;
+    if (staged) {
+        int64_t l = lo - b0, h = hi - b0;
+        while (l < h) {
+            const int64_t mid = l + ((h - l) >> 1);
+            if (Ps[mid] < key) l = mid + 1; else h = mid;
+        }
+        j = b0 + l;
+        pj = Ps[l];                 // l <= b1 - b0 + ... < span
+    } else {
+        j = lower_bound_f64(P, lo, hi, key);
+        pj = j < n ? __ldg(P + j) : 0.0;
+    }
     int64_t r;
     if (j >= n) r = n;                                            // even T - guard is never reached: no boundary
-    else if (__ldg(P + j) >= __dadd_rn(base, thi)) r = j;        // clears T + guard: certain
-    else {                                                       // within the guard band: the reference's own sum decides
-        const unsigned long long slot = atomicAdd(nwork, 1ull);
-        if ((int64_t)slot < work_cap) { work[slot] = (int32_t)i; r = -1; }
-        else r = volume_replay(v, n, i, T);                      // list full: replay inline
-    }
+    else if (pj >= __dadd_rn(base, thi)) r = j;                  // clears T + guard: certain
+    else r = -1;                                                 // within the guard band: the reference's own sum decides
     next[i] = (int32_t)r;
 }
 
-__global__ void k_volume_replay(const double *__restrict__ v, int64_t n, double T, const int32_t *__restrict__ work,
-                                const unsigned long long *nwork, int64_t work_cap, int32_t *__restrict__ next) {
-    const int64_t m = (int64_t)(*nwork < (unsigned long long)work_cap ? *nwork : (unsigned long long)work_cap);
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < m; q += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = work[q];
-        next[i] = (int32_t)volume_replay(v, n, i, T);
+// Exact replay of the ambiguous starts (exact ties: 2.6 % of all ticks on exchange-quantised sizes, i.e. ~27 per 1024
+// ticks, each needing the reference's sequential sum over a whole bar).  One thread per entry reading its ~1300 sizes from
+// L2 moved 270 GB at 1e9 ticks (94 ms).  Neighbouring entries sum over almost the same ticks, so a warp now owns a
+// 1024-tick segment of starts: it collects the segment's entries, and for 32 of them at a time streams the union of their
+// ranges through a shared-memory tile (coalesced loads, once) while every lane runs its own sequential sum from the tile.
+constexpr int VR_WARPS = 4;
+constexpr int VR_SEG = 1024;      // starts per warp-segment
+constexpr int VR_TILE = 1024;     // ticks per staged tile
+__global__ void __launch_bounds__(VR_WARPS * 32) k_volume_replay_seg(const double *__restrict__ v, int64_t n, double T,
+                                                                     int32_t *__restrict__ next,
+                                                                     unsigned long long *nreplays) {
+    __shared__ double tile_s[VR_WARPS][VR_TILE];
+    __shared__ int32_t list_s[VR_WARPS][VR_SEG];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double *tile = tile_s[w];
+    int32_t *list = list_s[w];
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nseg = (n + VR_SEG - 1) / VR_SEG;
+    for (int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < nseg; seg += nwarps) {
+        const int64_t base = seg * VR_SEG;
+        int cnt = 0;
+#pragma unroll 4
+        for (int g = 0; g < VR_SEG / 32; g++) {
+            const int64_t i = base + g * 32 + lane;
+            const bool amb = i < n && next[i] == -1;
+            const unsigned m = __ballot_sync(0xffffffffu, amb);
+            if (amb) list[cnt + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+            cnt += __popc(m);
+        }
+        __syncwarp();
+        if (cnt == 0) continue;
+        if (lane == 0) atomicAdd(nreplays, (unsigned long long)cnt);
+        for (int b0 = 0; b0 < cnt; b0 += 32) {
+            const bool have = b0 + lane < cnt;
+            const int64_t i = have ? list[b0 + lane] : n;
+            int64_t pos = i + 1;                    // next tick this lane adds
+            double cum = 0.0;
+            int64_t res = n;
+            bool active = have && pos < n;
+            // entries are ascending in i: lane 0 has the smallest start
+            int64_t a = __shfl_sync(0xffffffffu, pos, 0);
+            while (__any_sync(0xffffffffu, active) && a < n) {
+                __syncwarp();
+#pragma unroll 8
+                for (int q = lane; q < VR_TILE; q += 32) tile[q] = a + q < n ? __ldg(v + a + q) : 0.0;
+                __syncwarp();
+                if (active) {
+                    int64_t end = a + VR_TILE < n ? a + VR_TILE : n;
+                    int64_t t = pos > a ? pos : a;
+                    // sizes are >= 0 on this path (anything else took the serial fallback), so the running sum is
+                    // monotone: add eight ticks with independent loads, test once, and only then locate the crossing
+                    for (; t + 8 <= end; t += 8) {
+                        const double *x = tile + (t - a);
+                        const double x0 = x[0], x1 = x[1], x2 = x[2], x3 = x[3], x4 = x[4], x5 = x[5], x6 = x[6], x7 = x[7];
+                        const double c0 = __dadd_rn(cum, x0), c1 = __dadd_rn(c0, x1), c2 = __dadd_rn(c1, x2), c3 = __dadd_rn(c2, x3),
+                                     c4 = __dadd_rn(c3, x4), c5 = __dadd_rn(c4, x5), c6 = __dadd_rn(c5, x6), c7 = __dadd_rn(c6, x7);
+                        if (c7 >= T) {
+                            const int k = c0 >= T ? 0 : c1 >= T ? 1 : c2 >= T ? 2 : c3 >= T ? 3 : c4 >= T ? 4 : c5 >= T ? 5 : c6 >= T ? 6 : 7;
+                            res = t + k; active = false;
+                            break;
+                        }
+                        cum = c7;
+                    }
+                    if (active)
+                        for (; t < end; t++) {
+                            cum = __dadd_rn(cum, tile[t - a]);
+                            if (cum >= T) { res = t; active = false; break; }
+                        }
+                    pos = end;
+                    if (pos >= n) active = false;
+                }
+                a += VR_TILE;
+            }
+            if (have) next[i] = (int32_t)res;
+            __syncwarp();
+        }
+        __syncwarp();
     }
 }
 
@@ -302,13 +412,15 @@ int fmk_volume_index_impl(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index
     FMK_CUDA(ctx, cudaMemsetAsync(entryS.p, 0xff, (size_t)nS * 8, ctx->stream));
     FMK_CUDA(ctx, cudaMemsetAsync(entryC.p, 0xff, (size_t)nC * 8, ctx->stream));
     FMK_CUDA(ctx, cudaMemsetAsync(off.p, 0, 8, ctx->stream));
-    const int64_t work_cap = n / 4 + 1024;
-    Scratch<int32_t> work(ctx);
-    FMK_TRY(work.alloc(work_cap));
     FMK_LAUNCH(ctx, k_volume_next, (unsigned)cdiv(n, VN_THREADS), VN_THREADS, 0, (const double *)P.p, t->amount, n, T, guard,
-               next.p, work.p, (unsigned long long *)replays.p, work_cap);
-    FMK_LAUNCH(ctx, k_volume_replay, (unsigned)(ctx->sm_count * 16), 128, 0, t->amount, n, T, (const int32_t *)work.p,
-               (const unsigned long long *)replays.p, work_cap, next.p);
+               next.p);
+    {
+        int64_t blocks = cdiv(cdiv(n, VR_SEG), VR_WARPS);
+        const int64_t maxb = (int64_t)ctx->sm_count * 16;
+        if (blocks > maxb) blocks = maxb;
+        FMK_LAUNCH(ctx, k_volume_replay_seg, (unsigned)blocks, VR_WARPS * 32, 0, t->amount, n, T, next.p,
+                   (unsigned long long *)replays.p);
+    }
     FMK_LAUNCH(ctx, k_volume_first, 1, 1, 0, t->amount, n, T, first.p);
     FMK_LAUNCH(ctx, k_volume_exit0, (unsigned)nC, 256, 0, (const int32_t *)next.p, n, exit0.p);
     FMK_LAUNCH(ctx, k_volume_exit1, (unsigned)nS, 256, 0, (const int32_t *)exit0.p, n, exit1.p);
