@@ -1110,15 +1110,16 @@ extern "C" int fmk_bar_footprints(fmk_ctx *ctx, const fmk_trades *t, const fmk_i
     int64_t blocks = cdiv(nb, 8);
     int64_t maxb = (int64_t)ctx->sm_count * 64;
     if (blocks > maxb) blocks = maxb;
-    k_bar_footprint<<<(unsigned)blocks, 256, 0, ctx->stream>>>(t->price, t->amount, t->side, ix->close_idx, nb, lh.p, tick,
-                                                              fp->level_offsets, fp->price_levels, fp->buy_vol,
-                                                              fp->sell_vol, fp->buy_ticks, fp->sell_ticks, err.p);
-    ctx->launches++;
-    k_footprint_features<<<(unsigned)cdiv(nb, 128), 128, 0, ctx->stream>>>(fp->level_offsets, nb, fp->price_levels, fp->buy_vol,
-                                                                          fp->sell_vol, factor, fp->buy_imb, fp->sell_imb,
-                                                                          fp->buy_imb_sum, fp->sell_imb_sum, fp->cot,
-                                                                          fp->run_signed, fp->vp_skew, fp->vp_gini);
-    ctx->launches++;
+    auto launch = [&]() -> int {
+        FMK_LAUNCH(ctx, k_bar_footprint, (unsigned)blocks, 256, 0, t->price, t->amount, t->side, ix->close_idx, nb, lh.p, tick,
+                   fp->level_offsets, fp->price_levels, fp->buy_vol, fp->sell_vol, fp->buy_ticks, fp->sell_ticks, err.p);
+        FMK_LAUNCH(ctx, k_footprint_features, (unsigned)cdiv(nb, 128), 128, 0, fp->level_offsets, nb, fp->price_levels,
+                   fp->buy_vol, fp->sell_vol, factor, fp->buy_imb, fp->sell_imb, fp->buy_imb_sum, fp->sell_imb_sum, fp->cot,
+                   fp->run_signed, fp->vp_skew, fp->vp_gini);
+        return FMK_OK;
+    };
+    rc = launch();
+    if (rc) { fmk_footprint_free(ctx, fp); return rc; }
     int herr = 0;
     cudaError_t e = cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
