@@ -59,26 +59,15 @@ __device__ int64_t volume_replay(const double *__restrict__ v, int64_t n, int64_
     return n;
 }
 
-// Block-cooperative lower bound: first index in [lo, n) with P[idx] >= key, found with two rounds of 256 probes (a 65536
-// window; bars are far shorter) instead of a 30-step dependent binary search by one thread while 255 threads wait.
-__device__ int64_t block_lower_bound(const double *__restrict__ P, int64_t lo, int64_t n, double key, int64_t *slot) {
-    const int t = threadIdx.x;
-    int64_t hi = lo + (int64_t)VN_THREADS * VN_THREADS;
-    if (hi > n) hi = n;
-    const int64_t p1 = lo + (int64_t)t * VN_THREADS;
-    const int c1 = __syncthreads_count(p1 < hi && __ldg(P + p1) < key);       // probes below the key form a prefix
-    if (c1 == 0) return lo;
-    const int64_t seg = lo + (int64_t)(c1 - 1) * VN_THREADS;                  // P[seg] < key <= P[seg + 256] (or window end)
-    const int64_t p2 = seg + 1 + t;
-    const int c2 = __syncthreads_count(p2 < hi && __ldg(P + p2) < key);
-    int64_t r = seg + 1 + c2;
-    if (r >= hi && hi < n) {                                                   // beyond the window: plain search (rare)
-        if (t == 0) *slot = lower_bound_f64(P, hi, n, key);
-        __syncthreads();
-        r = *slot;
-        __syncthreads();
-    }
-    return r;
+// Bracket pre-pass: the candidates of a block's 256 ticks are monotone, so the first and the last tick's candidates
+// bracket all of them.  One THREAD per bracket: a full binary search is ~30 dependent loads, but 2 n / 256 of them run
+// concurrently, so occupancy hides the latency (two threads of every block doing it stalled the whole block for ~15 us).
+__global__ void k_volume_brackets(const double *__restrict__ P, int64_t n, double tlo, int64_t nblk, int64_t *__restrict__ br) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= 2 * nblk) return;
+    int64_t i = (q >> 1) * VN_THREADS + ((q & 1) ? VN_THREADS - 1 : 0);
+    if (i > n - 1) i = n - 1;
+    br[q] = lower_bound_f64(P, i + 1, n, __dadd_rn(P[i], tlo));
 }
 
 // Ambiguous starts (candidate inside the guard band) are not replayed inline -- that would stall the whole warp on one
@@ -86,17 +75,12 @@ __device__ int64_t block_lower_bound(const double *__restrict__ P, int64_t lo, i
 constexpr int VN_STAGE = 1536;      // prefix values staged in shared memory for the per-tick searches
 __global__ void __launch_bounds__(VN_THREADS) k_volume_next(const double *__restrict__ P, const double *__restrict__ v,
                                                             int64_t n, double T, double guard,
-                                                            int32_t *__restrict__ next) {
-    __shared__ int64_t slot;
+                                                            const int64_t *__restrict__ br, int32_t *__restrict__ next) {
     __shared__ double Ps[VN_STAGE];
     const int64_t i0 = (int64_t)blockIdx.x * VN_THREADS;
     const int64_t i = i0 + threadIdx.x;
-    int64_t ilast = i0 + VN_THREADS - 1;
-    if (ilast > n - 1) ilast = n - 1;
     const double tlo = __dadd_rn(T, -guard), thi = __dadd_rn(T, guard);
-    // the candidates of the block's ticks are monotone in i: bracket them with the first and the last tick's candidates
-    const int64_t b0 = block_lower_bound(P, i0 + 1, n, __dadd_rn(P[i0], tlo), &slot);
-    const int64_t b1 = block_lower_bound(P, ilast + 1, n, __dadd_rn(P[ilast], tlo), &slot);
+    const int64_t b0 = br[2 * (int64_t)blockIdx.x], b1 = br[2 * (int64_t)blockIdx.x + 1];
     // stage P[b0 .. b1] (+1 for the certainty test) when it fits: the 256 searches then run on shared memory
     const int64_t span = b1 - b0 + 2;
     const bool staged = span <= VN_STAGE;
@@ -412,8 +396,15 @@ int fmk_volume_index_impl(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index
     FMK_CUDA(ctx, cudaMemsetAsync(entryS.p, 0xff, (size_t)nS * 8, ctx->stream));
     FMK_CUDA(ctx, cudaMemsetAsync(entryC.p, 0xff, (size_t)nC * 8, ctx->stream));
     FMK_CUDA(ctx, cudaMemsetAsync(off.p, 0, 8, ctx->stream));
-    FMK_LAUNCH(ctx, k_volume_next, (unsigned)cdiv(n, VN_THREADS), VN_THREADS, 0, (const double *)P.p, t->amount, n, T, guard,
-               next.p);
+    {
+        const int64_t nblk = cdiv(n, VN_THREADS);
+        Scratch<int64_t> br(ctx);
+        FMK_TRY(br.alloc(2 * nblk));
+        FMK_LAUNCH(ctx, k_volume_brackets, (unsigned)cdiv(2 * nblk, 256), 256, 0, (const double *)P.p, n,
+                   T - guard, nblk, br.p);
+        FMK_LAUNCH(ctx, k_volume_next, (unsigned)nblk, VN_THREADS, 0, (const double *)P.p, t->amount, n, T, guard,
+                   (const int64_t *)br.p, next.p);
+    }
     {
         int64_t blocks = cdiv(cdiv(n, VR_SEG), VR_WARPS);
         const int64_t maxb = (int64_t)ctx->sm_count * 16;

@@ -16,50 +16,89 @@ __device__ __forceinline__ int64_t ss_right_f64(const int64_t *__restrict__ ts, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// a13: lagged returns.  lag(i) is monotone in i, so the first and last thread of a block bracket every other
-// thread's answer: two full binary searches per block, the rest search a window of ~blockDim ticks (L1/L2 hits).
+// a13: lagged returns.  lag(i) is monotone in i, so the first and last tick of a block bracket every other tick's
+// answer.  The brackets come from a pre-pass with one thread per bracket (k_lagged_brackets), and the bracketed slice of
+// timestamps is staged in shared memory (as float64) so the per-tick searches are branch-free and never touch global
+// memory.  (r01: two full binary searches by two threads of every 256-tick block stalled the block for ~15 us -> 44 ms at
+// 1e9 ticks; a block-cooperative 256-way search cut the latency but issued 8x more scattered probes -> 37 ms.)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int LR_THREADS = 256;
+constexpr int LR_ITEMS = 4;                       // ticks per thread
+constexpr int LR_TILE = LR_THREADS * LR_ITEMS;    // ticks per block
+constexpr int LR_STAGE = 4096;
+
+// Bracket pre-pass: one THREAD per block bracket (two per 1024-tick block).  A full binary search is ~30 dependent loads,
+// but 2 n / 1024 of them run concurrently, so the latency is hidden by occupancy instead of stalling a whole block.
+__global__ void k_lagged_brackets(const int64_t *__restrict__ ts, int64_t n, double w, int64_t nblk,
+                                  int64_t *__restrict__ br) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= 2 * nblk) return;
+    const int64_t blk = q >> 1;
+    int64_t i = blk * LR_TILE + ((q & 1) ? LR_TILE - 1 : 0);
+    if (i > n - 1) i = n - 1;
+    br[q] = ss_right_f64(ts, 0, i + 1, __dadd_rn((double)ts[i], -w));
+}
+
 __global__ void __launch_bounds__(LR_THREADS) k_lagged_returns(const int64_t *__restrict__ ts,
                                                                const double *__restrict__ close, int64_t n, double w,
-                                                               int is_log, double *__restrict__ out) {
-    __shared__ int64_t bracket[2];
-    const int64_t i0 = (int64_t)blockIdx.x * LR_THREADS;
-    const int64_t i = i0 + threadIdx.x;
-    int64_t ilast = i0 + LR_THREADS - 1;
-    if (ilast > n - 1) ilast = n - 1;
-    if (threadIdx.x == 0) bracket[0] = ss_right_f64(ts, 0, i0 + 1, __dadd_rn((double)ts[i0], -w));
-    if (threadIdx.x == 32) bracket[1] = ss_right_f64(ts, 0, ilast + 1, __dadd_rn((double)ts[ilast], -w));
+                                                               int is_log, const int64_t *__restrict__ br,
+                                                               double *__restrict__ out) {
+    __shared__ double ts_s[LR_STAGE];          // staged as float64: the comparisons are float64, convert once
+    const int64_t i0 = (int64_t)blockIdx.x * LR_TILE;
+    const int64_t b0 = br[2 * (int64_t)blockIdx.x], b1 = br[2 * (int64_t)blockIdx.x + 1];
+    const int64_t span = b1 - b0;                   // per-tick insertion points lie in [b0, b1]: they read ts[b0 .. b1 - 1]
+    const bool staged = span <= LR_STAGE;
+    if (staged)
+        for (int64_t q = threadIdx.x; q < span; q += LR_THREADS) ts_s[q] = (double)__ldg(ts + b0 + q);
     __syncthreads();
-    if (i >= n) return;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     // start_idx = searchsorted(ts, ts[0] + w, 'left'):  i < start_idx  <=>  (double)ts[i] < (double)ts[0] + w
     const double first_key = __dadd_rn((double)__ldg(ts), w);
-    const int64_t tsi = ts[i];
-    if ((double)tsi < first_key) { out[i] = nan; return; }
-    const double target = __dadd_rn((double)tsi, -w);
-    int64_t hi = bracket[1];
-    if (hi > i + 1) hi = i + 1;
-    int64_t lo = bracket[0];
-    if (lo > hi) lo = hi;
-    // the bracket holds searchsorted results (insertion points); the answer lies in [lo, hi]
-    const int64_t lag = ss_right_f64(ts, lo, hi, target) - 1;
-    double r = nan;
-    if (lag >= 0 && lag < i) {
-        const double cl = close[lag];
-        if (cl != 0.0) {
-            const double q = __ddiv_rn(close[i], cl);
-            r = is_log ? log(q) : __dadd_rn(q, -1.0);
-        } else r = __longlong_as_double(0x7ff0000000000000ll);  // +inf
+#pragma unroll
+    for (int k = 0; k < LR_ITEMS; k++) {
+        const int64_t i = i0 + threadIdx.x + (int64_t)k * LR_THREADS;
+        if (i >= n) break;
+        const int64_t tsi = ts[i];
+        if ((double)tsi < first_key) { out[i] = nan; continue; }
+        const double target = __dadd_rn((double)tsi, -w);
+        int64_t hi = b1;
+        if (hi > i + 1) hi = i + 1;
+        int64_t lo = b0;
+        if (lo > hi) lo = hi;
+        // the bracket holds searchsorted results (insertion points); the answer lies in [lo, hi]
+        int64_t ip;
+        if (staged) {
+            // branch-free: number of staged timestamps in [lo, hi) that are <= target (they form a prefix)
+            int l = (int)(lo - b0);
+            const int h = (int)(hi - b0);
+#pragma unroll
+            for (int step = LR_STAGE / 2; step > 0; step >>= 1)
+                if (l + step <= h && ts_s[l + step - 1] <= target) l += step;
+            ip = b0 + l;
+        } else ip = ss_right_f64(ts, lo, hi, target);
+        const int64_t lag = ip - 1;
+        double r = nan;
+        if (lag >= 0 && lag < i) {
+            const double cl = close[lag];
+            if (cl != 0.0) {
+                const double q = __ddiv_rn(close[i], cl);
+                r = is_log ? log(q) : __dadd_rn(q, -1.0);
+            } else r = __longlong_as_double(0x7ff0000000000000ll);  // +inf
+        }
+        out[i] = r;
     }
-    out[i] = r;
 }
 
 static int run_lagged_returns(fmk_ctx *ctx, const int64_t *ts, const double *close, int64_t n, double window_sec,
                               int is_log, double *out) {
     if (!(window_sec > 0)) return fmk_fail(ctx, FMK_ERR_ARG, "The return window must be greater than zero.");
     if (n <= 0) return FMK_OK;
-    FMK_LAUNCH(ctx, k_lagged_returns, (unsigned)cdiv(n, LR_THREADS), LR_THREADS, 0, ts, close, n, window_sec * 1e9, is_log, out);
+    const int64_t nblk = cdiv(n, LR_TILE);
+    Scratch<int64_t> br(ctx);
+    FMK_TRY(br.alloc(2 * nblk));
+    FMK_LAUNCH(ctx, k_lagged_brackets, (unsigned)cdiv(2 * nblk, 256), 256, 0, ts, n, window_sec * 1e9, nblk, br.p);
+    FMK_LAUNCH(ctx, k_lagged_returns, (unsigned)nblk, LR_THREADS, 0, ts, close, n, window_sec * 1e9, is_log,
+               (const int64_t *)br.p, out);
     return FMK_OK;
 }
 
