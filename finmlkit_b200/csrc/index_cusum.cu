@@ -114,15 +114,17 @@ __global__ void __launch_bounds__(CT_WARPS * 32) k_cusum_tasks(const double *__r
                                                                CusumState *__restrict__ spec_start,
                                                                CusumState *__restrict__ spec_end,
                                                                const int64_t *__restrict__ work, int64_t nwork,
-                                                               const CusumState *__restrict__ prev_end) {
+                                                               const CusumState *__restrict__ prev_end, int tpw) {
+    // tpw = tasks (lanes that replay a chunk) per warp.  A replay is one long dependent chain, so throughput comes from the
+    // number of resident WARPS, not lanes: when there are few tasks (the repair rounds) they are spread one or two per warp.
     __shared__ double sr[CT_WARPS][32][CT_R + 1];
     __shared__ double sl[CT_WARPS][32][CT_R + 1];
     __shared__ uint8_t sa[CT_WARPS][32][CT_R];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t tid = ((int64_t)blockIdx.x * CT_WARPS + w) * 32 + lane;
+    const int64_t tid = ((int64_t)blockIdx.x * CT_WARPS + w) * tpw + lane;
     // work == nullptr: speculative pass over every chunk; otherwise replay of the listed chunks from prev_end[k-1]
-    int64_t k = tid;
-    if (work) k = tid < nwork ? work[tid] : nchunks;
+    int64_t k = lane < tpw ? tid : nchunks;
+    if (work) k = (lane < tpw && tid < nwork) ? work[tid] : nchunks;
     const int64_t lo = first + 1 + k * CH;              // first tick of the chunk (ticks <= first are never tested)
     int64_t hi = lo + CH;
     if (hi > n) hi = n;
@@ -135,16 +137,24 @@ __global__ void __launch_bounds__(CT_WARPS * 32) k_cusum_tasks(const double *__r
     const int half = lane >> 4, col = lane & 15;
     if (active && pos == lo) spec_start[k] = s;        // chunk 0: the true initial state
     while (__any_sync(0xffffffffu, active)) {
-#pragma unroll 4
+        // two phases: all 48 loads of the round are issued before the first shared-memory store waits on one of them
+        // (interleaved load/store batches serialised four HBM round trips per 16 ticks -- 0.29 us per tick in the repair
+        // rounds, where a single warp per SM has nothing else to overlap with)
+        double ga[16], gb[16];
+        uint8_t gc[16];
+#pragma unroll
         for (int q = 0; q < 16; q++) {
             const int row = 2 * q + half;
             const int64_t rp = __shfl_sync(0xffffffffu, pos, row);
             const int ra = __shfl_sync(0xffffffffu, (int)active, row);
             const int64_t idx = rp + col;
-            double a = 0.0, b = 0.0;
-            uint8_t c = 0;
-            if (ra && idx < n) { a = __ldg(r + idx); b = __ldg(lam + idx); c = __ldg(allowed + idx); }
-            sr[w][row][col] = a; sl[w][row][col] = b; sa[w][row][col] = c;
+            ga[q] = 0.0; gb[q] = 0.0; gc[q] = 0;
+            if (2 * q < tpw && ra && idx < n) { ga[q] = __ldg(r + idx); gb[q] = __ldg(lam + idx); gc[q] = __ldg(allowed + idx); }
+        }
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int row = 2 * q + half;
+            if (2 * q < tpw) { sr[w][row][col] = ga[q]; sl[w][row][col] = gb[q]; sa[w][row][col] = gc[q]; }
         }
         __syncwarp();
         if (active) {
@@ -238,9 +248,14 @@ static int cusum_chain(fmk_ctx *ctx, const Scratch<double> &r, const Scratch<dou
         FMK_TRY(bitmap.alloc(nwords)); FMK_TRY(ss.alloc(nchunks)); FMK_TRY(se.alloc(nchunks)); FMK_TRY(se_next.alloc(nchunks));
         FMK_TRY(work.alloc(nchunks)); FMK_TRY(dcount.alloc(1));
         FMK_TRY(dtotal.alloc(1));
-        CUSUM_TASKS( (unsigned)cdiv(nchunks, CT_WARPS * 32), CT_WARPS * 32, 0, (const double *)r.p,
-                   (const double *)lam.p, (const uint8_t *)allowed.p, n, first, CH, nchunks, bitmap.p, ss.p, se.p,
-                   (const int64_t *)nullptr, (int64_t)0, (const CusumState *)nullptr);
+        // tasks per warp: aim at >= 16 resident warps per SM
+        // (measured at 1e9 ticks: spreading the few tasks of a repair round over more warps -- 2 per warp instead of 32 --
+        //  is slower, 242 vs 199 ms for the whole chain: the per-warp staging cost dominates.  Kept at 32.)
+        auto pick_tpw = [&](int64_t) { return 32; };
+        int tpw = pick_tpw(nchunks);
+        CUSUM_TASKS((unsigned)cdiv(cdiv(nchunks, tpw), CT_WARPS), CT_WARPS * 32, 0, (const double *)r.p,
+                    (const double *)lam.p, (const uint8_t *)allowed.p, n, first, CH, nchunks, bitmap.p, ss.p, se.p,
+                    (const int64_t *)nullptr, (int64_t)0, (const CusumState *)nullptr, tpw);
         int64_t hrep = 0, rounds = 0;
         for (;;) {
             unsigned long long hcount = 0;
@@ -252,9 +267,10 @@ static int cusum_chain(fmk_ctx *ctx, const Scratch<double> &r, const Scratch<dou
             FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             if (hcount == 0) break;
             const int64_t nw = (int64_t)hcount;
-            CUSUM_TASKS( (unsigned)cdiv(nw, CT_WARPS * 32), CT_WARPS * 32, 0, (const double *)r.p,
-                       (const double *)lam.p, (const uint8_t *)allowed.p, n, first, CH, nchunks, bitmap.p, ss.p, se_next.p,
-                       (const int64_t *)work.p, nw, (const CusumState *)se.p);
+            tpw = pick_tpw(nw);
+            CUSUM_TASKS((unsigned)cdiv(cdiv(nw, tpw), CT_WARPS), CT_WARPS * 32, 0, (const double *)r.p,
+                        (const double *)lam.p, (const uint8_t *)allowed.p, n, first, CH, nchunks, bitmap.p, ss.p, se_next.p,
+                        (const int64_t *)work.p, nw, (const CusumState *)se.p, tpw);
             FMK_LAUNCH(ctx, k_cusum_commit, (unsigned)cdiv(nw, 256), 256, 0, (const int64_t *)work.p, nw,
                        (const CusumState *)se_next.p, se.p);
             hrep += nw; rounds++;
