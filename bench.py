@@ -354,7 +354,19 @@ def main():
             t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        # one extra, untimed step with a sync after every phase: where the end-to-end time goes (PCIe vs kernels vs host)
+        def phase_ms():
+            ctx.sync(); t0 = time.perf_counter()
+            tr_e.refill(None, h_px, h_qty, None); ctx.sync(); t1 = time.perf_counter()
+            ix = core.dollar_bar_index(tr_e, THRESHOLD); ctx.sync(); t2 = time.perf_counter()
+            ix.download(host_ts=h_ts); t3 = time.perf_counter()
+            core.bar_ohlcv(tr_e, ix); t4 = time.perf_counter()
+            return {"h2d_price_amount": (t1 - t0) * 1e3, "dollar_index_kernels": (t2 - t1) * 1e3,
+                    "index_d2h_and_host_ts_gather": (t3 - t2) * 1e3, "ohlcv_kernel_and_d2h": (t4 - t3) * 1e3,
+                    "h2d_GBps": 16 * n_e / (t1 - t0) / 1e9}
+        breakdown = phase_ms()
         e2e = {"value": world * n_e / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * n_e, "d2h_bytes_per_step": int(d2h[0]),
+               "phase_ms_untimed_extra_step": breakdown,
                "ticks_per_step_per_gpu": n_e, "ms_per_step": dt * 1e3,
                "api": "fmk_trades_refill(price, amount) + fmk_dollar_bar_index + fmk_index_download + host ts[idx] + fmk_bar_ohlcv "
                       "(host buffers; timestamps stay on the host, as in DollarBarKit.build_ohlcv)"}
