@@ -939,22 +939,33 @@ struct OffOut {
 // One warp per bar.  Level volumes are float32 accumulated in tick order (base.py:694-717): inside a 32-tick step,
 // lanes that hit the same (level, side) bin are serialised in lane (= tick) order by the lowest lane of the group,
 // so every bin sees exactly the reference's sequence of `float32(float64(bin) + amount)` updates.
+// Bars whose price range spans <= FP_CAP levels (practically all of them) accumulate in per-warp SHARED memory and are
+// flushed once: the float32 sums are order-dependent, so every 32-tick step is a read-modify-write of the (level, side)
+// cells it touches, and doing that through global memory cost two L2 round trips per step (17.8 ms at 1e9 ticks,
+// latency-bound at 32 % issue activity).  Wider bars keep the global-memory path.
+constexpr int FP_CAP = 192;
 __global__ void __launch_bounds__(256) k_bar_footprint(const double *__restrict__ p, const double *__restrict__ a,
                                                        const int8_t *__restrict__ side,
                                                        const int64_t *__restrict__ ci, int64_t nb,
                                                        const double *__restrict__ lows, double tick,
                                                        const int64_t *__restrict__ off, int32_t *levels, float *bvol,
                                                        float *svol, int32_t *bt, int32_t *st, int *err) {
-    const int lane = threadIdx.x & 31;
+    __shared__ float vol_s[8][2 * FP_CAP];        // [warp][2 * level + side]
+    __shared__ int32_t cnt_s[8][2 * FP_CAP];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nb; i += nwarps) {
         const int64_t start = ci[i] + 1, e = ci[i + 1];
         const int64_t o = off[i], L = off[i + 1] - o;
         const long long low = __double2ll_rn(__ddiv_rn(lows[i], tick));
-        for (int64_t k = lane; k < L; k += 32) {
-            levels[o + k] = (int32_t)(low + k);
-            bvol[o + k] = 0.0f; svol[o + k] = 0.0f; bt[o + k] = 0; st[o + k] = 0;
+        const bool in_smem = L <= FP_CAP;
+        __syncwarp();
+        if (in_smem) {
+            for (int k = lane; k < 2 * (int)L; k += 32) { vol_s[w][k] = 0.0f; cnt_s[w][k] = 0; }
+        } else {
+            for (int64_t k = lane; k < L; k += 32) { bvol[o + k] = 0.0f; svol[o + k] = 0.0f; bt[o + k] = 0; st[o + k] = 0; }
         }
+        for (int64_t k = lane; k < L; k += 32) levels[o + k] = (int32_t)(low + k);
         __syncwarp();
         for (int64_t base = start; base <= e; base += 32) {
             const int64_t j = base + lane;
@@ -976,9 +987,12 @@ __global__ void __launch_bounds__(256) k_bar_footprint(const double *__restrict_
             float *vp = nullptr;
             int32_t *tp = nullptr;
             if (lead) {
-                const int64_t lv = o + (bin >> 1);
-                vp = (bin & 1) ? svol + lv : bvol + lv;
-                tp = (bin & 1) ? st + lv : bt + lv;
+                if (in_smem) { vp = &vol_s[w][bin]; tp = &cnt_s[w][bin]; }
+                else {
+                    const int64_t lv = o + (bin >> 1);
+                    vp = (bin & 1) ? svol + lv : bvol + lv;
+                    tp = (bin & 1) ? st + lv : bt + lv;
+                }
                 acc = *vp;
             }
             // every lane walks the largest group size; shuffles are warp-wide
@@ -997,56 +1011,120 @@ __global__ void __launch_bounds__(256) k_bar_footprint(const double *__restrict_
             }
             __syncwarp();
         }
+        if (in_smem) {
+            for (int k = lane; k < (int)L; k += 32) {
+                bvol[o + k] = vol_s[w][2 * k]; svol[o + k] = vol_s[w][2 * k + 1];
+                bt[o + k] = cnt_s[w][2 * k]; st[o + k] = cnt_s[w][2 * k + 1];
+            }
+        }
     }
 }
 
 // one thread per bar: comp_footprint_features (base.py:755-850) with Numba's float32 typing of every intermediate
-__global__ void k_footprint_features(const int64_t *__restrict__ off, int64_t nb, const int32_t *__restrict__ levels,
-                                     const float *__restrict__ bvol, const float *__restrict__ svol, double factor,
-                                     uint8_t *bimb, uint8_t *simb, uint16_t *bsum, uint16_t *ssum, int32_t *cot,
-                                     int16_t *run_signed, double *vp_skew, double *vp_gini) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nb) return;
-    const int64_t o = off[i], L = off[i + 1] - o;
-    const int32_t *lv = levels + o;
-    const float *b = bvol + o, *s = svol + o;
+// comp_footprint_features (base.py:755-850).  The float32 sums (np.sum / np.dot of float32 arrays) are sequential per bar,
+// so a THREAD owns a bar -- but a bar has hundreds of levels, and 32 threads walking 32 different CSR segments touch 32
+// sectors per load.  The warp therefore stages 32 levels of each of its 32 bars at a time through shared memory with
+// coalesced row loads (row r = bar of lane r), and every lane consumes its own row.  Two staged passes: (1) imbalance flags,
+// longest signed run, total volume, argmax, sum(level * volume); (2) the vwap-centred dot product and the Gini sum.
+constexpr int FF_WARPS = 4;
+__global__ void __launch_bounds__(FF_WARPS * 32) k_footprint_features(const int64_t *__restrict__ off, int64_t nb,
+                                                                      const int32_t *__restrict__ levels,
+                                                                      const float *__restrict__ bvol,
+                                                                      const float *__restrict__ svol, double factor,
+                                                                      uint8_t *bimb, uint8_t *simb, uint16_t *bsum,
+                                                                      uint16_t *ssum, int32_t *cot, int16_t *run_signed,
+                                                                      double *vp_skew, double *vp_gini) {
+    __shared__ float sb[FF_WARPS][32][35];      // 34 used: one level of look-behind and one of look-ahead for the flags
+    __shared__ float ss_[FF_WARPS][32][35];
+    __shared__ uint8_t sfl[FF_WARPS][32][36];   // flags staged for coalesced stores: bit 0 buy, bit 1 sell
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t i = ((int64_t)blockIdx.x * FF_WARPS + w) * 32 + lane;
+    const bool have = i < nb;
+    const int64_t o = have ? off[i] : 0;
+    const int64_t L = have ? off[i + 1] - o : 0;
+    int64_t Lmax = L;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { const int64_t y = __shfl_xor_sync(FULL, Lmax, d); Lmax = y > Lmax ? y : Lmax; }
+    const int32_t lv0 = (have && L > 0) ? levels[o] : 0;     // levels are lv0 + k (k_bar_footprint writes an arange)
     long long max_run = 0, max_sign = 0, run = 0, run_sign = 0;
-    unsigned bs = 0, ss = 0;
-    float sumtot = 0.0f, best = 0.0f;
+    unsigned bs = 0, ssn = 0;
+    float sumtot = 0.0f, best = 0.0f, num = 0.0f;
     int64_t arg = 0;
-    for (int64_t k = 0; k < L; k++) {
-        const bool si = (L > 1 && k + 1 < L) ? ((double)s[k] > __dmul_rn((double)b[k + 1], factor)) : false;
-        const bool bi = (L > 1 && k >= 1) ? ((double)b[k] > __dmul_rn((double)s[k - 1], factor)) : false;
-        bimb[o + k] = bi; simb[o + k] = si;
-        bs += bi; ss += si;
-        const int sign = bi ? 1 : (si ? -1 : 0);
-        if (sign != 0 && sign == run_sign) run += 1;
-        else if (sign != 0) { run = 1; run_sign = sign; }
-        else { run = 0; run_sign = 0; }
-        if (run > max_run) { max_run = run; max_sign = run_sign; }
-        const float t = __fadd_rn(b[k], s[k]);
-        sumtot = __fadd_rn(sumtot, t);
-        if (k == 0 || t > best) { best = t; arg = k; }
-    }
-    bsum[i] = (uint16_t)bs; ssum[i] = (uint16_t)ss;
-    run_signed[i] = (int16_t)(max_run * max_sign);
-    cot[i] = L > 0 ? lv[arg] : 0;
-    double skew = 0.0, gini = 0.0;
-    if (sumtot > 0 && L > 0) {
-        float num = 0.0f;
-        for (int64_t k = 0; k < L; k++) num = __fadd_rn(num, __fmul_rn((float)lv[k], __fadd_rn(b[k], s[k])));
-        const float vw = __fdiv_rn(num, sumtot);
-        float dot = 0.0f, g = 0.0f;
-        for (int64_t k = 0; k < L; k++) {
-            const float t = __fadd_rn(b[k], s[k]);
-            dot = __fadd_rn(dot, __fmul_rn(__fsub_rn((float)lv[k], vw), t));
-            const float r = __fdiv_rn(t, sumtot);
-            g = __fadd_rn(g, __fmul_rn(r, r));
+    // ---- pass 1 ----
+    for (int64_t k0 = 0; k0 < Lmax; k0 += 32) {
+        __syncwarp();
+        for (int r = 0; r < 32; r++) {          // row r: levels k0-1 .. k0+32 of lane r's bar -> columns 0 .. 33
+            const int64_t orr = __shfl_sync(FULL, o, r), Lr = __shfl_sync(FULL, L, r);
+            for (int c = lane; c < 34; c += 32) {
+                const int64_t k = k0 - 1 + c;
+                const bool ok = k >= 0 && k < Lr;
+                sb[w][r][c] = ok ? __ldg(bvol + orr + k) : 0.0f;
+                ss_[w][r][c] = ok ? __ldg(svol + orr + k) : 0.0f;
+            }
         }
-        skew = (double)__fdiv_rn(dot, sumtot);
-        gini = 1.0 - (double)g;
+        __syncwarp();
+        for (int c = 0; c < 32; c++) {
+            const int64_t k = k0 + c;
+            unsigned char fl = 0;
+            if (k < L) {
+                const float bk = sb[w][lane][c + 1], sk = ss_[w][lane][c + 1];
+                const bool si = (L > 1 && k + 1 < L) ? ((double)sk > __dmul_rn((double)sb[w][lane][c + 2], factor)) : false;
+                const bool bi = (L > 1 && k >= 1) ? ((double)bk > __dmul_rn((double)ss_[w][lane][c], factor)) : false;
+                fl = (unsigned char)((bi ? 1 : 0) | (si ? 2 : 0));
+                bs += bi; ssn += si;
+                const int sign = bi ? 1 : (si ? -1 : 0);
+                if (sign != 0 && sign == run_sign) run += 1;
+                else if (sign != 0) { run = 1; run_sign = sign; }
+                else { run = 0; run_sign = 0; }
+                if (run > max_run) { max_run = run; max_sign = run_sign; }
+                const float t = __fadd_rn(bk, sk);
+                sumtot = __fadd_rn(sumtot, t);
+                if (k == 0 || t > best) { best = t; arg = k; }
+                num = __fadd_rn(num, __fmul_rn((float)(lv0 + (int32_t)k), t));
+            }
+            sfl[w][lane][c] = fl;
+        }
+        __syncwarp();
+        for (int r = 0; r < 32; r++) {          // coalesced flag stores, row by row
+            const int64_t orr = __shfl_sync(FULL, o, r), Lr = __shfl_sync(FULL, L, r);
+            const int64_t k = k0 + lane;
+            if (k < Lr) { const unsigned char fl = sfl[w][r][lane]; bimb[orr + k] = fl & 1; simb[orr + k] = (fl >> 1) & 1; }
+        }
     }
-    vp_skew[i] = skew; vp_gini[i] = gini;
+    if (have) {
+        bsum[i] = (uint16_t)bs; ssum[i] = (uint16_t)ssn;
+        run_signed[i] = (int16_t)(max_run * max_sign);
+        cot[i] = L > 0 ? lv0 + (int32_t)arg : 0;
+    }
+    // ---- pass 2 ----
+    const bool stats = have && sumtot > 0 && L > 0;
+    const float vw = stats ? __fdiv_rn(num, sumtot) : 0.0f;
+    float dot = 0.0f, g = 0.0f;
+    for (int64_t k0 = 0; k0 < Lmax; k0 += 32) {
+        __syncwarp();
+        for (int r = 0; r < 32; r++) {
+            const int64_t orr = __shfl_sync(FULL, o, r), Lr = __shfl_sync(FULL, L, r);
+            const int64_t k = k0 + lane;
+            const bool ok = k < Lr;
+            sb[w][r][lane] = ok ? __ldg(bvol + orr + k) : 0.0f;
+            ss_[w][r][lane] = ok ? __ldg(svol + orr + k) : 0.0f;
+        }
+        __syncwarp();
+        if (stats)
+            for (int c = 0; c < 32; c++) {
+                const int64_t k = k0 + c;
+                if (k < L) {
+                    const float t = __fadd_rn(sb[w][lane][c], ss_[w][lane][c]);
+                    dot = __fadd_rn(dot, __fmul_rn(__fsub_rn((float)(lv0 + (int32_t)k), vw), t));
+                    const float rr = __fdiv_rn(t, sumtot);
+                    g = __fadd_rn(g, __fmul_rn(rr, rr));
+                }
+            }
+    }
+    if (have) {
+        vp_skew[i] = stats ? (double)__fdiv_rn(dot, sumtot) : 0.0;
+        vp_gini[i] = stats ? 1.0 - (double)g : 0.0;
+    }
 }
 
 extern "C" void fmk_footprint_free(fmk_ctx *ctx, fmk_footprint *fp) {
@@ -1113,7 +1191,7 @@ extern "C" int fmk_bar_footprints(fmk_ctx *ctx, const fmk_trades *t, const fmk_i
     auto launch = [&]() -> int {
         FMK_LAUNCH(ctx, k_bar_footprint, (unsigned)blocks, 256, 0, t->price, t->amount, t->side, ix->close_idx, nb, lh.p, tick,
                    fp->level_offsets, fp->price_levels, fp->buy_vol, fp->sell_vol, fp->buy_ticks, fp->sell_ticks, err.p);
-        FMK_LAUNCH(ctx, k_footprint_features, (unsigned)cdiv(nb, 128), 128, 0, fp->level_offsets, nb, fp->price_levels,
+        FMK_LAUNCH(ctx, k_footprint_features, (unsigned)cdiv(nb, FF_WARPS * 32), FF_WARPS * 32, 0, fp->level_offsets, nb, fp->price_levels,
                    fp->buy_vol, fp->sell_vol, factor, fp->buy_imb, fp->sell_imb, fp->buy_imb_sum, fp->sell_imb_sum, fp->cot,
                    fp->run_signed, fp->vp_skew, fp->vp_gini);
         return FMK_OK;
