@@ -318,12 +318,32 @@ def main():
                 n_e //= 2
         except Exception:
             pass
+        def agree_min(x):
+            """Same value on every rank (min), so that the ranks size / skip the end-to-end leg together."""
+            if dist is None:
+                return int(x)
+            t = torch.tensor([int(x)], dtype=torch.int64, device=f"cuda:{local}")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return int(t.item())
+
+        n_e = agree_min(n_e)
         hp = []
-        for _ in range(3):
-            p = C.c_void_p()
-            if L.fmk_host_alloc(C.byref(p), 8 * n_e) != 0:
-                raise RuntimeError("pinned allocation failed")
-            hp.append(p)
+        for _attempt in range(5):          # pinned host memory is per-node: halve the sample until every rank gets its buffers
+            ok = 1
+            for _ in range(3):
+                p = C.c_void_p()
+                if L.fmk_host_alloc(C.byref(p), 8 * n_e) != 0:
+                    ok = 0
+                    break
+                hp.append(p)
+            if agree_min(ok):
+                break
+            for p in hp:
+                L.fmk_host_free(p)
+            hp = []
+            n_e //= 2
+        if not hp:
+            raise RuntimeError("pinned allocation failed on every attempt")
         h_ts = np.ctypeslib.as_array(C.cast(hp[0], C.POINTER(C.c_int64)), shape=(n_e,))
         h_px = np.ctypeslib.as_array(C.cast(hp[1], C.POINTER(C.c_double)), shape=(n_e,))
         h_qty = np.ctypeslib.as_array(C.cast(hp[2], C.POINTER(C.c_double)), shape=(n_e,))
