@@ -175,10 +175,31 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"first {sample} ticks; _dollar_bar_indexer serial + comp_bar_ohlcv on {cores} OpenMP threads"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries that chat on fd 1 (NCCL prints its version banner there) are sent to
+    stderr; the line itself is written to a private duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _JSON_OUT
+
+
+def emit(line):
+    out = _claim_stdout()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -425,7 +446,7 @@ def main():
                            "parallelism": f"symbols x{world}", "index_stats": stats,
                            "gather_bytes_per_step": gather_bytes[0]},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline, "time_bars_1min": time_bars}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
