@@ -429,6 +429,16 @@ __device__ bool warp_select_raw(const double *__restrict__ seg, int ncnt, int kk
         {
             int q = lane;
             if (mask == 0u) {                  // first level: every element is in play
+                for (; q + 224 < ncnt; q += 256) {      // eight loads in flight per lane: half as many L2 round trips
+                    unsigned h[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) h[u] = __ldg(segw + 2 * (q + 32 * u) + 1);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const unsigned d = (h[u] >> shift) & 1023u;
+                        atomicAdd(&hist[rs_word(d)], (d & 1u) ? 65536u : 1u);
+                    }
+                }
                 for (; q + 96 < ncnt; q += 128) {
                     const unsigned h0 = __ldg(segw + 2 * q + 1), h1 = __ldg(segw + 2 * q + 65),
                                    h2 = __ldg(segw + 2 * q + 129), h3 = __ldg(segw + 2 * q + 193);
@@ -494,6 +504,14 @@ __device__ bool warp_select_raw(const double *__restrict__ seg, int ncnt, int kk
             __syncwarp();
             {
                 int q = lane;
+                for (; q + 224 < ncnt; q += 256) {
+                    unsigned h[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) h[u] = __ldg(segw + 2 * (q + 32 * u) + 1);
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if ((h[u] & mask) == prefix) cidx[atomicAdd(ccnt, 1u) & 31u] = (unsigned)(q + 32 * u);
+                }
                 for (; q + 96 < ncnt; q += 128) {
                     const unsigned h0 = __ldg(segw + 2 * q + 1), h1 = __ldg(segw + 2 * q + 65),
                                    h2 = __ldg(segw + 2 * q + 129), h3 = __ldg(segw + 2 * q + 193);
@@ -559,7 +577,7 @@ __device__ bool warp_select_raw(const double *__restrict__ seg, int ncnt, int kk
 // of the raw size patterns), then selects the median on the sizes it has just pulled through L1/L2.
 // Occupancy: measured on B200 at 1e9 ticks -- 3 / 4-5 / 6 resident blocks per SM give 5.06 / 4.01 / 4.95 ms: fewer warps
 // cannot hide the L2 latency of the select passes, more warps shrink L1 (shared-memory carve-out) and thrash it.
-__global__ void __launch_bounds__(OS_WARPS * 32, 4) k_bar_ohlcv_median(const double *__restrict__ p,
+__global__ void __launch_bounds__(OS_WARPS * 32, 5) k_bar_ohlcv_median(const double *__restrict__ p,
                                                                     const double *__restrict__ v,
                                                                     const int64_t *__restrict__ ci, int64_t nb, int64_t n,
                                                                     OhlcvOut o, double *__restrict__ median_out) {
