@@ -182,12 +182,15 @@ class DeviceIndex:
         self.m = int(ctx._L.fmk_index_size(h))
         self._fin = weakref.finalize(self, ctx._L.fmk_index_free, ctx.h, h)
 
-    def download(self, host_ts=None):
+    def download(self, host_ts=None, out_idx=None, gather=True):
         """(close_ts, close_idx).  When the trades were uploaded without timestamps pass the host array: close_ts is
-        then ts[close_idx] gathered on the host (bar/kit.py:67 `close_ts = timestamps[close_indices]`)."""
-        ts, idx = np.empty(self.m, np.int64), np.empty(self.m, np.int64)
-        self.ctx.check(self.ctx._L.fmk_index_download(self.ctx.h, self.h, _ptr(ts) if host_ts is None else None, _ptr(idx)))
-        if host_ts is not None:
+        then ts[close_idx] gathered on the host (bar/kit.py:67 `close_ts = timestamps[close_indices]`).
+        ``out_idx``: optional preallocated int64 buffer of >= m elements (e.g. pinned memory, for repeated calls);
+        ``gather=False`` returns (None, close_idx) so that the caller can overlap the host gather with GPU work."""
+        idx = np.empty(self.m, np.int64) if out_idx is None else out_idx[:self.m]
+        ts = np.empty(self.m, np.int64) if host_ts is None else None
+        self.ctx.check(self.ctx._L.fmk_index_download(self.ctx.h, self.h, _ptr(ts), _ptr(idx)))
+        if host_ts is not None and gather:
             ts = np.asarray(host_ts)[idx]
         return ts, idx
 
@@ -228,13 +231,19 @@ def cusum_bar_index(trades: DeviceTrades, sigma: DeviceBuf, sigma_floor: float, 
 
 
 # ---- per-bar reductions ---------------------------------------------------------------------------------------------
-def bar_ohlcv(trades: DeviceTrades, index: DeviceIndex, median=True):
-    """(open, high, low, close, volume f32, vwap, trades i64, median) -- tuple order of comp_bar_ohlcv (base.py:407)."""
+def bar_ohlcv(trades: DeviceTrades, index: DeviceIndex, median=True, out=None):
+    """(open, high, low, close, volume f32, vwap, trades i64, median) -- tuple order of comp_bar_ohlcv (base.py:407).
+    ``out``: optional tuple of 8 preallocated arrays of >= n_bars elements in that order (e.g. pinned memory)."""
     nb = max(index.m - 1, 0)
-    o, h, l, c, vwap = (np.empty(nb) for _ in range(5))
-    vol = np.empty(nb, np.float32)
-    tr = np.empty(nb, np.int64)
-    med = np.empty(nb) if median else None
+    if out is not None:
+        o, h, l, c, vol, vwap, tr, med = (a[:nb] for a in out)
+        if not median:
+            med = None
+    else:
+        o, h, l, c, vwap = (np.empty(nb) for _ in range(5))
+        vol = np.empty(nb, np.float32)
+        tr = np.empty(nb, np.int64)
+        med = np.empty(nb) if median else None
     ctx = trades.ctx
     ctx.check(ctx._L.fmk_bar_ohlcv(ctx.h, trades.h, index.h, _ptr(o), _ptr(h), _ptr(l), _ptr(c), _ptr(vol), _ptr(vwap), _ptr(tr), _ptr(med)))
     return o, h, l, c, vol, vwap, tr, med
