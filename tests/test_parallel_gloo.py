@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from finmlkit_b200.parallel import gather_frames, shard_symbols
+from finmlkit_b200.parallel import PipelinedFrameGather, gather_frames, shard_symbols
 
 
 def _free_port():
@@ -32,6 +32,24 @@ def _worker(rank, world, port, q):
             q.put(("gather", ok))
         else:
             assert frames is None
+        # pipelined gatherer (synchronous path on CPU tensors): three steps with frames of varying length and content
+        g = PipelinedFrameGather(frame, dst=0)
+        ok = True
+        for step in range(3):
+            f = torch.from_numpy(np.full(900 + 50 * step + 37 * rank, 20 + step + rank, np.uint8))
+            g.submit(f)
+            fr = g.finish()
+            if rank == 0:
+                ok = ok and len(fr) == world and all(x.numel() == 900 + 50 * step + 37 * r and bool((x == 20 + step + r).all())
+                                                       for r, x in enumerate(fr))
+            else:
+                ok = ok and fr is None
+        try:
+            g.submit(torch.zeros(g.capacity + 1, dtype=torch.uint8))
+            ok = False
+        except ValueError:
+            pass
+        q.put(("pipelined", rank, ok))
         q.put(("shard", rank, mine))
         dist.barrier()
     finally:
@@ -46,10 +64,11 @@ def test_world_size_2_gather_and_sharding():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=120) for _ in range(world + 1)]
+    got = [q.get(timeout=120) for _ in range(2 * world + 1)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     shards = {g[1]: g[2] for g in got if g[0] == "shard"}
     assert shards[0] == ["BTC", "SOL", "ADA"] and shards[1] == ["ETH", "XRP"]
     assert ("gather", True) in got
+    assert ("pipelined", 0, True) in got and ("pipelined", 1, True) in got
