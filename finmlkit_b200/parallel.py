@@ -61,7 +61,9 @@ class PipelinedFrameGather:
         self.done = [None, None]
         self.k = 0
         self.last = None
-        self.comm = torch.cuda.Stream(frame.device) if self.cuda else None
+        import os
+        self.overlap = os.environ.get("FMK_GATHER_OVERLAP", "1") != "0"
+        self.comm = torch.cuda.Stream(frame.device) if (self.cuda and self.overlap) else None
 
     def submit(self, frame):
         torch, dist = self.torch, self.dist
@@ -75,14 +77,17 @@ class PipelinedFrameGather:
                 main.wait_event(self.done[s])               # the gather that read this buffer two steps ago is finished
             self.buf[s][:8].view(torch.int64).fill_(n)
             self.buf[s][self.HDR:self.HDR + n].copy_(frame, non_blocking=True)
-            ready = torch.cuda.Event()
-            ready.record(main)
-            with torch.cuda.stream(self.comm):
-                self.comm.wait_event(ready)
+            if self.comm is None:                           # same-stream variant: no overlap, no size exchange
                 dist.gather(self.buf[s], self.out[s], dst=self.dst)
-                ev = torch.cuda.Event()
-                ev.record(self.comm)
-            self.done[s] = ev
+            else:
+                ready = torch.cuda.Event()
+                ready.record(main)
+                with torch.cuda.stream(self.comm):
+                    self.comm.wait_event(ready)
+                    dist.gather(self.buf[s], self.out[s], dst=self.dst)
+                    ev = torch.cuda.Event()
+                    ev.record(self.comm)
+                self.done[s] = ev
         else:
             self.buf[s][:8].view(torch.int64).fill_(n)
             self.buf[s][self.HDR:self.HDR + n].copy_(frame)
