@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libfmk.so")
 SOURCES = ["api.cu", "reduce.cu", "series.cu", "index_dollar.cu", "index_volume.cu", "index_cusum.cu", "barlevel.cu", "weights.cu", "ingest.cu", "volprofile.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
-              "-prec-div=true", "-prec-sqrt=true", "--extended-lambda", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
+              "-prec-div=true", "-prec-sqrt=true", "--extended-lambda", "-diag-suppress", "20054", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
               "-Xcompiler", "-Wno-unused-function"]
 
 

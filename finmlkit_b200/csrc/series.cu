@@ -355,7 +355,6 @@ __global__ void __launch_bounds__(256) k_triple_barrier(const int64_t *__restric
         double mu = 0.0, ml = 0.0;       // per-lane maxima, reduced at the end
         int64_t touch = t1i;
         double ret_final = 0.0;
-        bool touched = false;
         for (int64_t j0 = t0i + 1; j0 <= t1i; j0 += 32) {
             const int64_t j = j0 + lane;
             const bool act = j <= t1i;
@@ -374,7 +373,6 @@ __global__ void __launch_bounds__(256) k_triple_barrier(const int64_t *__restric
                 else if (ret < 0.0 && lv) { const double r = __ddiv_rn(ret, lower); if (r > ml) ml = r; }
             }
             if (hm) {
-                touched = true;
                 touch = j0 + first;
                 ret_final = __shfl_sync(FULL, ret, first);
                 break;
@@ -403,7 +401,6 @@ __global__ void __launch_bounds__(256) k_triple_barrier(const int64_t *__restric
                 else { r = __ddiv_rn(ml, __dadd_rn(1.0, mu)); if (!lv) r = nan; }
                 ratios[e] = (1.0 < r) ? 1.0 : r;
             } else ratios[e] = 1.0;
-            (void)touched;
         }
     }
 }
