@@ -94,3 +94,19 @@ def check_weights(api):
         api.return_attribution(np.array(c["ev"], np.int64), np.array(c["touch"], np.int64), np.array(c["close"]), np.array(c["conc"], np.int16), True)
     w = api.return_attribution(np.zeros(0, np.int64), np.zeros(0, np.int64), np.array([100., 101., 102.]), np.ones(3, np.int16), False)
     assert len(w) == 0 and w.dtype == np.float64
+
+
+def check_volume_profile(vp_rolling_csr):
+    """One two-bar series whose second window aggregates exactly the five given levels (no bucketing)."""
+    for c in V.VP_ABOVE_POC:
+        vol = np.array(c["vol"], np.float32)
+        ts = np.array([0, 10**9], np.int64)
+        off = np.array([0, 5, 10], np.int64)
+        lv = np.tile(np.arange(100, 105, dtype=np.int32), 2)
+        buy = np.concatenate([np.zeros(5, np.float32), vol])
+        sell = np.zeros(10, np.float32)
+        poc, hva, lva, pct = vp_rolling_csr(ts, np.array([10.4, 10.4]), np.array([10.0, 10.0]), off, lv, buy, sell, 0.5, None, 0.1)
+        assert poc[0] == 0 and pct[0] == 0.0                  # no full window yet
+        assert poc[1] == c["poc"], (poc, c)
+        np.testing.assert_allclose(pct[1], np.float32(c["pct"]), rtol=1e-6)
+        assert lva[1] <= poc[1] <= hva[1]

@@ -92,3 +92,16 @@ RETURN_ATTRIBUTION = dict(close=[100., 102., 104., 106.], ev=[0], touch=[3], con
 RETURN_ATTRIBUTION_ZERO = dict(close=[100., 100., 100., 100.], ev=[0, 2], touch=[1, 3], conc=[1, 1, 1, 1])
 # time_decay -- reference tests/labels/test_time_decay.py:22-47
 TIME_DECAY = [([0.5, 0.5, 0.5, 0.5], 1.0, [1.0, 1.0, 1.0, 1.0]), ([0.5, 0.5, 0.5, 0.5], 0.4, [0.55, 0.7, 0.85, 1.0])]
+
+# class_balance_weights -- reference tests/labels/test_class_balace_weights.py:10-75 (hand-computed)
+CLASS_BALANCE = [
+    dict(labels=[1, -1, 1, 0, -1, 1], w=[1., 1., 1., 1., 1., 1.], uniq=[-1, 0, 1], sums=[2., 1., 3.], cw=[1.0, 2.0, 6 / 9]),
+    dict(labels=[1, -1, 1, 0, -1, 1], w=[1., 2., 1., 3., 2., 1.], uniq=[-1, 0, 1], sums=[4., 3., 3.], cw=[10 / 12, 10 / 9, 10 / 9]),
+]
+# calc_volume_percentage_above_poc through volume_profile_rolling on a single aggregated window -- reference
+# tests/features/test_volume_profile_rolling.py:13-50: five levels 100..104, POC at the max-volume level
+VP_ABOVE_POC = [
+    dict(vol=[10., 5., 20., 5., 10.], poc=102, pct=0.3),
+    dict(vol=[0., 0., 5., 10., 15.], poc=104, pct=0.0),
+    dict(vol=[10., 5., 0., 0., 0.], poc=100, pct=5. / 15.),
+]

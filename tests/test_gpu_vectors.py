@@ -40,3 +40,8 @@ def test_tbm(api):
 
 def test_weights(api):
     chk.check_weights(api)
+
+
+def test_volume_profile_vectors(ctx):
+    from finmlkit_b200 import core
+    chk.check_volume_profile(lambda *a: core.volume_profile_rolling_csr(*a, ctx=ctx))

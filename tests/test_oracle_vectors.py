@@ -54,3 +54,18 @@ def test_weights():
 def test_time_decay_host(u, last, want):
     from finmlkit_b200.label.weights import time_decay
     np.testing.assert_allclose(time_decay(np.array(u), last), np.array(want), rtol=1e-12)
+
+
+def test_volume_profile_vectors():
+    chk.check_volume_profile(oracle.volume_profile_rolling_csr)
+
+
+@pytest.mark.parametrize("c", V.CLASS_BALANCE)
+def test_class_balance_host(c):
+    from finmlkit_b200.label.weights import class_balance_weights
+    u, cw, sums, fw = class_balance_weights(np.array(c["labels"], np.int8), np.array(c["w"]))
+    np.testing.assert_array_equal(u, np.array(c["uniq"], np.int8))
+    np.testing.assert_allclose(sums, c["sums"], rtol=1e-12)
+    np.testing.assert_allclose(cw, c["cw"], rtol=1e-12)
+    idx = np.searchsorted(u, np.array(c["labels"]))
+    np.testing.assert_allclose(fw, np.array(c["w"]) * np.array(c["cw"])[idx], rtol=1e-12)
