@@ -1,38 +1,56 @@
 #!/usr/bin/env python
 """
-bench.py -- headline benchmark: ticks/s of the bar + feature build (BASELINE.json metric) on B200.
+bench.py -- ticks/s of the bar + feature build (BASELINE.json metric) on B200, every BASELINE config in one JSON line.
 
-Workload (BASELINE.json configs[1]): N synthetic BTCUSDT-like ticks per GPU -> dollar bars ($1M threshold, bit-exact
-boundaries) + OHLCV/VWAP/trade count/median trade size, float64.  One "step" = one full pass of that path over one
-stream: fmk_dollar_bar_index + fmk_bar_ohlcv_device on device-resident SoA columns (`value`), and the same through the
-host-buffer C ABI with H2D/D2H inside the timed region (`e2e`).  N>1: one independent symbol stream per GPU (weak
-scaling, no data-path collective inside a symbol) plus one NCCL gather of the finished bar frames to rank 0 per step.
+Headline (`value`, `e2e`, `roofline`; BASELINE configs[1]): N synthetic BTCUSDT-like ticks per GPU -> dollar bars ($1M
+threshold, bit-exact boundaries) + OHLCV / VWAP / trade count / median trade size, float64.  One "step" = one full pass of
+that path over one stream: fmk_dollar_bar_index + fmk_bar_features_device on device-resident SoA columns (`value`), and
+the same through the host-buffer C ABI with H2D / D2H inside the timed region (`e2e`).  N > 1: one independent symbol
+stream per GPU (weak scaling, no data-path collective inside a symbol) plus ONE gather of the finished bar frames to
+rank 0 per step through libfmk's own NCCL communicator (no torch anywhere in this file).
+
+Sub-records of the same line (each with ms/step, per-kernel ms, step-level `roofline`, `cpu_baseline`, `e2e`):
+  config1         1e6 ticks -> TimeBarKit(1 min).build_ohlcv() through the pandas wrapper (the reference's published case)
+  time_bars_1min  the north-star time-bar build at N ticks, device resident
+  config3         N ticks -> volume bars + OHLCV + directional + footprint CSR
+  config4         N ticks -> sigma (lagged log returns + ewmst, 1 h) -> CUSUM bars -> triple barrier (2 sigma, 1 h) -> weights
+  config5         5e8 ticks per GPU -> dollar bars + the FULL feature set (OHLCV, directional, trade size, footprints) +
+                  gather of every frame incl. the footprint CSR (BASELINE configs[4]; run at every N)
+  e2e_wrapper     DollarBarKit(trades, 1e6).build_ohlcv() on pageable pandas columns, ours next to the reference's
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--ticks T] [--impl ours|reference]
 
-Prints ONE JSON line.  `--impl reference` times the CPU restatement of the reference (oracle/, OpenMP where the
-reference uses prange) on the host cores on a bounded sample of the same workload.
+Prints ONE JSON line.  `--impl reference` times the UNMODIFIED reference (Numba, from baseline/_ref -- see
+scripts/install_ref.sh) on the host cores on a bounded sample of the same workload; the C port under oracle/ is only the
+declared fallback when baseline/_ref is absent.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
 import sys
 import threading
 import time
+import zlib
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-THRESHOLD = 1e6
+THRESHOLD = 1e6          # dollar bars
+VOLUME_T = 50.0          # volume bars (config 3)
+TICK = 0.1               # price tick of the synthetic stream
 METRIC = "ticks/sec bar+feature build"
 UNIT = "ticks/s"
 # algorithmic HBM bytes per tick of each streaming kernel
 ALGO_BYTES_PER_TICK = {"k_dollar_tasks": 16, "k_dollar_chunk_sums": 16, "k_bar_ohlcv_warp": 16, "k_bar_ohlcv_thread": 16,
-                       "k_bar_order_stats": 8, "k_bar_ohlcv_median": 16, "k_bar_ohlcv_conveyor": 16,
-                       "k_bar_ohlcv_median_v1": 16, "k_bar_ohlcv_median<true>": 16, "k_bar_ohlcv_median<false>": 16}
+                       "k_bar_order_stats": 8, "k_bar_ohlcv_median": 16, "k_bar_features": 17, "k_bar_directional": 17,
+                       "k_bar_footprint": 17, "k_bar_trade_size": 8, "k_lagged_returns": 24, "k_ewm_reduce": 16,
+                       "k_ewm_apply": 24, "k_cusum_prep": 41, "k_cusum_tasks<0>": 17, "k_triple_barrier": 16, "k_log": 16}
+# step-level algorithmic bytes per tick: what one pass over the inputs must read (+ per-tick outputs)
+STEP_BYTES = {"config2": 16, "time_bars": 16, "config3": 17, "config4": 24 + 24 + 24 + 16, "config5": 17}
 
 
 def env_int(name, default):
@@ -139,43 +157,234 @@ def ncu_traffic(kernel):
         return None
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ======================================================================================================================
+# the reference's own CPU implementation (Numba, UNMODIFIED, from baseline/_ref); the C port is the declared fallback
+# ======================================================================================================================
+class Reference:
+    """kind 'reference' = the real finmlkit (Numba) imported from baseline/_ref; kind 'port' = oracle/ (fallback only)."""
+
+    def __init__(self):
+        cores = host_cores()
+        ref_dir = os.path.join(ROOT, "baseline", "_ref")
+        self.kind, self.why_port = "port", None
+        if os.path.isdir(os.path.join(ref_dir, "finmlkit")) and os.environ.get("FMK_BENCH_FORCE_PORT") != "1":
+            # torchrun exports OMP_NUM_THREADS=1; the reference arm is supposed to use every host core it can
+            os.environ["OMP_NUM_THREADS"] = str(cores)
+            os.environ.setdefault("NUMBA_NUM_THREADS", str(cores))
+            os.environ.setdefault("FMK_CONSOLE_LOGGER_LEVEL", "ERROR")
+            if ref_dir not in sys.path:
+                sys.path.insert(0, ref_dir)
+            try:
+                import numba
+                from finmlkit.bar import base as rb, kit as rk, logic as rl
+                from finmlkit.bar.data_model import TradesData
+                from finmlkit.feature.core.utils import comp_lagged_returns
+                from finmlkit.feature.core.volatility import ewmst
+                from finmlkit.label.tbm import triple_barrier
+                from finmlkit.label.weights import average_uniqueness, return_attribution
+                self.kind = "reference"
+                self.cores = int(numba.get_num_threads())
+                self.numba = {"version": numba.__version__, "threading_layer_request": numba.config.THREADING_LAYER,
+                              "num_threads": self.cores}
+                self.rb, self.rk, self.rl, self.TradesData = rb, rk, rl, TradesData
+                self.lagged, self.ewmst_f, self.tbm, self.au, self.ra = comp_lagged_returns, ewmst, triple_barrier, average_uniqueness, return_attribution
+            except Exception as e:      # numba / pandas mismatch on the box: say so and fall back to the port
+                self.why_port = f"baseline/_ref import failed: {type(e).__name__}: {e}"
+        else:
+            self.why_port = "baseline/_ref/finmlkit absent (run scripts/install_ref.sh where /root/reference exists)"
+        if self.kind == "port":
+            import oracle
+            oracle.set_num_threads(cores)
+            self.cores = oracle.num_threads()
+            self.o = oracle
+
+    def describe(self):
+        if self.kind == "reference":
+            return f"finmlkit 0.1.11 Numba path from baseline/_ref (numba {self.numba['version']}, {self.cores} threads)"
+        return f"C port of the reference (oracle/, {self.cores} OpenMP threads) -- fallback: {self.why_port}"
+
+    # ---- kernel-level legs: each returns a callable doing ONE pass of the path on the given arrays ---------------------
+    def dollar_ohlcv(self, px, qty):
+        if self.kind == "reference":
+            rl, rb = self.rl, self.rb
+
+            def f():
+                idx = np.array(rl._dollar_bar_indexer(px, qty, THRESHOLD), dtype=np.int64)     # bar/kit.py:133-134
+                rb.comp_bar_ohlcv(px, qty, idx)
+                return len(idx) - 1
+            return f
+        o = self.o
+
+        def g():
+            idx = o.dollar_bar_indexer(px, qty, THRESHOLD)
+            o.comp_bar_ohlcv(px, qty, idx)
+            return len(idx) - 1
+        return g
+
+    def time_ohlcv(self, ts, px, qty):
+        if self.kind == "reference":
+            rl, rb = self.rl, self.rb
+
+            def f():
+                _, idx = rl._time_bar_indexer(ts, 60.0)
+                rb.comp_bar_ohlcv(px, qty, idx)
+                return len(idx) - 1
+            return f
+        o = self.o
+
+        def g():
+            _, idx = o.time_bar_indexer(ts, 60.0)
+            o.comp_bar_ohlcv(px, qty, idx)
+            return len(idx) - 1
+        return g
+
+    def config3(self, px, qty, side):
+        if self.kind == "reference":
+            rl, rb = self.rl, self.rb
+
+            def f():
+                idx = np.array(rl._volume_bar_indexer(qty, VOLUME_T), dtype=np.int64)
+                o = rb.comp_bar_ohlcv(px, qty, idx)
+                rb.comp_bar_directional_features(px, qty, idx, side)
+                rb.comp_bar_footprints(px, qty, idx, side, TICK, o[2], o[1], 3.0)
+                return len(idx) - 1
+            return f
+        o_ = self.o
+
+        def g():
+            idx = o_.volume_bar_indexer(qty, VOLUME_T)
+            o = o_.comp_bar_ohlcv(px, qty, idx)
+            o_.comp_bar_directional_features(px, qty, idx, side)
+            o_.comp_bar_footprints_csr(px, qty, idx, side, TICK, o[2], o[1], 3.0)
+            return len(idx) - 1
+        return g
+
+    def config4(self, ts, px):
+        last = int(ts[-1])
+        if self.kind == "reference":
+            lag, ew, cus, tbm, au, ra = self.lagged, self.ewmst_f, self.rl._cusum_bar_indexer, self.tbm, self.au, self.ra
+        else:
+            o = self.o
+            lag, ew, cus, tbm, au, ra = (o.comp_lagged_returns, o.ewmst, o.cusum_bar_indexer, o.triple_barrier,
+                                         o.average_uniqueness, o.return_attribution)
+
+        def f():
+            r = lag(ts, px, 3600.0, True)
+            sig = ew(ts, r, 3600.0)
+            cidx = np.array(cus(ts, px, sig, 5e-4, 2.0), dtype=np.int64)
+            ev = cidx[1:]
+            tg = sig[ev]
+            keep = np.isfinite(tg) & (ts[ev] + 3600 * 10**9 <= last)
+            ev, tg = ev[keep], tg[keep]
+            if len(ev) == 0:
+                return 0
+            lab = tbm(ts, px, ev, tg, (2.0, 2.0), 3600.0, 1.0, None, 0.0)
+            w, conc = au(ts, ev, lab[1])
+            ra(ev, lab[1], px, conc, False)
+            return len(ev)
+        return f
+
+    def trades_data(self, ts, px, qty, side):
+        if self.kind == "reference":
+            return self.TradesData(ts, px, qty, side=side)
+        from finmlkit_b200.bar.data_model import TradesData
+        return TradesData(ts, px, qty, side=side)
+
+    def dollar_kit(self, td):
+        if self.kind == "reference":
+            return lambda: len(self.rk.DollarBarKit(td, THRESHOLD).build_ohlcv())
+        return None
+
+    def time_kit(self, td):
+        if self.kind == "reference":
+            import pandas as pd
+            return lambda: len(self.rk.TimeBarKit(td, pd.Timedelta(minutes=1)).build_ohlcv())
+        return None
+
+
+def best_of(fn, reps=3, warm=1):
+    for _ in range(warm):
+        fn()
+    best, out = 1e30, None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = fn()
+        best = min(best, time.perf_counter() - t0)
+    return best, out
+
+
+def cpu_record(ref, seconds, ticks, what):
+    return {"value": ticks / seconds, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": what,
+            "seconds": seconds, "impl": ref.describe()}
+
+
 def run_reference(args):
-    """CPU arm: oracle port of the reference (dollar indexer serial like the reference; comp_bar_ohlcv over all cores)."""
-    import oracle
+    """CPU arm: the reference's own Numba implementation on the box's host cores (rank 0 only)."""
     from finmlkit_b200.synth import synth_trades
-    rank = env_int("RANK", 0)
-    if rank != 0:
+    if env_int("RANK", 0) != 0:
         return
+    ref = Reference()
     sample = int(min(args.ticks, args.cpu_sample))
     ts, px, qty, side = synth_trades(sample, seed=42)
-    # torchrun exports OMP_NUM_THREADS=1; the reference arm is supposed to use every host core it can
-    try:
-        oracle.set_num_threads(len(os.sched_getaffinity(0)))
-    except Exception:
-        oracle.set_num_threads(os.cpu_count() or 1)
-    cores = oracle.num_threads()
-
-    def step():
-        idx = oracle.dollar_bar_indexer(px, qty, THRESHOLD)
-        oracle.comp_bar_ohlcv(px, qty, idx)
-        return len(idx) - 1
-
-    for _ in range(max(args.warmup, 1)):
+    step = ref.dollar_ohlcv(px, qty)
+    for _ in range(max(args.warmup, 1)):          # the first call pays the JIT
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         nb = step()
     dt = (time.perf_counter() - t0) / args.steps
     val = sample / dt
+    what = (f"first {sample} ticks of the {args.ticks}-tick workload; _dollar_bar_indexer (serial, as the reference runs it) + "
+            f"np.array(NumbaList) + comp_bar_ohlcv (prange over bars) on {ref.cores} threads")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"dollar bars $1e6 + OHLCV (incl. median), {sample} synthetic ticks per step (bounded sample of the "
-                                   f"{args.ticks}-tick workload), CPU port of the reference's Numba path", "bars": nb},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"first {sample} ticks; _dollar_bar_indexer serial + comp_bar_ohlcv on {cores} OpenMP threads"},
+            "config": {"workload": f"BASELINE configs[1]: dollar bars $1e6 + OHLCV (incl. median), {sample} synthetic ticks per step "
+                                   f"(bounded sample of the {args.ticks}-tick workload), {ref.describe()}", "bars": nb,
+                       "reference_kind": ref.kind},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": what, "impl": ref.describe()},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not args.no_sub:
+        s2 = int(min(sample, args.cpu_sub_sample))
+        line.update(cpu_sub_records(ref, ts[:s2], px[:s2], qty[:s2], side[:s2]))
     emit(line)
+
+
+def cpu_sub_records(ref, ts, px, qty, side):
+    """configs 1 / 3 / 4 and the wrapper-level leg on the host cores (kernel-level = the reference's L0 functions)."""
+    out = {}
+    n = len(px)
+    # config 1: the reference's published case -- 1e6 ticks -> 1-minute time bars through the pandas wrapper
+    n1 = min(n, 1_000_000)
+    td1 = ref.trades_data(ts[:n1].copy(), px[:n1].copy(), qty[:n1].copy(), side[:n1].copy())
+    kit = ref.time_kit(td1)
+    rec = {}
+    if kit is not None:
+        sec, nb = best_of(kit, reps=5)
+        rec["wrapper"] = cpu_record(ref, sec, n1, f"TimeBarKit(trades, 1 min).build_ohlcv() on {n1} ticks, best of 5, warm JIT")
+        rec["wrapper"]["bars"] = nb
+    sec, nb = best_of(ref.time_ohlcv(ts[:n1], px[:n1], qty[:n1]), reps=5)
+    rec["kernels"] = cpu_record(ref, sec, n1, f"_time_bar_indexer + comp_bar_ohlcv on {n1} ticks, best of 5")
+    rec["published"] = {"ticks_per_s": 39171929 / 0.1728, "source": "examples/PerformanceTest.ipynb:311 (0.1728 s / 39.17 M ticks, unstated hardware)"}
+    out["config1"] = rec
+    sec, nb = best_of(ref.time_ohlcv(ts, px, qty), reps=2)
+    out["time_bars_1min"] = cpu_record(ref, sec, n, f"_time_bar_indexer + comp_bar_ohlcv on {n} ticks, best of 2")
+    sec, nb = best_of(ref.config3(px, qty, side), reps=2)
+    out["config3"] = cpu_record(ref, sec, n, f"_volume_bar_indexer (T={VOLUME_T}) + comp_bar_ohlcv + comp_bar_directional_features + "
+                                             f"comp_bar_footprints (serial in the reference) on {n} ticks, best of 2")
+    out["config3"]["bars"] = nb
+    sec, ne = best_of(ref.config4(ts, px), reps=2)
+    out["config4"] = cpu_record(ref, sec, n, f"comp_lagged_returns(1 h, log) + ewmst(1 h) + _cusum_bar_indexer + triple_barrier(2 sigma, 1 h) + "
+                                             f"average_uniqueness + return_attribution on {n} ticks, best of 2")
+    out["config4"]["events"] = ne
+    return out
 
 
 _JSON_OUT = None
@@ -198,6 +407,457 @@ def emit(line):
     out.flush()
 
 
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# ======================================================================================================================
+# ours
+# ======================================================================================================================
+class Pinned:
+    """pinned host arrays (fmk_host_alloc) that live until close()"""
+
+    def __init__(self, L):
+        self.L, self.ptrs = L, []
+
+    def array(self, dtype, count):
+        dt = np.dtype(dtype)
+        p = C.c_void_p()
+        if self.L.fmk_host_alloc(C.byref(p), max(int(count), 1) * dt.itemsize) != 0:
+            raise MemoryError("pinned allocation failed")
+        self.ptrs.append(p)
+        buf = (C.c_char * (max(int(count), 1) * dt.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dt, count=int(count))
+
+    def close(self):
+        for p in self.ptrs:
+            self.L.fmk_host_free(p)
+        self.ptrs = []
+
+
+def timed_steps(ctx, step, steps, warmup, finish=None, comm=None):
+    """(ms per step [max over ranks], per-kernel {name: ms per step}, launches in the timed region)"""
+    for _ in range(warmup):
+        step()
+    if finish:
+        finish()
+    ctx.sync()
+    if comm:
+        comm.barrier()
+    l0 = ctx.launch_count()
+    ctx.prof_enable(True)
+    ctx.timer_start()
+    for _ in range(steps):
+        step()
+    if finish:
+        finish()
+    ms = ctx.timer_stop()
+    ctx.prof_enable(False)
+    prof = ctx.prof_report()
+    launches = ctx.launch_count() - l0
+    if comm:
+        ms = float(comm.allreduce([ms], "max")[0])
+    kern = {k: v[1] / steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    return ms / steps, kern, launches, prof
+
+
+def step_roofline(name, n, ms_per_step, kern):
+    """step-level roofline: algorithmic bytes of ONE pass over the inputs / time of the whole step (sum of its kernels)"""
+    peak, src = measured_peak()
+    ach = STEP_BYTES[name] * n / (ms_per_step * 1e-3) / 1e9
+    dom = max(kern.items(), key=lambda kv: kv[1]) if kern else (None, 0.0)
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "algorithmic_bytes_per_tick": STEP_BYTES[name], "scope": "whole step (all kernels of the config)",
+            "dominant_kernel": dom[0], "dominant_kernel_ms": dom[1], "peak_source": src}
+
+
+def run_ours(args):
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    from finmlkit_b200 import core
+    ctx = core.Context(local)
+    L = ctx._L
+    comm = None
+    if world > 1:
+        from finmlkit_b200.parallel import Comm
+        comm = Comm.from_env(ctx, max_ctas=env_int("FMK_NCCL_MAX_CTAS", 4))
+    n = args.ticks
+    sub_steps, sub_warm = max(1, min(args.steps, args.sub_steps)), 1
+    tr = core.DeviceTrades.synth(n, seed=42 + rank, ctx=ctx)   # one independent symbol per rank
+    peak, peak_src = measured_peak()
+
+    # ---- headline: dollar bars + OHLCV incl. median (BASELINE configs[1]) ------------------------------------------------
+    state = {"nbars": 0, "frame_bytes": 0}
+
+    def step():
+        ix = core.dollar_bar_index(tr, THRESHOLD)
+        fr = core.bar_features_device(tr, ix, core.F_OHLCV | core.F_MEDIAN)
+        state["nbars"], state["frame_bytes"] = ix.m - 1, fr.bar_bytes
+        if comm:
+            comm.gather_submit(fr.segments(), dst=0)      # packed on the ctx stream now; the transfer overlaps the next step
+
+    finish = comm.gather_finish if comm else None
+    for _ in range(args.warmup):
+        step()
+    if finish:
+        finish()
+    ctx.sync()
+    if comm:
+        comm.barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms_per_step, kern, launches, prof = timed_steps(ctx, step, args.steps, 0, finish, comm)
+    clk = clocks.stop()
+    stats = ctx.index_stats()
+    value = world * n / (ms_per_step * 1e-3)
+    gather_bytes = sum(comm.gathered_bytes()) if comm else 0
+
+    roofline = None
+    if prof:
+        name, (cnt, tot_ms) = max(prof.items(), key=lambda kv: kv[1][1])
+        per_launch_ms = tot_ms / cnt
+        algo = ALGO_BYTES_PER_TICK.get(name)
+        if algo:
+            achieved = algo * n / (per_launch_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": ncu_traffic(name), "algorithmic_bytes_per_launch": algo * n, "launch_ms": per_launch_ms,
+                        "share_of_step": tot_ms / args.steps / ms_per_step if comm is None else None, "peak_source": peak_src,
+                        "all_kernels_ms_per_step": kern,
+                        "step_level": step_roofline("config2", n, ms_per_step, kern)}
+
+    sub = {}
+    # ---- north star: single-GPU 1-minute time-bar build ------------------------------------------------------------------
+    if world == 1 and not args.no_sub:
+        tb = {}
+        for with_median in (1, 0):
+            flags = core.F_OHLCV | (core.F_MEDIAN if with_median else 0)
+
+            def tstep():
+                tix = core.time_bar_index(tr, 60.0)
+                core.bar_features_device(tr, tix, flags)
+                state["tbars"] = tix.m - 1
+            tms, tk, _, _ = timed_steps(ctx, tstep, args.steps, 1)
+            rec = {"ticks_per_s": n / (tms * 1e-3), "ms_per_step": tms, "bars": state["tbars"], "kernels_ms_per_step": tk,
+                   "roofline": step_roofline("time_bars", n, tms, tk)}
+            tb["ohlcv+median" if with_median else "ohlcv"] = rec
+        sub["time_bars_1min"] = tb
+
+    # ---- config 3: volume bars + OHLCV + directional + footprint CSR -----------------------------------------------------
+    F3 = core.F_OHLCV | core.F_MEDIAN | core.F_DIRECTIONAL | core.F_FOOTPRINT
+    if world == 1 and not args.no_sub:
+        def step3():
+            vix = core.volume_bar_index(tr, VOLUME_T)
+            fr = core.bar_features_device(tr, vix, F3, price_tick_size=TICK, imbalance_factor=3.0)
+            state["c3"] = (vix.m - 1, fr.n_levels, fr.bar_bytes + fr.level_bytes)
+        ms3, k3, _, _ = timed_steps(ctx, step3, sub_steps, sub_warm)
+        sub["config3"] = {"workload": f"BASELINE configs[2]: {n} ticks -> volume bars (T={VOLUME_T}) + OHLCV incl. median + 14 directional "
+                                      f"features + footprint CSR (tick {TICK}, imbalance factor 3), device resident",
+                          "ticks_per_s": n / (ms3 * 1e-3), "ms_per_step": ms3, "steps": sub_steps, "bars": state["c3"][0],
+                          "footprint_levels": state["c3"][1], "output_bytes": state["c3"][2], "kernels_ms_per_step": k3,
+                          "index_stats": ctx.index_stats(), "roofline": step_roofline("config3", n, ms3, k3)}
+        log("config3", sub["config3"]["ms_per_step"])
+
+    # ---- config 4: sigma -> CUSUM bars -> triple barrier -> sample weights -----------------------------------------------
+    if world == 1 and not args.no_sub:
+        last_ts = int(np.asarray(core_last_ts(core, tr)))
+
+        def step4():
+            r = core.lagged_returns_dev(tr, 3600.0, True)
+            sig = core.ewmst_dev(tr, r, 3600.0)
+            del r
+            cix = core.cusum_bar_index(tr, sig, 5e-4, 2.0)
+            state["c4stats"] = ctx.index_stats()
+            cts, cidx = cix.download()
+            ev, tg = cidx[1:], sig.gather(cidx[1:])
+            keep = np.isfinite(tg) & (cts[1:] + 3600 * 10**9 <= last_ts)
+            ev, tg = ev[keep], tg[keep]
+            lab = core.triple_barrier_dev(tr, ev, tg, (2.0, 2.0), 3600.0, 1.0, None, 0.0)
+            core.sample_weights_dev(tr, ev, lab[1])
+            state["c4"] = (cix.m - 1, len(ev), float(np.mean(lab[1] - ev)) if len(ev) else 0.0)
+        ms4, k4, _, _ = timed_steps(ctx, step4, max(1, min(sub_steps, 3)), sub_warm)
+        sub["config4"] = {"workload": f"BASELINE configs[3] (oracle-pinned half): {n} ticks -> sigma = ewmst(log returns 1 h, half-life 1 h) -> "
+                                      "CUSUM bars (2 sigma, floor 5e-4) -> triple barrier (2 sigma / 2 sigma, 1 h vertical, 1 s min close) -> "
+                                      "average uniqueness + return attribution; device resident, event lists through the host",
+                          "ticks_per_s": n / (ms4 * 1e-3), "ms_per_step": ms4, "steps": max(1, min(sub_steps, 3)),
+                          "cusum_bars": state["c4"][0], "events": state["c4"][1], "mean_path_ticks": state["c4"][2],
+                          "kernels_ms_per_step": k4,
+                          "cusum_stats": {"chunks": state["c4stats"]["tasks"], "chunk_replays": state["c4stats"]["serial_repairs"],
+                                          "rounds": state["c4stats"]["chain_passes"]}, "roofline": step_roofline("config4", n, ms4, k4)}
+        log("config4", sub["config4"]["ms_per_step"])
+        # EMA-imbalance bars (the other half of configs[3]): no reference implementation -> own oracle, parity unpinned
+        if hasattr(core, "imbalance_bar_index"):
+            def step4i():
+                iix = core.imbalance_bar_index(tr, args.imbalance_threshold)
+                state["c4i"] = iix.m - 1
+            msi, ki, _, _ = timed_steps(ctx, step4i, sub_steps, sub_warm)
+            sub["config4"]["imbalance_bars"] = {"parity": "unpinned -- own oracle (the reference raises NotImplementedError, bar/logic.py:224-241)",
+                                                "variant": "tick-imbalance, fixed threshold", "threshold": args.imbalance_threshold,
+                                                "ms_per_step": msi, "ticks_per_s": n / (msi * 1e-3), "bars": state["c4i"],
+                                                "kernels_ms_per_step": ki}
+
+    # ---- config 5: dollar bars + FULL feature set + gather of every frame (all N) ----------------------------------------
+    if not args.no_sub and not args.no_config5:
+        n5 = int(min(args.config5_ticks, n))
+        tr5 = tr if n5 == n else core.DeviceTrades.synth(n5, seed=1042 + rank, ctx=ctx)
+
+        def step5():
+            ix = core.dollar_bar_index(tr5, THRESHOLD)
+            fr = core.bar_features_device(tr5, ix, core.F_ALL, theta=None, theta_mult=5.0, price_tick_size=TICK, imbalance_factor=3.0)
+            state["c5"] = (ix.m - 1, fr.n_levels, fr.bar_bytes + fr.level_bytes)
+            state["c5_frame"] = fr
+            if comm:
+                comm.gather_submit(fr.segments(), dst=0)
+        ms5, k5, _, _ = timed_steps(ctx, step5, sub_steps, sub_warm, finish, comm)
+        rec5 = {"workload": f"BASELINE configs[4]: {n5} ticks per GPU, one symbol per GPU -> dollar bars ($1e6) + OHLCV incl. median + directional "
+                            f"+ trade-size (theta = the bar's median size, x5) + footprint CSR, "
+                            + ("one NCCL gather-v of every frame (per-bar block + footprint CSR block) to rank 0 per step" if comm else "single GPU: no gather"),
+                "ticks_per_s": world * n5 / (ms5 * 1e-3), "ms_per_step": ms5, "steps": sub_steps, "ticks_per_gpu": n5, "n_gpus": world,
+                "bars_per_gpu": state["c5"][0], "footprint_levels_per_gpu": state["c5"][1], "frame_bytes_per_gpu": state["c5"][2],
+                "kernels_ms_per_step_rank0": k5, "roofline": step_roofline("config5", n5, ms5, k5)}
+        if comm:
+            # the gathered bytes on rank 0 equal what each rank produced: crc32 of every rank's own frame vs the received copy
+            fr = state["c5_frame"]
+            mine = np.concatenate(frame_blocks(fr, ctx))
+            crc = np.zeros(world)
+            crc[rank] = float(zlib.crc32(mine.tobytes()))
+            crc = comm.allreduce(crc, "sum")
+            ok = None
+            if rank == 0:
+                ok = all(float(zlib.crc32(comm.gathered_frame(r).tobytes())) == crc[r] for r in range(world))
+            rec5["gather"] = {"bytes_per_step_total": sum(comm.gathered_bytes()), "received_equals_sent_crc32": ok,
+                              "nccl_version": int(L.fmk_comm_nccl_version())}
+        state.pop("c5_frame", None)
+        sub["config5"] = rec5
+        if tr5 is not tr:
+            del tr5
+        log("config5", rec5["ms_per_step"])
+
+    # ---- end to end through the host-buffer C ABI --------------------------------------------------------------------
+    e2e = None
+    cpu_baseline = None
+    if not args.no_e2e:
+        e2e, cpu_baseline, extra = run_e2e(args, core, ctx, comm, tr, n, rank, world, sub)
+        sub.update(extra)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"BASELINE configs[1]: {n} synthetic ticks per GPU -> dollar bars ($1e6, bit-exact boundaries) "
+                                       "+ OHLCV/VWAP/trades/median, fp64; one symbol stream per GPU"
+                                       + (", one NCCL gather-v (exact byte counts, libfmk's own communicator) of the bar frames to rank 0 per "
+                                          "step on a communication stream (overlaps the next step)" if world > 1 else ""),
+                           "ticks_per_gpu": n, "bars_per_gpu": state["nbars"], "threshold": THRESHOLD,
+                           "l2": "inputs (16-24 GB/step) exceed the 126 MB L2; no flush needed" if n * 16 > 4e8 else "inputs fit L2: timing is warm-L2",
+                           "parallelism": f"symbols x{world}", "index_stats": stats,
+                           "gather_bytes_per_step": gather_bytes},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline}
+        line.update(sub)
+        emit(line)
+    if comm:
+        comm.barrier()
+        comm.destroy()
+
+
+def core_last_ts(core, tr):
+    """ts[n-1] of a device stream without downloading the column: a one-element time-bar style gather via the index API"""
+    ix = core.DeviceIndex.from_host(tr, np.array([tr.n - 1, tr.n - 1], np.int64))
+    cts, _ = ix.download()
+    return cts[0]
+
+
+def frame_blocks(fr, ctx):
+    """host copies of a frame's blocks exactly as fmk_comm_gather_submit packs them (each padded to 16 bytes)"""
+    bar = np.zeros((fr.bar_bytes + 15) // 16 * 16, np.uint8)
+    lvl = np.zeros((fr.level_bytes + 15) // 16 * 16, np.uint8)
+    ctx.check(ctx._L.fmk_frame_download(ctx.h, fr.h, bar.ctypes.data_as(C.c_void_p), lvl.ctypes.data_as(C.c_void_p) if fr.level_bytes else None))
+    return [b for b in (bar, lvl) if b.size]
+
+
+def run_e2e(args, core, ctx, comm, tr, n, rank, world, sub):
+    """host buffers -> device -> host, inside the timed region: headline, config 3, config 4, the pandas wrapper; and the CPU
+    baselines (rank 0, N = 1) on a bounded prefix of the same arrays"""
+    L = ctx._L
+    extra = {}
+
+    def agree_min(x):
+        return int(comm.allreduce([float(x)], "min")[0]) if comm else int(x)
+
+    n_e = n
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+        while 26 * n_e > 0.55 * avail / max(world, 1) and n_e > 1_000_000:
+            n_e //= 2
+    except Exception:
+        pass
+    n_e = agree_min(n_e)
+    pin = Pinned(L)
+    for _attempt in range(6):      # pinned host memory is per node: halve the sample until every rank gets its buffers
+        try:
+            h_ts, h_px, h_qty, h_side = pin.array(np.int64, n_e), pin.array(np.float64, n_e), pin.array(np.float64, n_e), pin.array(np.int8, n_e)
+            ok = 1
+        except MemoryError:
+            ok = 0
+        if agree_min(ok):
+            break
+        pin.close()
+        n_e //= 2
+    else:
+        raise RuntimeError("pinned allocation failed on every attempt")
+    if n_e == n:
+        tr_e = tr
+    else:
+        tr_e = core.DeviceTrades.synth(n_e, seed=42 + rank, ctx=ctx)
+    tr_e.download(out=(h_ts, h_px, h_qty, h_side))
+
+    def wall(stepf, steps):
+        stepf()
+        ctx.sync()
+        if comm:
+            comm.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            stepf()
+        ctx.sync()
+        dt = (time.perf_counter() - t0) / steps
+        if comm:
+            dt = float(comm.allreduce([dt], "max")[0])
+        return dt
+
+    # ---- headline e2e: price + amount up, index + 8 OHLCV columns down ------------------------------------------------
+    cap = core.dollar_bar_index(tr_e, THRESHOLD).m + 1024
+    res_idx = pin.array(np.int64, cap)
+    res = [pin.array(dt_, cap) for dt_ in (np.float64, np.float64, np.float64, np.float64, np.float32, np.float64, np.int64, np.float64)]
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(1)
+    d2h = [0]
+
+    def e2e_step():
+        tr_e.refill(None, h_px, h_qty, None)                    # H2D of the step's inputs (pinned): price, amount
+        ix = core.dollar_bar_index(tr_e, THRESHOLD)
+        _, cidx = ix.download(host_ts=h_ts, out_idx=res_idx, gather=False)   # D2H close indices (pinned)
+        fut = pool.submit(lambda: h_ts[cidx])                     # close_ts = ts[idx] on the host, overlapped with ...
+        cols = core.bar_ohlcv(tr_e, ix, out=tuple(res))           # ... the OHLCV kernel + D2H of the 8 columns (pinned)
+        cts = fut.result()
+        d2h[0] = cts.nbytes + cidx.nbytes + sum(c.nbytes for c in cols)
+        return cols
+
+    dt = wall(e2e_step, args.e2e_steps)
+
+    def phase_ms():     # one extra, untimed step with a sync after every phase: where the end-to-end time goes
+        ctx.sync(); t0 = time.perf_counter()
+        tr_e.refill(None, h_px, h_qty, None); ctx.sync(); t1 = time.perf_counter()
+        ix = core.dollar_bar_index(tr_e, THRESHOLD); ctx.sync(); t2 = time.perf_counter()
+        _, ci_ = ix.download(host_ts=h_ts, out_idx=res_idx, gather=False); t3a = time.perf_counter()
+        h_ts[ci_]; t3 = time.perf_counter()
+        core.bar_ohlcv(tr_e, ix, out=tuple(res)); t4 = time.perf_counter()
+        return {"h2d_price_amount": (t1 - t0) * 1e3, "dollar_index_kernels": (t2 - t1) * 1e3,
+                "index_d2h": (t3a - t2) * 1e3, "host_ts_gather": (t3 - t3a) * 1e3, "ohlcv_kernel_and_d2h": (t4 - t3) * 1e3,
+                "h2d_GBps": 16 * n_e / (t1 - t0) / 1e9}
+    e2e = {"value": world * n_e / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * n_e, "d2h_bytes_per_step": int(d2h[0]),
+           "phase_ms_untimed_extra_step": phase_ms(), "steps": args.e2e_steps,
+           "ticks_per_step_per_gpu": n_e, "ms_per_step": dt * 1e3,
+           "api": "fmk_trades_refill(price, amount) + fmk_dollar_bar_index + fmk_index_download + host ts[idx] (overlapped, "
+                  "one helper thread) + fmk_bar_ohlcv; pinned host input and result buffers; timestamps stay on the host, as in "
+                  "DollarBarKit.build_ohlcv"}
+    pool.shutdown()
+
+    cpu_baseline = None
+    if world == 1 and rank == 0 and not args.no_sub:
+        # ---- config 3 e2e: price, amount, side up (17 B/tick); index + per-bar block + footprint CSR block down -----------
+        F3 = core.F_OHLCV | core.F_MEDIAN | core.F_DIRECTIONAL | core.F_FOOTPRINT
+        vix0 = core.volume_bar_index(tr_e, VOLUME_T)
+        fr0 = core.bar_features_device(tr_e, vix0, F3, price_tick_size=TICK)
+        try:
+            bar_out = pin.array(np.uint8, fr0.bar_bytes + 65536)
+            lvl_out = pin.array(np.uint8, fr0.level_bytes + (1 << 20))
+            del fr0, vix0
+            d3 = [0]
+
+            def e2e3():
+                tr_e.refill(None, h_px, h_qty, h_side)
+                vix = core.volume_bar_index(tr_e, VOLUME_T)
+                fr = core.bar_features_device(tr_e, vix, F3, price_tick_size=TICK)
+                cols = fr.download(bar_out, lvl_out)
+                cts = h_ts[cols["close_idx"]]
+                d3[0] = fr.bar_bytes + fr.level_bytes + cts.nbytes
+            dt3 = wall(e2e3, max(1, min(args.e2e_steps, 3)))
+            sub["config3"]["e2e"] = {"value": n_e / dt3, "unit": UNIT, "ms_per_step": dt3 * 1e3, "h2d_bytes_per_step": 17 * n_e,
+                                     "d2h_bytes_per_step": int(d3[0]), "ticks_per_step": n_e,
+                                     "api": "fmk_trades_refill(price, amount, side) + fmk_volume_bar_index + fmk_bar_features_device + "
+                                            "fmk_frame_download (two copies into pinned blocks) + host ts[idx]"}
+        except MemoryError:
+            sub["config3"]["e2e"] = {"unavailable": "pinned result buffers for the footprint CSR did not fit"}
+
+        # ---- config 4 e2e: ts, price up (16 B/tick); sigma at the events, labels, weights down ------------------------------
+        last_ts = int(h_ts[n_e - 1])
+        d4 = [0]
+
+        def e2e4():
+            tr_e.refill(h_ts, h_px, h_qty, None)                 # amount is not read by this path but the handle carries it
+            r = core.lagged_returns_dev(tr_e, 3600.0, True)
+            sig = core.ewmst_dev(tr_e, r, 3600.0)
+            del r
+            cix = core.cusum_bar_index(tr_e, sig, 5e-4, 2.0)
+            cts, cidx = cix.download()
+            ev, tg = cidx[1:], sig.gather(cidx[1:])
+            keep = np.isfinite(tg) & (cts[1:] + 3600 * 10**9 <= last_ts)
+            ev, tg = ev[keep], tg[keep]
+            lab = core.triple_barrier_dev(tr_e, ev, tg, (2.0, 2.0), 3600.0, 1.0, None, 0.0)
+            w = core.sample_weights_dev(tr_e, ev, lab[1])
+            d4[0] = cts.nbytes + cidx.nbytes + tg.nbytes + sum(x.nbytes for x in lab) + sum(x.nbytes for x in w)
+        dt4 = wall(e2e4, max(1, min(args.e2e_steps, 3)))
+        sub["config4"]["e2e"] = {"value": n_e / dt4, "unit": UNIT, "ms_per_step": dt4 * 1e3, "h2d_bytes_per_step": 24 * n_e,
+                                 "d2h_bytes_per_step": int(d4[0]), "ticks_per_step": n_e,
+                                 "api": "fmk_trades_refill(ts, price, amount) + fmk_lagged_returns_dev + fmk_ewmst_dev + fmk_cusum_bar_index + "
+                                        "fmk_index_download + fmk_buf_gather8 + fmk_triple_barrier + fmk_sample_weights"}
+
+        # ---- CPU baselines on a bounded prefix of the same arrays (the reference's Numba path when baseline/_ref is there) ----
+        ref = Reference()
+        s = int(min(n_e, args.cpu_sample))
+        px, qty = np.array(h_px[:s]), np.array(h_qty[:s])
+        sec, nb = best_of(ref.dollar_ohlcv(px, qty), reps=3)
+        cpu_baseline = cpu_record(ref, sec, s, f"first {s} ticks of the same stream; _dollar_bar_indexer (serial, as the reference runs it) + "
+                                               f"comp_bar_ohlcv (prange over bars), best of 3, warm JIT")
+        s2 = int(min(n_e, args.cpu_sub_sample))
+        cs = cpu_sub_records(ref, np.array(h_ts[:s2]), px[:s2].copy(), qty[:s2].copy(), np.array(h_side[:s2]))
+        for k in ("config3", "config4"):
+            sub[k]["cpu_baseline"] = cs[k]
+        if "time_bars_1min" in sub:
+            sub["time_bars_1min"]["cpu_baseline"] = cs["time_bars_1min"]
+
+        # ---- config 1 + wrapper-level e2e: the pandas-in / pandas-out call a user makes, pageable memory ---------------------
+        import pandas as pd
+        from finmlkit_b200.bar.data_model import TradesData
+        from finmlkit_b200.bar.kit import DollarBarKit, TimeBarKit
+        n1 = min(n_e, 1_000_000)
+        td1 = TradesData(np.array(h_ts[:n1]), np.array(h_px[:n1]), np.array(h_qty[:n1]), side=np.array(h_side[:n1]))
+        sec1, nb1 = best_of(lambda: len(TimeBarKit(td1, pd.Timedelta(minutes=1), ctx=ctx).build_ohlcv()), reps=5)
+        extra["config1"] = {"workload": f"BASELINE configs[0]: {n1} ticks -> TimeBarKit(trades, 1 min).build_ohlcv() (pandas in, pandas out; "
+                                        "upload + kernels + download + frame assembly inside the timed call)",
+                            "ours": {"ticks_per_s": n1 / sec1, "seconds": sec1, "bars": nb1},
+                            "cpu_baseline": cs["config1"].get("wrapper", cs["config1"]["kernels"]),
+                            "cpu_baseline_kernels": cs["config1"]["kernels"], "published": cs["config1"]["published"]}
+        nw = int(min(n_e, args.wrapper_ticks))
+        try:
+            tdw = TradesData(np.array(h_ts[:nw]), np.array(h_px[:nw]), np.array(h_qty[:nw]), side=np.array(h_side[:nw]))
+            secw, nbw = best_of(lambda: len(DollarBarKit(tdw, THRESHOLD, ctx=ctx).build_ohlcv()), reps=2)
+            rec = {"workload": f"DollarBarKit(trades, 1e6).build_ohlcv() on {nw} ticks, pageable pandas columns (bar/kit.py:110-137)",
+                   "ours": {"ticks_per_s": nw / secw, "seconds": secw, "bars": nbw}}
+            del tdw
+            tdr = ref.trades_data(np.array(h_ts[:nw]), np.array(h_px[:nw]), np.array(h_qty[:nw]), np.array(h_side[:nw]))
+            kit = ref.dollar_kit(tdr)
+            if kit is not None:
+                secr, nbr = best_of(kit, reps=2)
+                rec["cpu_baseline"] = cpu_record(ref, secr, nw, f"the reference's DollarBarKit(trades, 1e6).build_ohlcv() on the same {nw} ticks, best of 2")
+                rec["cpu_baseline"]["bars"] = nbr
+            extra["e2e_wrapper"] = rec
+        except MemoryError:
+            extra["e2e_wrapper"] = {"unavailable": "host memory"}
+    pin.close()
+    return e2e, cpu_baseline, extra
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -206,278 +866,23 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--ticks", type=float, default=1e9, help="ticks per GPU (one symbol stream per GPU)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample", type=float, default=1e8, help="ticks of the CPU baseline sample")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample", type=float, default=1e8, help="ticks of the headline CPU baseline sample")
+    ap.add_argument("--cpu-sub-sample", type=float, default=2e7, help="ticks of the config 1/3/4 CPU baseline samples")
+    ap.add_argument("--config5-ticks", type=float, default=5e8)
+    ap.add_argument("--wrapper-ticks", type=float, default=1e8)
+    ap.add_argument("--imbalance-threshold", type=float, default=200.0)
+    ap.add_argument("--sub-steps", type=int, default=5, help="timed steps of the config 3/4/5 sub-records")
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="headline only")
+    ap.add_argument("--no-config5", action="store_true")
     args = ap.parse_args()
-    args.ticks = int(args.ticks)
-    args.cpu_sample = int(args.cpu_sample)
+    for k in ("ticks", "cpu_sample", "cpu_sub_sample", "config5_ticks", "wrapper_ticks"):
+        setattr(args, k, int(getattr(args, k)))
     if args.impl == "reference":
         run_reference(args)
-        return
-
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    from finmlkit_b200 import core
-    dist = torch = None
-    stream = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        tstream = torch.cuda.Stream()
-        torch.cuda.set_stream(tstream)
-        stream = tstream.cuda_stream
-    ctx = core.Context(local, stream=stream)
-    n = args.ticks
-    tr = core.DeviceTrades.synth(n, seed=42 + rank, ctx=ctx)   # one independent symbol per rank
-
-    def barrier():
-        ctx.sync()
-        if dist is not None:
-            torch.cuda.synchronize()
-            dist.barrier()
-
-    gather_bytes = [0]
-    gatherer = [None]
-
-    def gather_frames():
-        """One NCCL gather of the finished bar frame (all OHLCV columns) to rank 0 per step, on a communication stream:
-        the transfer of step k overlaps the kernels of step k+1 (finmlkit_b200.parallel.PipelinedFrameGather)."""
-        ptr, nb, nbytes = ctx.result_cols()
-
-        class _Arr:   # zero-copy view of the library-owned device columns
-            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
-        frame = torch.as_tensor(_Arr(), device=f"cuda:{local}")
-        if gatherer[0] is None:
-            from finmlkit_b200.parallel import PipelinedFrameGather
-            gatherer[0] = PipelinedFrameGather(frame, dst=0)
-        gatherer[0].submit(frame)
-
-    def finish_gathers():
-        if gatherer[0] is None:
-            return
-        frames = gatherer[0].finish()          # stream-ordered wait: the timer stopped next covers every gather
-        if frames is not None:
-            gather_bytes[0] = int(sum(f.numel() for f in frames))
-
-    nbars = [0]
-
-    def step():
-        ix = core.dollar_bar_index(tr, THRESHOLD)
-        ctx.check(ctx._L.fmk_bar_ohlcv_device(ctx.h, tr.h, ix.h, 1))
-        nbars[0] = ix.m - 1
-        if dist is not None:
-            gather_frames()
-
-    for _ in range(args.warmup):
-        step()
-    finish_gathers()
-    barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
-    l0 = ctx.launch_count()
-    ctx.prof_enable(True)
-    ctx.timer_start()
-    for _ in range(args.steps):
-        step()
-    finish_gathers()
-    ms = ctx.timer_stop()
-    barrier()
-    ctx.prof_enable(False)
-    prof = ctx.prof_report()
-    launches = ctx.launch_count() - l0
-    clk = clocks.stop()
-    stats = ctx.index_stats()
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
-    value = world * n / (ms_per_step * 1e-3)
-
-    # ---- secondary: the north_star's single-GPU time-bar build (1-minute bars + OHLCV incl. median), same stream ------
-    time_bars = None
-    if world == 1:
-        def tstep(with_median):
-            tix = core.time_bar_index(tr, 60.0)
-            ctx.check(ctx._L.fmk_bar_ohlcv_device(ctx.h, tr.h, tix.h, with_median))
-            return tix.m - 1
-        time_bars = {}
-        for with_median in (1, 0):
-            tstep(with_median)
-            ctx.sync()
-            ctx.prof_enable(True)
-            ctx.timer_start()
-            for _ in range(args.steps):
-                nb_t = tstep(with_median)
-            tms = ctx.timer_stop() / args.steps
-            ctx.prof_enable(False)
-            pr = ctx.prof_report()
-            kname, (kc, kms) = max(pr.items(), key=lambda kv: kv[1][1])
-            time_bars["ohlcv+median" if with_median else "ohlcv"] = {
-                "ticks_per_s": n / (tms * 1e-3), "ms_per_step": tms, "bars": nb_t, "dominant_kernel": kname,
-                "kernel_GBps_on_16B_per_tick": 16 * n / (kms / kc * 1e-3) / 1e9,
-                "frac_of_peak": 16 * n / (kms / kc * 1e-3) / 1e9 / measured_peak()[0]}
-
-    # ---- roofline of the dominant kernel (CUDA events around every launch of the timed region) ----------------------
-    peak, peak_src = measured_peak()
-    roofline = None
-    if prof:
-        dom = max(prof.items(), key=lambda kv: kv[1][1])
-        name, (cnt, tot_ms) = dom
-        per_launch_ms = tot_ms / cnt
-        algo = ALGO_BYTES_PER_TICK.get(name)
-        if algo:
-            achieved = algo * n / (per_launch_ms * 1e-3) / 1e9
-            traffic = ncu_traffic(name)
-            roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": traffic, "algorithmic_bytes_per_launch": algo * n, "launch_ms": per_launch_ms,
-                        "share_of_step": tot_ms / ms if dist is None else None, "peak_source": peak_src,
-                        "all_kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
-
-    # ---- end to end through the host-buffer C ABI --------------------------------------------------------------------
-    e2e = None
-    cpu_baseline = None
-    if not args.no_e2e:
-        import ctypes as C
-        L = ctx._L
-        n_e = n
-        try:
-            import psutil
-            avail = psutil.virtual_memory().available
-            while 24 * n_e > 0.6 * avail / max(world, 1) and n_e > 1_000_000:
-                n_e //= 2
-        except Exception:
-            pass
-        def agree_min(x):
-            """Same value on every rank (min), so that the ranks size / skip the end-to-end leg together."""
-            if dist is None:
-                return int(x)
-            t = torch.tensor([int(x)], dtype=torch.int64, device=f"cuda:{local}")
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            return int(t.item())
-
-        n_e = agree_min(n_e)
-        hp = []
-        for _attempt in range(5):          # pinned host memory is per-node: halve the sample until every rank gets its buffers
-            ok = 1
-            for _ in range(3):
-                p = C.c_void_p()
-                if L.fmk_host_alloc(C.byref(p), 8 * n_e) != 0:
-                    ok = 0
-                    break
-                hp.append(p)
-            if agree_min(ok):
-                break
-            for p in hp:
-                L.fmk_host_free(p)
-            hp = []
-            n_e //= 2
-        if not hp:
-            raise RuntimeError("pinned allocation failed on every attempt")
-        h_ts = np.ctypeslib.as_array(C.cast(hp[0], C.POINTER(C.c_int64)), shape=(n_e,))
-        h_px = np.ctypeslib.as_array(C.cast(hp[1], C.POINTER(C.c_double)), shape=(n_e,))
-        h_qty = np.ctypeslib.as_array(C.cast(hp[2], C.POINTER(C.c_double)), shape=(n_e,))
-        if n_e == n:
-            tr.download(out=(h_ts, h_px, h_qty, None))
-            tr_e = tr
-        else:
-            tr_e = core.DeviceTrades.synth(n_e, seed=42 + rank, ctx=ctx)
-            tr_e.download(out=(h_ts, h_px, h_qty, None))
-        d2h = [0]
-        # result buffers a caller of repeated builds would keep: pinned, sized from a first (untimed) index build
-        cap = core.dollar_bar_index(tr_e, THRESHOLD).m + 1024
-        res_ptrs, res = [], []
-        for dt_, isz in ((np.int64, 8), (np.float64, 8), (np.float64, 8), (np.float64, 8), (np.float64, 8), (np.float32, 4),
-                         (np.float64, 8), (np.int64, 8), (np.float64, 8)):
-            p = C.c_void_p()
-            if L.fmk_host_alloc(C.byref(p), isz * cap) != 0:
-                raise RuntimeError("pinned allocation failed")
-            res_ptrs.append(p)
-            ctype = {np.int64: C.c_int64, np.float64: C.c_double, np.float32: C.c_float}[dt_]
-            res.append(np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=(cap,)))
-        from concurrent.futures import ThreadPoolExecutor
-        pool = ThreadPoolExecutor(1)
-
-        def e2e_step():
-            tr_e.refill(None, h_px, h_qty, None)                    # H2D of the step's inputs (pinned): price, amount
-            ix = core.dollar_bar_index(tr_e, THRESHOLD)
-            _, cidx = ix.download(host_ts=h_ts, out_idx=res[0], gather=False)   # D2H close indices (pinned)
-            fut = pool.submit(lambda: h_ts[cidx])                     # close_ts = ts[idx] on the host, overlapped with ...
-            cols = core.bar_ohlcv(tr_e, ix, out=tuple(res[1:]))       # ... the OHLCV kernel + D2H of the 8 columns (pinned)
-            cts = fut.result()
-            d2h[0] = cts.nbytes + cidx.nbytes + sum(c.nbytes for c in cols)
-            return cols
-
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        ctx.sync()
-        dt = (time.perf_counter() - t0) / args.e2e_steps
-        if dist is not None:
-            t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        # one extra, untimed step with a sync after every phase: where the end-to-end time goes (PCIe vs kernels vs host)
-        def phase_ms():
-            ctx.sync(); t0 = time.perf_counter()
-            tr_e.refill(None, h_px, h_qty, None); ctx.sync(); t1 = time.perf_counter()
-            ix = core.dollar_bar_index(tr_e, THRESHOLD); ctx.sync(); t2 = time.perf_counter()
-            _, ci_ = ix.download(host_ts=h_ts, out_idx=res[0], gather=False); t3a = time.perf_counter()
-            h_ts[ci_]; t3 = time.perf_counter()
-            core.bar_ohlcv(tr_e, ix, out=tuple(res[1:])); t4 = time.perf_counter()
-            return {"h2d_price_amount": (t1 - t0) * 1e3, "dollar_index_kernels": (t2 - t1) * 1e3,
-                    "index_d2h": (t3a - t2) * 1e3, "host_ts_gather": (t3 - t3a) * 1e3, "ohlcv_kernel_and_d2h": (t4 - t3) * 1e3,
-                    "h2d_GBps": 16 * n_e / (t1 - t0) / 1e9}
-        breakdown = phase_ms()
-        e2e = {"value": world * n_e / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * n_e, "d2h_bytes_per_step": int(d2h[0]),
-               "phase_ms_untimed_extra_step": breakdown,
-               "ticks_per_step_per_gpu": n_e, "ms_per_step": dt * 1e3,
-               "api": "fmk_trades_refill(price, amount) + fmk_dollar_bar_index + fmk_index_download + host ts[idx] (overlapped, "
-                      "one helper thread) + fmk_bar_ohlcv; pinned host input and result buffers; timestamps stay on the host, as in "
-                      "DollarBarKit.build_ohlcv"}
-
-        # ---- CPU baseline beside it (rank 0, N=1 only): oracle port on a bounded sample of the same arrays ----------
-        if world == 1 and rank == 0:
-            import oracle
-            try:
-                oracle.set_num_threads(len(os.sched_getaffinity(0)))
-            except Exception:
-                pass
-            s = int(min(n_e, args.cpu_sample))
-            px, qty = np.array(h_px[:s]), np.array(h_qty[:s])
-            oracle.comp_bar_ohlcv(px[:1000], qty[:1000], np.array([0, 999], np.int64))
-            best = 1e30
-            for _ in range(2):
-                t0 = time.perf_counter()
-                idx = oracle.dollar_bar_indexer(px, qty, THRESHOLD)
-                oracle.comp_bar_ohlcv(px, qty, idx)
-                best = min(best, time.perf_counter() - t0)
-            cpu_baseline = {"value": s / best, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
-                            "sample": f"first {s} ticks of the same stream; dollar indexer serial (as in the reference) + "
-                                      f"comp_bar_ohlcv on {oracle.num_threads()} OpenMP threads, best of 2"}
-        pool.shutdown()
-        for p in hp + res_ptrs:
-            L.fmk_host_free(p)
-
-    if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic",
-                "config": {"workload": f"BASELINE configs[1]: {n} synthetic ticks per GPU -> dollar bars ($1e6, bit-exact boundaries) "
-                                       "+ OHLCV/VWAP/trades/median, fp64; one symbol stream per GPU"
-                                       + (", one NCCL gather of the bar frames to rank 0 per step on a communication stream (overlaps the next step)" if world > 1 else ""),
-                           "ticks_per_gpu": n, "bars_per_gpu": nbars[0], "threshold": THRESHOLD,
-                           "l2": "inputs (16-24 GB/step) exceed the 126 MB L2; no flush needed" if n * 16 > 4e8 else "inputs fit L2: timing is warm-L2",
-                           "parallelism": f"symbols x{world}", "index_stats": stats,
-                           "gather_bytes_per_step": gather_bytes[0]},
-                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline, "time_bars_1min": time_bars}
-        emit(line)
-    if dist is not None:
-        dist.destroy_process_group()
+    else:
+        run_ours(args)
 
 
 if __name__ == "__main__":

@@ -32,6 +32,7 @@ SIGNATURES = {
     "fmk_host_alloc": (INT, [C.POINTER(P), I64]),
     "fmk_host_free": (None, [P]),
     "fmk_trades_upload": (INT, [P, P, P, P, P, I64, C.POINTER(P)]),
+    "fmk_trades_upload_f32amt": (INT, [P, P, P, P, P, I64, C.POINTER(P)]),
     "fmk_trades_synth": (INT, [P, I64, C.c_uint64, C.POINTER(P)]),
     "fmk_trades_refill": (INT, [P, P, P, P, P, P, I64]),
     "fmk_trades_download": (INT, [P, P, P, P, P, P]),
@@ -43,6 +44,7 @@ SIGNATURES = {
     "fmk_buf_bytes": (I64, [P]),
     "fmk_buf_devptr": (P, [P]),
     "fmk_buf_free": (None, [P, P]),
+    "fmk_buf_gather8": (INT, [P, P, P, I64, P]),
     "fmk_time_bar_index": (INT, [P, P, F64, C.POINTER(P)]),
     "fmk_tick_bar_index": (INT, [P, P, I64, C.POINTER(P)]),
     "fmk_volume_bar_index": (INT, [P, P, F64, C.POINTER(P)]),
@@ -77,6 +79,23 @@ SIGNATURES = {
     "fmk_merge_split_trades": (INT, [P, P, P, P, P, I64, P, P, P, P, C.POINTER(I64)]),
     "fmk_volume_profile_rolling": (INT, [P, P, P, P, P, I64, P, P, P, F64, I64, F64, F64, P, P, P, P]),
     "fmk_volume_profile_rolling_fp": (INT, [P, P, P, P, P, F64, I64, F64, F64, P, P, P, P]),
+    "fmk_bar_features_device": (INT, [P, P, P, INT, P, I64, F64, F64, F64, C.POINTER(P)]),
+    "fmk_frame_info": (INT, [P, C.POINTER(I64), C.POINTER(I64), C.POINTER(I64), C.POINTER(I64), P]),
+    "fmk_frame_devptrs": (INT, [P, C.POINTER(P), C.POINTER(P)]),
+    "fmk_frame_download": (INT, [P, P, P, P]),
+    "fmk_frame_free": (None, [P, P]),
+    "fmk_comm_unique_id": (INT, [P]),
+    "fmk_comm_init": (INT, [P, P, INT, INT, INT, C.POINTER(P)]),
+    "fmk_comm_destroy": (None, [P]),
+    "fmk_comm_rank": (INT, [P]),
+    "fmk_comm_world": (INT, [P]),
+    "fmk_comm_nccl_version": (INT, []),
+    "fmk_comm_barrier": (INT, [P]),
+    "fmk_comm_allreduce_f64": (INT, [P, P, INT, INT]),
+    "fmk_comm_gather_submit": (INT, [P, P, P, INT, INT]),
+    "fmk_comm_gather_finish": (INT, [P]),
+    "fmk_comm_gather_result": (INT, [P, INT, C.POINTER(P), C.POINTER(I64)]),
+    "fmk_comm_gather_download": (INT, [P, INT, P, I64]),
     "fmk_triple_barrier": (INT, [P, P, P, P, I64, I64, F64, F64, F64, F64, P, I64, F64, P, P, P, P]),
 }
 

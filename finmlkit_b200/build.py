@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libfmk.so")
-SOURCES = ["api.cu", "reduce.cu", "series.cu", "index_dollar.cu", "index_volume.cu", "index_cusum.cu", "barlevel.cu", "weights.cu", "ingest.cu", "volprofile.cu"]
+SOURCES = ["api.cu", "reduce.cu", "series.cu", "index_dollar.cu", "index_volume.cu", "index_cusum.cu", "barlevel.cu", "weights.cu", "ingest.cu", "volprofile.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
               "-prec-div=true", "-prec-sqrt=true", "--extended-lambda", "-diag-suppress", "20054", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
               "-Xcompiler", "-Wno-unused-function"]
@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc, "-shared", "-o", SO, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    subprocess.check_call([nvcc, "-shared", "-o", SO, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
     return SO
 
 

@@ -122,6 +122,14 @@ class DeviceBuf:
         self.ctx.check(self.ctx._L.fmk_buf_download(self.ctx.h, self.h, _ptr(out), out.nbytes))
         return out
 
+    def gather(self, idx, dtype=np.float64):
+        """src[idx] for host indices into a device array of 8-byte elements, without downloading the array."""
+        ii = _c(idx, np.int64)
+        out = np.empty(len(ii), dtype)
+        assert out.itemsize == 8
+        self.ctx.check(self.ctx._L.fmk_buf_gather8(self.ctx.h, self.h, _ptr(ii), len(ii), _ptr(out)))
+        return out
+
     @property
     def devptr(self):
         return self.ctx._L.fmk_buf_devptr(self.h)
@@ -142,13 +150,17 @@ class DeviceTrades:
     @classmethod
     def upload(cls, ts, price, amount, side=None, ctx: Context = None):
         ctx = ctx or default_context()
-        price, amount = _c(price, np.float64), _c(amount, np.float64)
+        # float32 amounts (TradesData after the reference's split-trade merge, data_model.py:326-344) cross PCIe as 4 B/tick
+        # and are widened exactly on the device; anything else is float64
+        f32 = isinstance(amount, np.ndarray) and amount.dtype == np.float32
+        price, amount = _c(price, np.float64), _c(amount, np.float32 if f32 else np.float64)
         ts = _c(ts, np.int64) if ts is not None else None      # None: the host keeps the timestamps (see fmk.h)
         if len(price) != len(amount) or (ts is not None and len(ts) != len(price)):
             raise ValueError("Prices and volumes arrays must have the same length.")
         sd = _c(side, np.int8) if side is not None else None
         h = C.c_void_p()
-        ctx.check(ctx._L.fmk_trades_upload(ctx.h, _ptr(ts), _ptr(price), _ptr(amount), _ptr(sd), len(price), C.byref(h)))
+        up = ctx._L.fmk_trades_upload_f32amt if f32 else ctx._L.fmk_trades_upload
+        ctx.check(up(ctx.h, _ptr(ts), _ptr(price), _ptr(amount), _ptr(sd), len(price), C.byref(h)))
         ctx.sync()
         obj = cls(ctx, h, len(price))
         obj.has_ts = ts is not None
@@ -315,6 +327,24 @@ def ewmst_series(timestamps, y, half_life, sigma_floor=1e-12, ctx: Context = Non
     return out
 
 
+def lagged_returns_dev(trades: DeviceTrades, return_window_sec, is_log) -> DeviceBuf:
+    """comp_lagged_returns on the device-resident ts / price columns; the result stays on the device."""
+    if return_window_sec <= 0:
+        raise ValueError("The return window must be greater than zero.")
+    h = C.c_void_p()
+    ctx = trades.ctx
+    ctx.check(ctx._L.fmk_lagged_returns_dev(ctx.h, trades.h, float(return_window_sec), int(bool(is_log)), C.byref(h)))
+    return DeviceBuf(ctx, h)
+
+
+def ewmst_dev(trades: DeviceTrades, y: DeviceBuf, half_life, sigma_floor=1e-12) -> DeviceBuf:
+    """ewmst of a device-resident series on the trades' timestamps; the result stays on the device."""
+    h = C.c_void_p()
+    ctx = trades.ctx
+    ctx.check(ctx._L.fmk_ewmst_dev(ctx.h, trades.h, y.h, float(half_life), float(sigma_floor), C.byref(h)))
+    return DeviceBuf(ctx, h)
+
+
 def triple_barrier_dev(trades: DeviceTrades, event_idxs, targets, horizontal_barriers, vertical_barrier, min_close_time_sec, side, min_ret):
     ev, tg = _c(event_idxs, np.int64), _c(targets, np.float64)
     sd = _c(side, np.int8) if side is not None else None
@@ -446,3 +476,88 @@ def volume_profile_rolling_csr(ts, highs, lows, level_offsets, price_levels, buy
                                                 float(window_size_sec), int(n_bins) if n_bins else 0, float(price_tick),
                                                 float(va_pct), _ptr(poc), _ptr(hva), _ptr(lva), _ptr(pct)))
     return poc, hva, lva, pct
+
+
+# ---- device-resident bar frame (fmk_bar_features_device) ---------------------------------------------------------------
+F_OHLCV, F_MEDIAN, F_DIRECTIONAL, F_TRADE_SIZE, F_FOOTPRINT = 1, 2, 4, 8, 16
+F_ALL = F_OHLCV | F_MEDIAN | F_DIRECTIONAL | F_TRADE_SIZE | F_FOOTPRINT
+
+# column id -> (name, dtype, block, extra elements); order = the fmk_col enum of include/fmk.h
+FRAME_COLS = [
+    ("close_ts", np.int64, "bar", 0), ("close_idx", np.int64, "bar", 0),
+    ("open", np.float64, "bar", 0), ("high", np.float64, "bar", 0), ("low", np.float64, "bar", 0), ("close", np.float64, "bar", 0),
+    ("vwap", np.float64, "bar", 0), ("median_trade_size", np.float64, "bar", 0), ("trades", np.int64, "bar", 0),
+    ("volume", np.float32, "bar", 0),
+    ("ticks_buy", np.int64, "bar", 0), ("ticks_sell", np.int64, "bar", 0), ("cum_ticks_min", np.int64, "bar", 0),
+    ("cum_ticks_max", np.int64, "bar", 0),
+    ("volume_buy", np.float32, "bar", 0), ("volume_sell", np.float32, "bar", 0), ("dollars_buy", np.float32, "bar", 0),
+    ("dollars_sell", np.float32, "bar", 0), ("mean_spread", np.float32, "bar", 0), ("max_spread", np.float32, "bar", 0),
+    ("cum_volume_min", np.float32, "bar", 0), ("cum_volume_max", np.float32, "bar", 0), ("cum_dollars_min", np.float32, "bar", 0),
+    ("cum_dollars_max", np.float32, "bar", 0),
+    ("mean_size_rel", np.float32, "bar", 0), ("size_95_rel", np.float32, "bar", 0), ("pct_block", np.float32, "bar", 0),
+    ("size_gini", np.float32, "bar", 0),
+    ("fp_level_offsets", np.int64, "bar", 1), ("fp_vp_skew", np.float64, "bar", 0), ("fp_vp_gini", np.float64, "bar", 0),
+    ("fp_cot", np.int32, "bar", 0), ("fp_buy_imb_sum", np.uint16, "bar", 0), ("fp_sell_imb_sum", np.uint16, "bar", 0),
+    ("fp_run_signed", np.int16, "bar", 0),
+    ("fp_price_levels", np.int32, "level", 0), ("fp_buy_vol", np.float32, "level", 0), ("fp_sell_vol", np.float32, "level", 0),
+    ("fp_buy_ticks", np.int32, "level", 0), ("fp_sell_ticks", np.int32, "level", 0), ("fp_buy_imb", np.bool_, "level", 0),
+    ("fp_sell_imb", np.bool_, "level", 0),
+]
+
+
+def frame_views(bar_block: np.ndarray, level_block, n_bars, n_levels, col_offsets):
+    """{column name: NumPy view} into host copies of a frame's two blocks (uint8 arrays)."""
+    out = {}
+    for k, (name, dt, blk, extra) in enumerate(FRAME_COLS):
+        off = int(col_offsets[k])
+        if off < 0:
+            continue
+        src, cnt = (bar_block, n_bars + extra) if blk == "bar" else (level_block, n_levels)
+        if src is None:
+            continue
+        out[name] = np.frombuffer(src, dtype=dt, count=cnt, offset=off)
+    return out
+
+
+class DeviceFrame:
+    """Every per-bar output of one index on the device (fmk_frame): two blocks, described by ``col_offsets``."""
+
+    def __init__(self, ctx: Context, h):
+        self.ctx, self.h = ctx, h
+        nb, nl, bb, lb = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        self.col_offsets = np.zeros(len(FRAME_COLS), np.int64)
+        ctx._L.fmk_frame_info(h, C.byref(nb), C.byref(nl), C.byref(bb), C.byref(lb), _ptr(self.col_offsets))
+        self.n_bars, self.n_levels, self.bar_bytes, self.level_bytes = int(nb.value), int(nl.value), int(bb.value), int(lb.value)
+        self._fin = weakref.finalize(self, ctx._L.fmk_frame_free, ctx.h, h)
+
+    def devptrs(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self.ctx._L.fmk_frame_devptrs(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def segments(self):
+        """[(device pointer, bytes)] of the non-empty blocks -- what fmk_comm_gather_submit takes."""
+        a, b = self.devptrs()
+        return [(p, n) for p, n in ((a, self.bar_bytes), (b, self.level_bytes)) if n > 0]
+
+    def download(self, bar_out=None, level_out=None):
+        """{column: array}; ``bar_out`` / ``level_out``: optional preallocated uint8 buffers (e.g. pinned)."""
+        bar = np.empty(self.bar_bytes, np.uint8) if bar_out is None else bar_out[:self.bar_bytes]
+        lvl = None
+        if self.level_bytes > 0:
+            lvl = np.empty(self.level_bytes, np.uint8) if level_out is None else level_out[:self.level_bytes]
+        self.ctx.check(self.ctx._L.fmk_frame_download(self.ctx.h, self.h, _ptr(bar), _ptr(lvl)))
+        return frame_views(bar, lvl, self.n_bars, self.n_levels, self.col_offsets)
+
+    def free(self):
+        self._fin()
+
+
+def bar_features_device(trades: DeviceTrades, index: DeviceIndex, flags=F_OHLCV | F_MEDIAN, theta=None, theta_mult=5.0,
+                        price_tick_size=0.0, imbalance_factor=3.0) -> DeviceFrame:
+    th = _c(theta, np.float64) if theta is not None else None
+    h = C.c_void_p()
+    ctx = trades.ctx
+    ctx.check(ctx._L.fmk_bar_features_device(ctx.h, trades.h, index.h, int(flags), _ptr(th), len(th) if th is not None else 0,
+                                             float(theta_mult), float(price_tick_size), float(imbalance_factor), C.byref(h)))
+    return DeviceFrame(ctx, h)

@@ -49,6 +49,8 @@ static int ctx_create(int device, void *ext_stream, int use_ext, fmk_ctx **out) 
 
 void fmk_ctx_destroy(fmk_ctx *ctx) {
     if (!ctx) return;
+    int prev_dev = -1;               // run from a finalizer at an arbitrary time: leave the caller's current device alone
+    cudaGetDevice(&prev_dev);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->res_cols) cudaFree(ctx->res_cols);
@@ -61,21 +63,25 @@ void fmk_ctx_destroy(fmk_ctx *ctx) {
     delete ctx->ev_pool;
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
 }
 
 const char *fmk_last_error(fmk_ctx *ctx) { return ctx ? ctx->err : "no context (CUDA device missing?)"; }
 
 int fmk_ctx_sync(fmk_ctx *ctx) {
+    FMK_ENTER(ctx);
     FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FMK_OK;
 }
 
 int fmk_timer_start(fmk_ctx *ctx) {
+    FMK_ENTER(ctx);
     FMK_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     return FMK_OK;
 }
 
 int fmk_timer_stop(fmk_ctx *ctx, float *ms_out) {
+    FMK_ENTER(ctx);
     FMK_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     FMK_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
     FMK_CUDA(ctx, cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
@@ -85,6 +91,7 @@ int fmk_timer_stop(fmk_ctx *ctx, float *ms_out) {
 int64_t fmk_launch_count(fmk_ctx *ctx) { return ctx->launches; }
 
 int fmk_prof_enable(fmk_ctx *ctx, int on) {
+    FMK_ENTER(ctx);
     ctx->prof_on = on;
     return FMK_OK;
 }
@@ -92,6 +99,7 @@ int fmk_prof_enable(fmk_ctx *ctx, int on) {
 // Drains the recorded launches: writes up to cap rows of (name, launches, total ms); returns the number of distinct
 // kernels.  names_out receives cap * 64 bytes of NUL-terminated names.
 int fmk_prof_report(fmk_ctx *ctx, char *names_out, int64_t *counts_out, float *ms_out, int cap) {
+    FMK_ENTER(ctx);
     cudaStreamSynchronize(ctx->stream);
     int nk = 0;
     for (auto &r : *ctx->prof) {
@@ -118,11 +126,13 @@ int fmk_prof_report(fmk_ctx *ctx, char *names_out, int64_t *counts_out, float *m
 // device pointer / bar count of the columns written by fmk_bar_ohlcv_device (layout: 6 x f64[nb] open, high, low,
 // close, vwap, median ; i64[nb] trades ; f32[nb] volume)
 int fmk_result_cols(fmk_ctx *ctx, void **ptr, int64_t *n_bars, int64_t *bytes) {
+    FMK_ENTER(ctx);
     *ptr = ctx->res_cols; *n_bars = ctx->res_nb; *bytes = ctx->res_nb * (6 * 8 + 8 + 4);
     return FMK_OK;
 }
 
 int fmk_index_stats(fmk_ctx *ctx, int64_t *s) {
+    FMK_ENTER(ctx);
     s[0] = ctx->stats[0]; s[1] = ctx->stats[1]; s[2] = ctx->stats[2];
     return FMK_OK;
 }
@@ -140,6 +150,7 @@ __global__ void k_flush(uint4 *buf, int64_t n16, unsigned v) {
 }
 
 extern "C" int fmk_flush_l2(fmk_ctx *ctx) {
+    FMK_ENTER(ctx);
     const int64_t bytes = 512ll << 20;  // 4x the 126 MB L2
     if (!ctx->flush_buf) {
         FMK_CUDA(ctx, cudaMalloc(&ctx->flush_buf, (size_t)bytes));
@@ -156,6 +167,7 @@ extern "C" int fmk_flush_l2(fmk_ctx *ctx) {
 extern "C" {
 
 int fmk_buf_alloc(fmk_ctx *ctx, int64_t bytes, fmk_buf **out) {
+    FMK_ENTER(ctx);
     *out = nullptr;
     fmk_buf *b = new (std::nothrow) fmk_buf();
     if (!b) return FMK_ERR_ALLOC;
@@ -169,12 +181,14 @@ int fmk_buf_alloc(fmk_ctx *ctx, int64_t bytes, fmk_buf **out) {
 }
 
 int fmk_buf_upload(fmk_ctx *ctx, const void *host, int64_t bytes, fmk_buf **out) {
+    FMK_ENTER(ctx);
     FMK_TRY(fmk_buf_alloc(ctx, bytes, out));
     if (bytes > 0) FMK_CUDA(ctx, cudaMemcpyAsync((*out)->ptr, host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
     return FMK_OK;
 }
 
 int fmk_buf_download(fmk_ctx *ctx, const fmk_buf *b, void *host, int64_t bytes) {
+    FMK_ENTER(ctx);
     if (bytes > b->bytes) return fmk_fail(ctx, FMK_ERR_CAPACITY, "download larger than buffer");
     if (bytes > 0) FMK_CUDA(ctx, cudaMemcpyAsync(host, b->ptr, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
     FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -184,6 +198,7 @@ int fmk_buf_download(fmk_ctx *ctx, const fmk_buf *b, void *host, int64_t bytes) 
 int64_t fmk_buf_bytes(const fmk_buf *b) { return b->bytes; }
 void *fmk_buf_devptr(const fmk_buf *b) { return b->ptr; }
 void fmk_buf_free(fmk_ctx *ctx, fmk_buf *b) {
+    FMK_ENTER(ctx);
     if (!b) return;
     fmk_dfree(ctx, b->ptr);
     delete b;
@@ -207,6 +222,7 @@ static int trades_alloc(fmk_ctx *ctx, int64_t n, int with_ts, int with_side, fmk
 
 int fmk_trades_refill(fmk_ctx *ctx, fmk_trades *t, const int64_t *ts, const double *price, const double *amount,
                       const int8_t *side, int64_t n) {
+    FMK_ENTER(ctx);
     if (n != t->n) return fmk_fail(ctx, FMK_ERR_ARG, "refill length differs from handle length");
     if (n == 0) return FMK_OK;
     if (ts && t->ts) FMK_CUDA(ctx, cudaMemcpyAsync(t->ts, ts, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -219,6 +235,7 @@ int fmk_trades_refill(fmk_ctx *ctx, fmk_trades *t, const int64_t *ts, const doub
 
 int fmk_trades_upload(fmk_ctx *ctx, const int64_t *ts, const double *price, const double *amount, const int8_t *side,
                       int64_t n, fmk_trades **out) {
+    FMK_ENTER(ctx);
     if (n < 0) return fmk_fail(ctx, FMK_ERR_ARG, "negative length");
     FMK_TRY(trades_alloc(ctx, n, ts != nullptr, side != nullptr, out));
     int rc = fmk_trades_refill(ctx, *out, ts, price, amount, side, n);
@@ -229,6 +246,7 @@ int fmk_trades_upload(fmk_ctx *ctx, const int64_t *ts, const double *price, cons
 }
 
 int fmk_trades_download(fmk_ctx *ctx, const fmk_trades *t, int64_t *ts, double *price, double *amount, int8_t *side) {
+    FMK_ENTER(ctx);
     const size_t n = (size_t)t->n;
     if (ts && t->ts) FMK_CUDA(ctx, cudaMemcpyAsync(ts, t->ts, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (price) FMK_CUDA(ctx, cudaMemcpyAsync(price, t->price, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -238,9 +256,67 @@ int fmk_trades_download(fmk_ctx *ctx, const fmk_trades *t, int64_t *ts, double *
     return FMK_OK;
 }
 
+}  // extern "C"
+
+// float32 amounts (what the reference's split-trade merge yields, bar/data_model.py:326-344) travel over PCIe as 4 B/tick
+// and are widened on the device: float -> double is exact, so every kernel sees the value Numba's float64 arithmetic sees.
+__global__ void k_widen_f32(const float *__restrict__ in, int64_t n, double *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (double)in[i];
+}
+
+// out[k] = src[idx[k]] for 8-byte elements (e.g. CUSUMBarKit.get_sigma, bar/kit.py:176-181: sigma[bar_close_indices])
+__global__ void k_gather8(const unsigned long long *__restrict__ src, const int64_t *__restrict__ idx, int64_t m, int64_t n,
+                          unsigned long long *__restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    int64_t j = idx[k];
+    if (j < 0) j += n;
+    out[k] = (j >= 0 && j < n) ? src[j] : 0ull;
+}
+
+extern "C" {
+
+int fmk_trades_upload_f32amt(fmk_ctx *ctx, const int64_t *ts, const double *price, const float *amount, const int8_t *side,
+                             int64_t n, fmk_trades **out) {
+    FMK_ENTER(ctx);
+    if (n < 0) return fmk_fail(ctx, FMK_ERR_ARG, "negative length");
+    FMK_TRY(trades_alloc(ctx, n, ts != nullptr, side != nullptr, out));
+    fmk_trades *t = *out;
+    auto body = [&]() -> int {
+        if (n == 0) return FMK_OK;
+        Scratch<float> f(ctx);
+        FMK_TRY(f.alloc(n));
+        if (ts) FMK_CUDA(ctx, cudaMemcpyAsync(t->ts, ts, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        FMK_CUDA(ctx, cudaMemcpyAsync(t->price, price, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        FMK_CUDA(ctx, cudaMemcpyAsync(f.p, amount, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (side) FMK_CUDA(ctx, cudaMemcpyAsync(t->side, side, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        FMK_LAUNCH(ctx, k_widen_f32, ctx->sm_count * 8, 256, 0, (const float *)f.p, n, t->amount);
+        return FMK_OK;
+    };
+    const int rc = body();
+    if (rc) { fmk_trades_free(ctx, t); *out = nullptr; }
+    return rc;
+}
+
+int fmk_buf_gather8(fmk_ctx *ctx, const fmk_buf *src, const int64_t *idx, int64_t m, void *out) {
+    FMK_ENTER(ctx);
+    if (m <= 0) return FMK_OK;
+    Scratch<int64_t> di(ctx);
+    Scratch<unsigned long long> d(ctx);
+    FMK_TRY(di.alloc(m)); FMK_TRY(d.alloc(m));
+    FMK_CUDA(ctx, cudaMemcpyAsync(di.p, idx, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FMK_LAUNCH(ctx, k_gather8, (unsigned)cdiv(m, 256), 256, 0, (const unsigned long long *)src->ptr, (const int64_t *)di.p, m,
+               src->bytes / 8, d.p);
+    FMK_CUDA(ctx, cudaMemcpyAsync(out, d.p, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMK_OK;
+}
+
 int64_t fmk_trades_size(const fmk_trades *t) { return t->n; }
 
 void fmk_trades_free(fmk_ctx *ctx, fmk_trades *t) {
+    FMK_ENTER(ctx);
     if (!t) return;
     fmk_dfree(ctx, t->ts);
     fmk_dfree(ctx, t->price);
@@ -253,6 +329,7 @@ void fmk_trades_free(fmk_ctx *ctx, fmk_trades *t) {
 int64_t fmk_index_size(const fmk_index *ix) { return ix->m; }
 
 int fmk_index_download(fmk_ctx *ctx, const fmk_index *ix, int64_t *close_ts, int64_t *close_idx) {
+    FMK_ENTER(ctx);
     if (close_ts && ix->close_ts)
         FMK_CUDA(ctx, cudaMemcpyAsync(close_ts, ix->close_ts, (size_t)ix->m * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (close_idx)
@@ -262,6 +339,7 @@ int fmk_index_download(fmk_ctx *ctx, const fmk_index *ix, int64_t *close_ts, int
 }
 
 void fmk_index_free(fmk_ctx *ctx, fmk_index *ix) {
+    FMK_ENTER(ctx);
     if (!ix) return;
     fmk_dfree(ctx, ix->close_ts);
     fmk_dfree(ctx, ix->close_idx);
@@ -281,6 +359,7 @@ __global__ void k_gather_ts(const int64_t *ts, const int64_t *ci, int64_t m, int
 }
 
 int fmk_gather_close_ts(fmk_ctx *ctx, const fmk_trades *t, fmk_index *ix) {
+    FMK_ENTER(ctx);
     if (!t->ts) return FMK_OK;   // timestamps were not uploaded: the host gathers ts[close_idx] itself
     if (!ix->close_ts) FMK_TRY(fmk_dalloc(ctx, &ix->close_ts, ix->m));
     if (ix->m > 0)
@@ -289,6 +368,7 @@ int fmk_gather_close_ts(fmk_ctx *ctx, const fmk_trades *t, fmk_index *ix) {
 }
 
 extern "C" int fmk_index_from_host(fmk_ctx *ctx, const fmk_trades *t, const int64_t *close_idx, int64_t m, fmk_index **out) {
+    FMK_ENTER(ctx);
     *out = nullptr;
     fmk_index *ix = new (std::nothrow) fmk_index();
     if (!ix) return FMK_ERR_ALLOC;
@@ -346,6 +426,7 @@ __global__ void k_time_bar(const int64_t *__restrict__ ts, int64_t n, double sta
 }
 
 extern "C" int fmk_time_bar_index(fmk_ctx *ctx, const fmk_trades *t, double interval_seconds, fmk_index **out) {
+    FMK_ENTER(ctx);
     *out = nullptr;
     if (t->n <= 0) return fmk_fail(ctx, FMK_ERR_ARG, "empty trades");
     if (!t->ts) return fmk_fail(ctx, FMK_ERR_ARG, "time bars need the timestamp column on the device");
@@ -371,10 +452,12 @@ extern "C" int fmk_time_bar_index(fmk_ctx *ctx, const fmk_trades *t, double inte
     if (!rc) rc = fmk_dalloc(ctx, &ix->close_idx, m);
     if (rc) { fmk_index_free(ctx, ix); return rc; }
     if (m > 0) {
-        k_time_bar<<<(unsigned)cdiv(m, 256), 256, 0, ctx->stream>>>(t->ts, t->n, start, iv, m, ix->close_ts, ix->close_idx);
-        ctx->launches++;
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { fmk_index_free(ctx, ix); return fmk_fail(ctx, FMK_ERR_CUDA, cudaGetErrorString(e)); }
+        auto launch = [&]() -> int {
+            FMK_LAUNCH(ctx, k_time_bar, (unsigned)cdiv(m, 256), 256, 0, (const int64_t *)t->ts, t->n, start, iv, m, ix->close_ts, ix->close_idx);
+            return FMK_OK;
+        };
+        rc = launch();
+        if (rc) { fmk_index_free(ctx, ix); return rc; }
     }
     *out = ix;
     return FMK_OK;
@@ -391,6 +474,7 @@ __global__ void k_tick_bar(int64_t m, int64_t thr, int64_t *idx) {
 }
 
 extern "C" int fmk_tick_bar_index(fmk_ctx *ctx, const fmk_trades *t, int64_t threshold, fmk_index **out) {
+    FMK_ENTER(ctx);
     *out = nullptr;
     const int64_t n = t->n;
     if (n <= 0) return fmk_fail(ctx, FMK_ERR_ARG, "empty trades");
@@ -403,22 +487,28 @@ extern "C" int fmk_tick_bar_index(fmk_ctx *ctx, const fmk_trades *t, int64_t thr
     ix->sorted = 1;
     int rc = fmk_dalloc(ctx, &ix->close_idx, m);
     if (rc) { fmk_index_free(ctx, ix); return rc; }
-    k_tick_bar<<<(unsigned)cdiv(m, 256), 256, 0, ctx->stream>>>(m, threshold, ix->close_idx);
-    ctx->launches++;
-    rc = fmk_gather_close_ts(ctx, t, ix);
+    auto launch = [&]() -> int {
+        FMK_LAUNCH(ctx, k_tick_bar, (unsigned)cdiv(m, 256), 256, 0, m, threshold, ix->close_idx);
+        return FMK_OK;
+    };
+    rc = launch();
+    if (!rc) rc = fmk_gather_close_ts(ctx, t, ix);
     if (rc) { fmk_index_free(ctx, ix); return rc; }
     *out = ix;
     return FMK_OK;
 }
 
 extern "C" int fmk_volume_bar_index(fmk_ctx *ctx, const fmk_trades *t, double threshold, fmk_index **out) {
+    FMK_ENTER(ctx);
     return fmk_volume_index_impl(ctx, t, threshold, out);
 }
 extern "C" int fmk_dollar_bar_index(fmk_ctx *ctx, const fmk_trades *t, double threshold, fmk_index **out) {
+    FMK_ENTER(ctx);
     return fmk_dollar_index_impl(ctx, t, threshold, out);
 }
 extern "C" int fmk_cusum_bar_index(fmk_ctx *ctx, const fmk_trades *t, fmk_buf *sigma, double sigma_floor,
                                    double sigma_mult, fmk_index **out) {
+    FMK_ENTER(ctx);
     return fmk_cusum_index_impl(ctx, t, sigma, sigma_floor, sigma_mult, out);
 }
 
@@ -479,6 +569,7 @@ __global__ void k_synth_amount(uint64_t seed, int64_t n, double *amt) {
 }
 
 extern "C" int fmk_trades_synth(fmk_ctx *ctx, int64_t n, uint64_t seed, fmk_trades **out) {
+    FMK_ENTER(ctx);
     if (n <= 0) return fmk_fail(ctx, FMK_ERR_ARG, "n must be positive");
     FMK_TRY(trades_alloc(ctx, n, 1, 1, out));
     fmk_trades *t = *out;
@@ -486,9 +577,11 @@ extern "C" int fmk_trades_synth(fmk_ctx *ctx, int64_t n, uint64_t seed, fmk_trad
     if (!rc) rc = device_inclusive_scan<double>(ctx, RetIn{seed}, PxOut{t->price}, n, (double *)nullptr);
     if (!rc) rc = device_inclusive_scan<int64_t>(ctx, FlipIn{seed}, SideOut{t->side}, n, (int64_t *)nullptr);
     if (!rc) {
-        k_synth_amount<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(seed, n, t->amount);
-        ctx->launches++;
-        if (cudaGetLastError() != cudaSuccess) rc = fmk_fail(ctx, FMK_ERR_CUDA, "synth launch failed");
+        auto launch = [&]() -> int {
+            FMK_LAUNCH(ctx, k_synth_amount, (unsigned)cdiv(n, 256), 256, 0, seed, n, t->amount);
+            return FMK_OK;
+        };
+        rc = launch();
     }
     if (rc) { fmk_trades_free(ctx, t); *out = nullptr; }
     return rc;

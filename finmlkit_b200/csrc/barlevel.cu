@@ -79,9 +79,10 @@ struct EwmsOut {
 // prefix sums for vpin / flow acceleration: P[i+1] = P[i] + x_i, P[0] = 0
 struct PreIn {
     const double *a, *b;
-    int mode;   // 0: a ; 1: b ; 2: |a-b| ; 3: nan flag ; values with a NaN partner count as 0
+    int mode;   // 0: a ; 1: b ; 2: |a-b| ; 3: nan flag ; values with a NaN partner count as 0 ; 4: a as is (NaN propagates)
     __device__ double operator()(int64_t i) const {
         const double x = a[i], y = b ? b[i] : 0.0;
+        if (mode == 4) return x;
         const bool nan = (x != x) || (y != y);
         if (mode == 3) return nan ? 1.0 : 0.0;
         if (nan) return 0.0;
@@ -129,6 +130,7 @@ static int down(fmk_ctx *ctx, T *host, const T *dev, int64_t n) {
 }
 
 extern "C" int fmk_realized_vol(fmk_ctx *ctx, const double *r, int64_t n, int64_t window, int is_sample, double *out) {
+    FMK_ENTER(ctx);
     Scratch<double> dr(ctx), dout(ctx);
     FMK_TRY(dr.alloc(n)); FMK_TRY(dout.alloc(n));
     FMK_TRY(up(ctx, dr.p, r, n));
@@ -137,6 +139,7 @@ extern "C" int fmk_realized_vol(fmk_ctx *ctx, const double *r, int64_t n, int64_
 }
 
 extern "C" int fmk_ewms(fmk_ctx *ctx, const double *y, int64_t n, int64_t span, double *out) {
+    FMK_ENTER(ctx);
     if (span <= 1) {   // volatility.py:27-30: all NaN
         for (int64_t i = 0; i < n; i++) out[i] = NAN;
         return FMK_OK;
@@ -151,6 +154,7 @@ extern "C" int fmk_ewms(fmk_ctx *ctx, const double *y, int64_t n, int64_t span, 
 
 extern "C" int fmk_vpin(fmk_ctx *ctx, const double *volume_buy, const double *volume_sell, int64_t n, int64_t window,
                         float *out) {
+    FMK_ENTER(ctx);
     if (window < 1) return fmk_fail(ctx, FMK_ERR_ARG, "window must be positive");
     Scratch<double> db(ctx), ds(ctx), P(ctx);
     Scratch<float> dout(ctx);
@@ -166,10 +170,12 @@ extern "C" int fmk_vpin(fmk_ctx *ctx, const double *volume_buy, const double *vo
 
 extern "C" int fmk_flow_acceleration(fmk_ctx *ctx, const double *volumes, int64_t n, int64_t window, int64_t recent,
                                      double *out) {
+    FMK_ENTER(ctx);
     Scratch<double> dv(ctx), S(ctx), dout(ctx);
     FMK_TRY(dv.alloc(n)); FMK_TRY(S.alloc(n + 1)); FMK_TRY(dout.alloc(n));
     FMK_TRY(up(ctx, dv.p, volumes, n));
-    FMK_TRY((device_inclusive_scan<double>(ctx, PreIn{dv.p, nullptr, 0}, PreOut{S.p}, n, (double *)nullptr)));
+    // volume.py:590-593 builds S[i+1] = S[i] + volumes[i] with no NaN handling: a NaN volume poisons every later sum
+    FMK_TRY((device_inclusive_scan<double>(ctx, PreIn{dv.p, nullptr, 4}, PreOut{S.p}, n, (double *)nullptr)));
     if (n > 0) FMK_LAUNCH(ctx, k_flow_out, (unsigned)cdiv(n, 128), 128, 0, (const double *)S.p, n, window, recent, dout.p);
     return down(ctx, out, dout.p, n);
 }

@@ -1,0 +1,324 @@
+// comm.cu -- the ONE collective of the path: a gather-v of the finished bar frames to one rank, over NCCL, behind the C ABI.
+//
+// Symbols are independent (the reference holds one symbol per TradesData), so nothing on the data path crosses GPUs;
+// each rank finishes its own frame and rank `dst` collects them (BASELINE configs[4]).  NCCL has no
+// gather-v, so a step is:   ncclAllGather of the exact byte counts  ->  grouped ncclSend / ncclRecv of exactly those bytes
+// (no padding to a common capacity).  The transfer of step k runs on a communication stream and overlaps the kernels of
+// step k+1:
+//     submit(k):  [ctx stream]  pack the step's segments into staging[k&1] (device-to-device), record `ready`
+//                 [comm stream] wait `ready`; all-gather the counts; copy them to pinned host memory; record `sized`
+//     submit(k+1) / finish():   host waits `sized(k)` (the GPU already has step k+1's kernels queued, so it stays busy),
+//                               sizes the receive buffers, posts the grouped send/recv of step k on the comm stream
+//     finish():   the ctx stream waits for the last transfer, so a timer stopped on it covers every gather.
+// libnccl is loaded with dlopen at fmk_comm_init: single-GPU use of libfmk.so needs no NCCL at all.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <new>
+#include "common.cuh"
+
+namespace {
+struct NcclApi {
+    void *h;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRankConfig)(ncclComm_t *, int, ncclUniqueId, int, ncclConfig_t *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    const char *(*GetErrorString)(ncclResult_t);
+    ncclResult_t (*GetVersion)(int *);
+};
+NcclApi g_nccl = {};
+
+const char *nccl_load() {
+    if (g_nccl.h) return nullptr;
+    const char *names[] = {getenv("FMK_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *nm : names) {
+        if (!nm || !*nm) continue;
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return "libnccl.so.2 not found (set FMK_NCCL_LIB)";
+#define FMK_SYM(field, name)                                         \
+    *(void **)(&g_nccl.field) = dlsym(h, name);                      \
+    if (!g_nccl.field) { dlclose(h); return "libnccl lacks " name; }
+    FMK_SYM(GetUniqueId, "ncclGetUniqueId")
+    FMK_SYM(CommInitRank, "ncclCommInitRank")
+    FMK_SYM(CommDestroy, "ncclCommDestroy")
+    FMK_SYM(AllGather, "ncclAllGather")
+    FMK_SYM(AllReduce, "ncclAllReduce")
+    FMK_SYM(Send, "ncclSend")
+    FMK_SYM(Recv, "ncclRecv")
+    FMK_SYM(GroupStart, "ncclGroupStart")
+    FMK_SYM(GroupEnd, "ncclGroupEnd")
+    FMK_SYM(GetErrorString, "ncclGetErrorString")
+    FMK_SYM(GetVersion, "ncclGetVersion")
+#undef FMK_SYM
+    *(void **)(&g_nccl.CommInitRankConfig) = dlsym(h, "ncclCommInitRankConfig");   // optional (NCCL >= 2.14)
+    g_nccl.h = h;
+    return nullptr;
+}
+}  // namespace
+
+constexpr int FMK_COMM_MAXSEG = 8;
+
+struct fmk_comm {
+    fmk_ctx *ctx;
+    ncclComm_t comm;
+    int rank, world;
+    cudaStream_t stream;            // communication stream
+    // per pipeline slot
+    char *staging[2];               // packed frame of this rank
+    int64_t staging_cap[2];
+    cudaEvent_t ready[2], sized[2], done[2];
+    int has_done[2];
+    int64_t *counts_dev[2];         // [world] byte counts after the all-gather
+    int64_t *counts_host[2];        // pinned
+    int64_t *mine_host[2];          // pinned: this rank's byte count (source of the all-gather input)
+    int64_t *mine_dev[2];
+    char *recv[2];                  // dst only: frames of all ranks, back to back
+    int64_t recv_cap[2];
+    int64_t recv_off[2][65];        // dst only: offsets of each rank's frame in recv[s]
+    int pending;                    // slot whose counts were exchanged but whose send/recv is not posted yet (-1: none)
+    int pending_dst;
+    int last;                       // slot of the last completed gather (-1: none)
+    int64_t k;                      // steps submitted
+    double *scal_dev;               // small device scratch for barrier / host all-reduce
+    double *scal_host;              // pinned
+};
+
+#define FMK_NCCL(ctx, call)                                                                                   \
+    do {                                                                                                      \
+        ncclResult_t r__ = (call);                                                                            \
+        if (r__ != ncclSuccess) {                                                                             \
+            char b__[400];                                                                                    \
+            snprintf(b__, sizeof(b__), "NCCL error %s at %s:%d (%s)", g_nccl.GetErrorString(r__), __FILE__,   \
+                     __LINE__, #call);                                                                        \
+            return fmk_fail((ctx), FMK_ERR_CUDA, b__);                                                        \
+        }                                                                                                     \
+    } while (0)
+
+extern "C" {
+
+int fmk_comm_unique_id(void *out128) {
+    const char *e = nccl_load();
+    if (e) return FMK_ERR_CUDA;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return FMK_ERR_CUDA;
+    memcpy(out128, &id, sizeof(id));
+    return FMK_OK;
+}
+
+int fmk_comm_init(fmk_ctx *ctx, const void *id128, int rank, int world, int max_ctas, fmk_comm **out) {
+    FMK_ENTER(ctx);
+    *out = nullptr;
+    if (world < 1 || world > 64 || rank < 0 || rank >= world) return fmk_fail(ctx, FMK_ERR_ARG, "bad rank / world size");
+    const char *e = nccl_load();
+    if (e) return fmk_fail(ctx, FMK_ERR_CUDA, e);
+    fmk_comm *c = new (std::nothrow) fmk_comm();
+    if (!c) return FMK_ERR_ALLOC;
+    memset(c, 0, sizeof(*c));
+    c->ctx = ctx; c->rank = rank; c->world = world; c->pending = -1; c->last = -1;
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclResult_t r;
+    if (g_nccl.CommInitRankConfig && max_ctas > 0) {
+        // a small CTA budget: the payload is MBs against NVLink 5, and every SM NCCL takes is an SM the step's own
+        // kernels lose (the r01 scaling loss at N = 8 was a wave-exact kernel spilling into an extra partial wave)
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.maxCTAs = max_ctas;
+        cfg.minCTAs = 1;
+        r = g_nccl.CommInitRankConfig(&c->comm, world, id, rank, &cfg);
+    } else r = g_nccl.CommInitRank(&c->comm, world, id, rank);
+    if (r != ncclSuccess) {
+        char b[300];
+        snprintf(b, sizeof(b), "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+        delete c;
+        return fmk_fail(ctx, FMK_ERR_CUDA, b);
+    }
+    cudaError_t ce = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    for (int s = 0; s < 2 && ce == cudaSuccess; s++) {
+        ce = cudaEventCreateWithFlags(&c->ready[s], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->sized[s], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->done[s], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaMalloc(&c->counts_dev[s], sizeof(int64_t) * world);
+        if (ce == cudaSuccess) ce = cudaMalloc(&c->mine_dev[s], sizeof(int64_t));
+        if (ce == cudaSuccess) ce = cudaHostAlloc(&c->counts_host[s], sizeof(int64_t) * world, cudaHostAllocDefault);
+        if (ce == cudaSuccess) ce = cudaHostAlloc(&c->mine_host[s], sizeof(int64_t), cudaHostAllocDefault);
+    }
+    if (ce == cudaSuccess) ce = cudaMalloc(&c->scal_dev, 64 * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaHostAlloc(&c->scal_host, 64 * sizeof(double), cudaHostAllocDefault);
+    if (ce != cudaSuccess) return fmk_fail(ctx, FMK_ERR_CUDA, cudaGetErrorString(ce));
+    *out = c;
+    return FMK_OK;
+}
+
+void fmk_comm_destroy(fmk_comm *c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    for (int s = 0; s < 2; s++) {
+        cudaFree(c->staging[s]); cudaFree(c->recv[s]); cudaFree(c->counts_dev[s]); cudaFree(c->mine_dev[s]);
+        cudaFreeHost(c->counts_host[s]); cudaFreeHost(c->mine_host[s]);
+        cudaEventDestroy(c->ready[s]); cudaEventDestroy(c->sized[s]); cudaEventDestroy(c->done[s]);
+    }
+    cudaFree(c->scal_dev);
+    cudaFreeHost(c->scal_host);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int fmk_comm_rank(const fmk_comm *c) { return c->rank; }
+int fmk_comm_world(const fmk_comm *c) { return c->world; }
+
+// Host-value all-reduce (op: 0 = max, 1 = min, 2 = sum) of n <= 64 doubles; also the barrier (n = 0 reduces one dummy).
+// Ordered after everything queued on the ctx stream; returns when every rank has contributed.
+int fmk_comm_allreduce_f64(fmk_comm *c, double *inout, int n, int op) {
+    fmk_ctx *ctx = c->ctx;
+    FMK_ENTER(ctx);
+    if (n < 0 || n > 64) return fmk_fail(ctx, FMK_ERR_ARG, "allreduce of at most 64 values");
+    const int m = n > 0 ? n : 1;
+    for (int i = 0; i < m; i++) c->scal_host[i] = n > 0 ? inout[i] : 0.0;
+    FMK_CUDA(ctx, cudaMemcpyAsync(c->scal_dev, c->scal_host, m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const ncclRedOp_t rop = op == 0 ? ncclMax : (op == 1 ? ncclMin : ncclSum);
+    FMK_NCCL(ctx, g_nccl.AllReduce(c->scal_dev, c->scal_dev, (size_t)m, ncclDouble, rop, c->comm, ctx->stream));
+    FMK_CUDA(ctx, cudaMemcpyAsync(c->scal_host, c->scal_dev, m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; i++) inout[i] = c->scal_host[i];
+    return FMK_OK;
+}
+
+int fmk_comm_barrier(fmk_comm *c) {
+    FMK_CUDA(c->ctx, cudaStreamSynchronize(c->stream));
+    return fmk_comm_allreduce_f64(c, nullptr, 0, 2);
+}
+
+static int comm_grow(fmk_ctx *ctx, char **buf, int64_t *cap, int64_t need, cudaStream_t quiesce) {
+    if (*cap >= need) return FMK_OK;
+    if (*buf) { FMK_CUDA(ctx, cudaStreamSynchronize(quiesce)); FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(*buf); }
+    *buf = nullptr; *cap = 0;
+    const int64_t want = need + need / 4 + 4096;         // slack: streams of similar size never reallocate again
+    FMK_CUDA(ctx, cudaMalloc((void **)buf, (size_t)want));
+    *cap = want;
+    return FMK_OK;
+}
+
+// post the send / recv of the slot whose byte counts have been exchanged
+static int comm_complete_pending(fmk_comm *c) {
+    fmk_ctx *ctx = c->ctx;
+    if (c->pending < 0) return FMK_OK;
+    const int s = c->pending, dst = c->pending_dst;
+    FMK_CUDA(ctx, cudaEventSynchronize(c->sized[s]));
+    const int64_t *cnt = c->counts_host[s];
+    if (c->rank == dst) {
+        int64_t tot = 0;
+        for (int r = 0; r < c->world; r++) { c->recv_off[s][r] = tot; tot += (cnt[r] + 255) / 256 * 256; }
+        c->recv_off[s][c->world] = tot;
+        FMK_TRY(comm_grow(ctx, &c->recv[s], &c->recv_cap[s], tot, c->stream));
+    }
+    FMK_NCCL(ctx, g_nccl.GroupStart());
+    if (c->rank == dst) {
+        for (int r = 0; r < c->world; r++) {
+            if (r == dst || cnt[r] == 0) continue;
+            FMK_NCCL(ctx, g_nccl.Recv(c->recv[s] + c->recv_off[s][r], (size_t)cnt[r], ncclUint8, r, c->comm, c->stream));
+        }
+    } else if (cnt[c->rank] > 0) {
+        FMK_NCCL(ctx, g_nccl.Send(c->staging[s], (size_t)cnt[c->rank], ncclUint8, dst, c->comm, c->stream));
+    }
+    FMK_NCCL(ctx, g_nccl.GroupEnd());
+    if (c->rank == dst && cnt[dst] > 0)   // own frame: device-to-device on the comm stream
+        FMK_CUDA(ctx, cudaMemcpyAsync(c->recv[s] + c->recv_off[s][dst], c->staging[s], (size_t)cnt[dst], cudaMemcpyDeviceToDevice, c->stream));
+    FMK_CUDA(ctx, cudaEventRecord(c->done[s], c->stream));
+    c->has_done[s] = 1;
+    c->last = s;
+    c->pending = -1;
+    return FMK_OK;
+}
+
+// One gather step: the nseg device segments (pointers valid on the ctx stream) are packed back to back, each padded to 16
+// bytes, into this rank's frame; the frame is gathered to `dst`.  Returns immediately (see the pipeline at the top).
+int fmk_comm_gather_submit(fmk_comm *c, const void *const *seg_ptrs, const int64_t *seg_bytes, int nseg, int dst) {
+    fmk_ctx *ctx = c->ctx;
+    FMK_ENTER(ctx);
+    if (nseg < 0 || nseg > FMK_COMM_MAXSEG) return fmk_fail(ctx, FMK_ERR_ARG, "too many segments");
+    if (dst < 0 || dst >= c->world) return fmk_fail(ctx, FMK_ERR_ARG, "bad destination rank");
+    FMK_TRY(comm_complete_pending(c));
+    const int s = (int)(c->k & 1);
+    int64_t total = 0;
+    for (int q = 0; q < nseg; q++) {
+        if (seg_bytes[q] < 0) return fmk_fail(ctx, FMK_ERR_ARG, "negative segment size");
+        total += (seg_bytes[q] + 15) / 16 * 16;
+    }
+    if (c->has_done[s]) {             // the transfer that read this slot two steps ago must be finished before it is rewritten
+        FMK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, c->done[s], 0));
+    }
+    FMK_TRY(comm_grow(ctx, &c->staging[s], &c->staging_cap[s], total, c->stream));
+    int64_t off = 0;
+    for (int q = 0; q < nseg; q++) {
+        if (seg_bytes[q] > 0)
+            FMK_CUDA(ctx, cudaMemcpyAsync(c->staging[s] + off, seg_ptrs[q], (size_t)seg_bytes[q], cudaMemcpyDeviceToDevice, ctx->stream));
+        off += (seg_bytes[q] + 15) / 16 * 16;
+    }
+    FMK_CUDA(ctx, cudaEventRecord(c->ready[s], ctx->stream));
+    FMK_CUDA(ctx, cudaStreamWaitEvent(c->stream, c->ready[s], 0));
+    *c->mine_host[s] = total;
+    FMK_CUDA(ctx, cudaMemcpyAsync(c->mine_dev[s], c->mine_host[s], 8, cudaMemcpyHostToDevice, c->stream));
+    FMK_NCCL(ctx, g_nccl.AllGather(c->mine_dev[s], c->counts_dev[s], 1, ncclInt64, c->comm, c->stream));
+    FMK_CUDA(ctx, cudaMemcpyAsync(c->counts_host[s], c->counts_dev[s], 8 * (size_t)c->world, cudaMemcpyDeviceToHost, c->stream));
+    FMK_CUDA(ctx, cudaEventRecord(c->sized[s], c->stream));
+    c->pending = s;
+    c->pending_dst = dst;
+    c->k++;
+    return FMK_OK;
+}
+
+// Posts what is still pending and makes the ctx stream wait for every outstanding transfer (stream-ordered, no host sync
+// beyond the byte-count wait): a timer stopped on the ctx stream afterwards covers all gathers.
+int fmk_comm_gather_finish(fmk_comm *c) {
+    fmk_ctx *ctx = c->ctx;
+    FMK_ENTER(ctx);
+    FMK_TRY(comm_complete_pending(c));
+    for (int s = 0; s < 2; s++)
+        if (c->has_done[s]) FMK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, c->done[s], 0));
+    return FMK_OK;
+}
+
+// On the destination rank, after fmk_comm_gather_finish: where rank r's frame of the LAST step landed (device pointer,
+// exact byte count).  Other ranks get bytes = their own count and a null pointer.
+int fmk_comm_gather_result(fmk_comm *c, int r, void **dev_ptr, int64_t *bytes) {
+    fmk_ctx *ctx = c->ctx;
+    *dev_ptr = nullptr; *bytes = 0;
+    if (c->last < 0 || r < 0 || r >= c->world) return fmk_fail(ctx, FMK_ERR_ARG, "no finished gather / bad rank");
+    const int s = c->last;
+    *bytes = c->counts_host[s][r];
+    if (c->recv[s]) *dev_ptr = c->recv[s] + c->recv_off[s][r];
+    return FMK_OK;
+}
+
+// Copies rank r's gathered frame to the host (destination rank only; waits for the transfer).
+int fmk_comm_gather_download(fmk_comm *c, int r, void *host, int64_t cap) {
+    fmk_ctx *ctx = c->ctx;
+    FMK_ENTER(ctx);
+    void *p; int64_t b;
+    FMK_TRY(fmk_comm_gather_result(c, r, &p, &b));
+    if (!p) return fmk_fail(ctx, FMK_ERR_ARG, "not the destination rank");
+    if (b > cap) return fmk_fail(ctx, FMK_ERR_CAPACITY, "host buffer too small for the gathered frame");
+    FMK_CUDA(ctx, cudaStreamSynchronize(c->stream));
+    if (b > 0) FMK_CUDA(ctx, cudaMemcpy(host, p, (size_t)b, cudaMemcpyDeviceToHost));
+    return FMK_OK;
+}
+
+int fmk_comm_nccl_version(void) {
+    if (nccl_load()) return 0;
+    int v = 0;
+    g_nccl.GetVersion(&v);
+    return v;
+}
+
+}  // extern "C"

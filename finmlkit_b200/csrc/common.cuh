@@ -72,6 +72,17 @@ struct fmk_footprint {
     double *vp_skew, *vp_gini;
 };
 
+// device-resident bar frame (fmk_bar_features_device): one block of per-bar columns + one block of per-level columns
+struct fmk_frame {
+    int64_t n_bars, n_levels;
+    int flags;
+    char *bar_block;
+    int64_t bar_bytes;
+    char *level_block;
+    int64_t level_bytes;
+    int64_t col_off[FMK_COL_COUNT];   // byte offset inside its block; -1 = column absent
+};
+
 static inline int fmk_fail(fmk_ctx *ctx, int code, const char *msg) {
     if (ctx) {
         snprintf(ctx->err, sizeof(ctx->err), "%s", msg);
@@ -88,6 +99,13 @@ static inline int fmk_fail(fmk_ctx *ctx, int code, const char *msg) {
                      __FILE__, __LINE__, #call);                                                 \
             return fmk_fail((ctx), FMK_ERR_CUDA, b__);                                           \
         }                                                                                        \
+    } while (0)
+
+// Every extern "C" entry point that takes a ctx starts with this: a process may hold one ctx per GPU, and the CUDA
+// "current device" is per host thread, so each call re-binds its own device (a no-op when it already is current).
+#define FMK_ENTER(ctx)                                   \
+    do {                                                 \
+        if (ctx) cudaSetDevice((ctx)->device);           \
     } while (0)
 
 #define FMK_TRY(call)                \

@@ -295,6 +295,7 @@ static int cusum_chain(fmk_ctx *ctx, const Scratch<double> &r, const Scratch<dou
 
 int fmk_cusum_index_impl(fmk_ctx *ctx, const fmk_trades *t, fmk_buf *sigma, double sigma_floor, double sigma_mult,
                          fmk_index **out_ix) {
+    FMK_ENTER(ctx);
     *out_ix = nullptr;
     const int64_t n = t->n;
     if (n <= 0) return fmk_fail(ctx, FMK_ERR_ARG, "empty trades");
@@ -323,8 +324,11 @@ int fmk_cusum_index_impl(fmk_ctx *ctx, const fmk_trades *t, fmk_buf *sigma, doub
     int64_t total = 0;
     int64_t *idx = nullptr;
     FMK_TRY(cusum_chain(ctx, r, lam, allowed, n, first, 0, &idx, &total));
-    k_set_first<<<1, 1, 0, ctx->stream>>>(idx, first);
-    ctx->launches++;
+    {
+        auto launch = [&]() -> int { FMK_LAUNCH(ctx, k_set_first, 1, 1, 0, idx, first); return FMK_OK; };
+        const int lrc = launch();
+        if (lrc) { fmk_dfree(ctx, idx); return lrc; }
+    }
     fmk_index *ix = new (std::nothrow) fmk_index();
     if (!ix) { fmk_dfree(ctx, idx); return FMK_ERR_ALLOC; }
     memset(ix, 0, sizeof(*ix));
@@ -342,6 +346,7 @@ int fmk_cusum_index_impl(fmk_ctx *ctx, const fmk_trades *t, fmk_buf *sigma, doub
 // cusum_filter (sampling/filters.py:6-70): host series / thresholds in, device buffer of int64 event indices out.
 extern "C" int fmk_cusum_filter(fmk_ctx *ctx, const double *series, int64_t n, const double *threshold, int64_t n_thr,
                                 fmk_buf **events_out, int64_t *n_events) {
+    FMK_ENTER(ctx);
     *events_out = nullptr; *n_events = 0;
     if (n <= 1) return fmk_fail(ctx, FMK_ERR_ARG, "Input time series must have at least 2 elements.");
     if (n_thr != 1 && n_thr != n)

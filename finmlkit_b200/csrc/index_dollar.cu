@@ -402,6 +402,7 @@ static int64_t dollar_pick_chunk(fmk_ctx *ctx, int64_t n) {
 }
 
 int fmk_dollar_index_impl(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index **out_ix) {
+    FMK_ENTER(ctx);
     *out_ix = nullptr;
     const int64_t n = t->n;
     if (n <= 0) return fmk_fail(ctx, FMK_ERR_ARG, "empty trades");

@@ -365,6 +365,7 @@ static int volume_serial(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index 
 }
 
 int fmk_volume_index_impl(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index **out_ix) {
+    FMK_ENTER(ctx);
     *out_ix = nullptr;
     const int64_t n = t->n;
     if (n <= 0) return fmk_fail(ctx, FMK_ERR_ARG, "empty trades");
@@ -425,9 +426,13 @@ int fmk_volume_index_impl(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index
     ctx->stats[0] = nC; ctx->stats[1] = hrep; ctx->stats[2] = 1;
     int64_t *idx = nullptr;
     FMK_TRY(fmk_dalloc(ctx, &idx, nb + 1));
-    k_volume_emit<<<(unsigned)cdiv(nC, 128), 128, 0, ctx->stream>>>((const int32_t *)next.p, (const int64_t *)entryC.p,
-                                                                   (const int64_t *)off.p, nC, n, idx);
-    ctx->launches++;
+    auto emit = [&]() -> int {
+        FMK_LAUNCH(ctx, k_volume_emit, (unsigned)cdiv(nC, 128), 128, 0, (const int32_t *)next.p, (const int64_t *)entryC.p,
+                   (const int64_t *)off.p, nC, n, idx);
+        return FMK_OK;
+    };
+    const int erc = emit();
+    if (erc) { fmk_dfree(ctx, idx); return erc; }
     return finish_index(ctx, t, idx, nb + 1, out_ix);
 }
 

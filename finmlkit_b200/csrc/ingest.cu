@@ -33,6 +33,7 @@ struct SideOut {
 };
 
 extern "C" int fmk_trade_side_vector(fmk_ctx *ctx, const double *prices, int64_t n, int8_t *sides_out) {
+    FMK_ENTER(ctx);
     if (n <= 0) return FMK_OK;
     Scratch<double> p(ctx);
     Scratch<int8_t> s(ctx);
@@ -91,6 +92,7 @@ __global__ void k_merge_write(const int64_t *__restrict__ ts, const double *__re
 extern "C" int fmk_merge_split_trades(fmk_ctx *ctx, const int64_t *ts, const double *prices, const float *amounts,
                                       const uint8_t *is_buyer_maker, int64_t n, int64_t *ts_out, double *prices_out,
                                       float *amounts_out, int8_t *sides_out, int64_t *n_out) {
+    FMK_ENTER(ctx);
     *n_out = 0;
     if (n <= 0) return FMK_OK;
     Scratch<int64_t> dts(ctx), gid(ctx), ots(ctx), dtot(ctx);

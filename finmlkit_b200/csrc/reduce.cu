@@ -336,60 +336,6 @@ __global__ void __launch_bounds__(OS_WARPS * 32) k_bar_order_stats(const double 
     }
 }
 
-// Fused comp_bar_ohlcv: one warp streams the bar once from HBM (price + amount: O/H/L/C, sums, and the OR/AND of the
-// amount keys), then runs the radix select for the median on the amounts it has just pulled through L1/L2.
-__global__ void __launch_bounds__(OS_WARPS * 32) k_bar_ohlcv_median_v1(const double *__restrict__ p,
-                                                                    const double *__restrict__ v,
-                                                                    const int64_t *__restrict__ ci, int64_t nb, int64_t n,
-                                                                    OhlcvOut o, double *__restrict__ median_out) {
-    __shared__ unsigned hist_s[OS_WARPS][OS_HIST];
-    __shared__ unsigned long long cand_s[OS_WARPS][32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nb; i += nwarps) {
-        const int64_t s = ci[i], e = ci[i + 1];
-        if (s == e) {
-            if (lane == 0) { ohlcv_empty(o, i, p, e, n); median_out[i] = 0.0; }
-            continue;
-        }
-        const int64_t start = s + 1;
-        double hi = -INFINITY, lo = INFINITY, sv = 0.0, sd = 0.0;
-        unsigned long long orv = 0ull, andv = ~0ull;
-        int64_t j = start + lane;
-        for (; j + 96 <= e; j += 128) {
-            double p0 = __ldg(p + j), p1 = __ldg(p + j + 32), p2 = __ldg(p + j + 64), p3 = __ldg(p + j + 96);
-            double v0 = __ldg(v + j), v1 = __ldg(v + j + 32), v2 = __ldg(v + j + 64), v3 = __ldg(v + j + 96);
-            hi = fmax(fmax(hi, fmax(p0, p1)), fmax(p2, p3));
-            lo = fmin(fmin(lo, fmin(p0, p1)), fmin(p2, p3));
-            sv += (v0 + v1) + (v2 + v3);
-            sd += (p0 * v0 + p1 * v1) + (p2 * v2 + p3 * v3);
-            const unsigned long long k0 = dkey(v0), k1 = dkey(v1), k2 = dkey(v2), k3 = dkey(v3);
-            orv |= (k0 | k1) | (k2 | k3);
-            andv &= (k0 & k1) & (k2 & k3);
-        }
-        for (; j <= e; j += 32) {
-            double pj = __ldg(p + j), vj = __ldg(v + j);
-            hi = fmax(hi, pj); lo = fmin(lo, pj);
-            sv += vj; sd += pj * vj;
-            const unsigned long long kj = dkey(vj);
-            orv |= kj; andv &= kj;
-        }
-        hi = warp_max(hi); lo = warp_min(lo); sv = warp_sum(sv); sd = warp_sum(sd);
-        orv = warp_or64(orv); andv = warp_and64(andv);
-        const int64_t cnt = e - start + 1;
-        if (lane == 0) {
-            o.open[i] = p[start]; o.close[i] = p[e]; o.high[i] = hi; o.low[i] = lo;
-            o.volume[i] = (float)sv;
-            o.vwap[i] = sv > 0 ? sd / sv : 0.0;
-            o.trades[i] = cnt;
-        }
-        const int64_t mk = (cnt & 1) ? (cnt >> 1) : (cnt >> 1) - 1;
-        double r0, r1;
-        warp_select_two(v + start, cnt, mk, hist_s[w], cand_s[w], &r0, &r1, true, orv, andv);
-        if (lane == 0) median_out[i] = (cnt & 1) ? r0 : (r0 + r1) / 2;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // Order statistics on RAW bit patterns.  Trade sizes are never negative, and for non-negative doubles the IEEE bit
 // pattern orders like the value, so the per-element key transform (14 % of the fused kernel's instructions) can be
@@ -645,8 +591,6 @@ __global__ void __launch_bounds__(OS_WARPS * 32, 5) k_bar_ohlcv_median(const dou
     }
 }
 
-#include "ohlcv_conveyor.cuh"
-
 static int launch_order_stats(fmk_ctx *ctx, const double *a, const int64_t *ci, int64_t nb, int mode, double *med,
                               double *p95) {
     if (nb <= 0) return FMK_OK;
@@ -660,6 +604,10 @@ static int launch_order_stats(fmk_ctx *ctx, const double *a, const int64_t *ci, 
 static int check_index(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix) {
     if (ix->m < 2) return fmk_fail(ctx, FMK_ERR_ARG, "Bar close indices must contain at least two elements.");
     if (ix->n_ticks != t->n) return fmk_fail(ctx, FMK_ERR_ARG, "index was built for a different trades handle");
+    // caller-supplied indices (fmk_index_from_host) were validated on upload: an index outside [-1, n) or a decreasing pair
+    // would make every per-bar kernel read out of bounds, and an illegal address poisons the whole CUDA context
+    if (!ix->sorted)
+        return fmk_fail(ctx, FMK_ERR_ARG, "Bar close indices must be non-decreasing and lie in [-1, len(prices)).");
     return FMK_OK;
 }
 
@@ -669,18 +617,6 @@ static int run_ohlcv(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, Ohl
         int64_t blocks = cdiv(nb, OS_WARPS);
         const int64_t maxb = (int64_t)ctx->sm_count * 16;
         if (blocks > maxb) blocks = maxb;
-        // FMK_MEDIAN_KERNEL=v1|conveyor selects the earlier variants for A/B profiling
-        static const char *variant = getenv("FMK_MEDIAN_KERNEL");
-        if (variant && variant[0] == 'c' && ix->sorted && ((((uintptr_t)t->price | (uintptr_t)t->amount) & 15u) == 0) && t->n / nb <= 1536) {
-            const size_t smem = sizeof(CvShared);
-            FMK_CUDA(ctx, cudaFuncSetAttribute(k_bar_ohlcv_conveyor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            FMK_LAUNCH(ctx, k_bar_ohlcv_conveyor, (unsigned)ctx->sm_count, CV_THREADS, smem, t->price, t->amount, ix->close_idx, nb, t->n, o, median);
-            return FMK_OK;
-        }
-        if (variant && variant[0] == 'v') {
-            FMK_LAUNCH(ctx, k_bar_ohlcv_median_v1, (unsigned)blocks, OS_WARPS * 32, 0, t->price, t->amount, ix->close_idx, nb, t->n, o, median);
-            return FMK_OK;
-        }
         FMK_LAUNCH(ctx, k_bar_ohlcv_median, (unsigned)blocks, OS_WARPS * 32, 0, t->price, t->amount, ix->close_idx, nb, t->n, o, median);
         return FMK_OK;
     }
@@ -705,6 +641,7 @@ static int d2h(fmk_ctx *ctx, T *host, const T *dev, int64_t count) {
 
 extern "C" int fmk_bar_ohlcv(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, double *open, double *high,
                              double *low, double *close, float *volume, double *vwap, int64_t *trades, double *median) {
+    FMK_ENTER(ctx);
     FMK_TRY(check_index(ctx, t, ix));
     const int64_t nb = ix->m - 1;
     Scratch<double> d(ctx);   // open, high, low, close, vwap, median
@@ -728,14 +665,18 @@ extern "C" int fmk_bar_ohlcv(fmk_ctx *ctx, const fmk_trades *t, const fmk_index 
 }
 
 extern "C" int fmk_bar_ohlcv_device(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, int with_median) {
+    FMK_ENTER(ctx);
     FMK_TRY(check_index(ctx, t, ix));
     const int64_t nb = ix->m - 1;
     const int64_t need = nb * (6 * 8 + 4 + 8);
     if (ctx->res_cols_bytes < need) {
-        if (ctx->res_cols) cudaFree(ctx->res_cols);
+        // grow with 25 % slack: repeated builds over streams of similar size never reallocate inside a step
+        const int64_t want = need + need / 4 + 4096;
+        if (ctx->res_cols) { FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->res_cols); }
         ctx->res_cols = nullptr;
-        FMK_CUDA(ctx, cudaMalloc(&ctx->res_cols, (size_t)need));
-        ctx->res_cols_bytes = need;
+        ctx->res_cols_bytes = 0;
+        FMK_CUDA(ctx, cudaMalloc(&ctx->res_cols, (size_t)want));
+        ctx->res_cols_bytes = want;
     }
     ctx->res_nb = nb;
     double *d = (double *)ctx->res_cols;
@@ -844,6 +785,7 @@ extern "C" int fmk_bar_directional(fmk_ctx *ctx, const fmk_trades *t, const fmk_
                                    float *dollars_sell, float *mean_spread, float *max_spread, int64_t *cum_ticks_min,
                                    int64_t *cum_ticks_max, float *cum_volume_min, float *cum_volume_max,
                                    float *cum_dollars_min, float *cum_dollars_max) {
+    FMK_ENTER(ctx);
     FMK_TRY(check_index(ctx, t, ix));
     if (!t->side) return fmk_fail(ctx, FMK_ERR_ARG, "trades have no 'side' column");
     const int64_t nb = ix->m - 1;
@@ -915,6 +857,7 @@ __global__ void __launch_bounds__(256) k_bar_trade_size(const double *__restrict
 extern "C" int fmk_bar_trade_size(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, const double *theta,
                                   int64_t n_theta, double theta_mult, float *mean_size_rel, float *size_95_rel,
                                   float *pct_block, float *size_gini) {
+    FMK_ENTER(ctx);
     FMK_TRY(check_index(ctx, t, ix));
     const int64_t nb = ix->m - 1;
     if (n_theta != nb)
@@ -1146,6 +1089,7 @@ __global__ void __launch_bounds__(FF_WARPS * 32) k_footprint_features(const int6
 }
 
 extern "C" void fmk_footprint_free(fmk_ctx *ctx, fmk_footprint *fp) {
+    FMK_ENTER(ctx);
     if (!fp) return;
     fmk_dfree(ctx, fp->level_offsets); fmk_dfree(ctx, fp->price_levels);
     fmk_dfree(ctx, fp->buy_vol); fmk_dfree(ctx, fp->sell_vol);
@@ -1159,8 +1103,42 @@ extern "C" void fmk_footprint_free(fmk_ctx *ctx, fmk_footprint *fp) {
 
 extern "C" int64_t fmk_footprint_levels(const fmk_footprint *fp) { return fp->n_levels; }
 
+// level_offsets[0..nb] from device lows / highs (one scan); *total_out = number of (bar, level) rows (host sync)
+static int fp_offsets(fmk_ctx *ctx, int64_t nb, const double *dlows, const double *dhighs, double tick,
+                      int64_t *level_offsets, int64_t *total_out) {
+    FMK_CUDA(ctx, cudaMemsetAsync(level_offsets, 0, 8, ctx->stream));
+    FMK_TRY(device_inclusive_scan<int64_t>(ctx, LevelsIn{dlows, dhighs, tick}, OffOut{level_offsets}, nb, (int64_t *)nullptr));
+    FMK_CUDA(ctx, cudaMemcpyAsync(total_out, level_offsets + nb, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMK_OK;
+}
+
+// fills every array of `fp` (pointers already set, level_offsets computed); err_dev: device int, zeroed by the caller
+static int fp_fill(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, const double *dlows, double tick, double factor,
+                   const fmk_footprint *fp, int *err_dev) {
+    const int64_t nb = fp->n_bars;
+    int64_t blocks = cdiv(nb, 8);
+    int64_t maxb = (int64_t)ctx->sm_count * 64;
+    if (blocks > maxb) blocks = maxb;
+    FMK_LAUNCH(ctx, k_bar_footprint, (unsigned)blocks, 256, 0, t->price, t->amount, t->side, ix->close_idx, nb, dlows, tick,
+               fp->level_offsets, fp->price_levels, fp->buy_vol, fp->sell_vol, fp->buy_ticks, fp->sell_ticks, err_dev);
+    FMK_LAUNCH(ctx, k_footprint_features, (unsigned)cdiv(nb, FF_WARPS * 32), FF_WARPS * 32, 0, fp->level_offsets, nb, fp->price_levels,
+               fp->buy_vol, fp->sell_vol, factor, fp->buy_imb, fp->sell_imb, fp->buy_imb_sum, fp->sell_imb_sum, fp->cot,
+               fp->run_signed, fp->vp_skew, fp->vp_gini);
+    return FMK_OK;
+}
+
+static int fp_check_err(fmk_ctx *ctx, const int *err_dev) {
+    int herr = 0;
+    FMK_CUDA(ctx, cudaMemcpyAsync(&herr, err_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (herr) return fmk_fail(ctx, FMK_ERR_LEVEL, "Something went wrong! Invalid price level index!");
+    return FMK_OK;
+}
+
 extern "C" int fmk_bar_footprints(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, double tick,
                                   const double *bar_lows, const double *bar_highs, double factor, fmk_footprint **out) {
+    FMK_ENTER(ctx);
     *out = nullptr;
     FMK_TRY(check_index(ctx, t, ix));
     if (!t->side) return fmk_fail(ctx, FMK_ERR_ARG, "trades have no 'side' column");
@@ -1178,16 +1156,8 @@ extern "C" int fmk_bar_footprints(fmk_ctx *ctx, const fmk_trades *t, const fmk_i
     memset(fp, 0, sizeof(*fp));
     fp->n_bars = nb;
     int rc = fmk_dalloc(ctx, &fp->level_offsets, nb + 1);
-    if (!rc) {
-        cudaMemsetAsync(fp->level_offsets, 0, 8, ctx->stream);
-        rc = device_inclusive_scan<int64_t>(ctx, LevelsIn{lh.p, lh.p + nb, tick}, OffOut{fp->level_offsets}, nb, (int64_t *)nullptr);
-    }
     int64_t total = 0;
-    if (!rc) {
-        cudaError_t e = cudaMemcpyAsync(&total, fp->level_offsets + nb, 8, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) rc = fmk_fail(ctx, FMK_ERR_CUDA, cudaGetErrorString(e));
-    }
+    if (!rc) rc = fp_offsets(ctx, nb, lh.p, lh.p + nb, tick, fp->level_offsets, &total);
     fp->n_levels = total;
     if (!rc) rc = fmk_dalloc(ctx, &fp->price_levels, total);
     if (!rc) rc = fmk_dalloc(ctx, &fp->buy_vol, total);
@@ -1202,28 +1172,9 @@ extern "C" int fmk_bar_footprints(fmk_ctx *ctx, const fmk_trades *t, const fmk_i
     if (!rc) rc = fmk_dalloc(ctx, &fp->run_signed, nb);
     if (!rc) rc = fmk_dalloc(ctx, &fp->vp_skew, nb);
     if (!rc) rc = fmk_dalloc(ctx, &fp->vp_gini, nb);
+    if (!rc) rc = fp_fill(ctx, t, ix, lh.p, tick, factor, fp, err.p);
+    if (!rc) rc = fp_check_err(ctx, err.p);
     if (rc) { fmk_footprint_free(ctx, fp); return rc; }
-    int64_t blocks = cdiv(nb, 8);
-    int64_t maxb = (int64_t)ctx->sm_count * 64;
-    if (blocks > maxb) blocks = maxb;
-    auto launch = [&]() -> int {
-        FMK_LAUNCH(ctx, k_bar_footprint, (unsigned)blocks, 256, 0, t->price, t->amount, t->side, ix->close_idx, nb, lh.p, tick,
-                   fp->level_offsets, fp->price_levels, fp->buy_vol, fp->sell_vol, fp->buy_ticks, fp->sell_ticks, err.p);
-        FMK_LAUNCH(ctx, k_footprint_features, (unsigned)cdiv(nb, FF_WARPS * 32), FF_WARPS * 32, 0, fp->level_offsets, nb, fp->price_levels,
-                   fp->buy_vol, fp->sell_vol, factor, fp->buy_imb, fp->sell_imb, fp->buy_imb_sum, fp->sell_imb_sum, fp->cot,
-                   fp->run_signed, fp->vp_skew, fp->vp_gini);
-        return FMK_OK;
-    };
-    rc = launch();
-    if (rc) { fmk_footprint_free(ctx, fp); return rc; }
-    int herr = 0;
-    cudaError_t e = cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { fmk_footprint_free(ctx, fp); return fmk_fail(ctx, FMK_ERR_CUDA, cudaGetErrorString(e)); }
-    if (herr) {
-        fmk_footprint_free(ctx, fp);
-        return fmk_fail(ctx, FMK_ERR_LEVEL, "Something went wrong! Invalid price level index!");
-    }
     *out = fp;
     return FMK_OK;
 }
@@ -1234,6 +1185,7 @@ extern "C" int fmk_footprint_download(fmk_ctx *ctx, const fmk_footprint *fp, int
                                       uint8_t *sell_imbalances, uint16_t *buy_imb_sum, uint16_t *sell_imb_sum,
                                       int32_t *cot_price_level, int16_t *imb_max_run_signed, double *vp_skew,
                                       double *vp_gini) {
+    FMK_ENTER(ctx);
     const int64_t nb = fp->n_bars, nl = fp->n_levels;
     FMK_TRY(d2h(ctx, level_offsets, fp->level_offsets, nb + 1));
     FMK_TRY(d2h(ctx, price_levels, fp->price_levels, nl));
@@ -1244,5 +1196,184 @@ extern "C" int fmk_footprint_download(fmk_ctx *ctx, const fmk_footprint *fp, int
     FMK_TRY(d2h(ctx, cot_price_level, fp->cot, nb)); FMK_TRY(d2h(ctx, imb_max_run_signed, fp->run_signed, nb));
     FMK_TRY(d2h(ctx, vp_skew, fp->vp_skew, nb)); FMK_TRY(d2h(ctx, vp_gini, fp->vp_gini, nb));
     FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device-resident bar frame: build_ohlcv + build_directional_features + build_trade_size_features + build_footprints
+// (bar/base.py:132-300) against one index, every output column kept on the device (fmk.h: fmk_frame).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_copy_theta(const double *__restrict__ med, int64_t nb, double *__restrict__ theta) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nb) theta[i] = med[i];
+}
+
+extern "C" void fmk_frame_free(fmk_ctx *ctx, fmk_frame *f) {
+    if (!f) return;
+    FMK_ENTER(ctx);
+    fmk_dfree(ctx, f->bar_block);
+    fmk_dfree(ctx, f->level_block);
+    delete f;
+}
+
+extern "C" int fmk_frame_info(const fmk_frame *f, int64_t *n_bars, int64_t *n_levels, int64_t *bar_block_bytes,
+                              int64_t *level_block_bytes, int64_t *col_offsets) {
+    if (n_bars) *n_bars = f->n_bars;
+    if (n_levels) *n_levels = f->n_levels;
+    if (bar_block_bytes) *bar_block_bytes = f->bar_bytes;
+    if (level_block_bytes) *level_block_bytes = f->level_bytes;
+    if (col_offsets) for (int k = 0; k < FMK_COL_COUNT; k++) col_offsets[k] = f->col_off[k];
+    return FMK_OK;
+}
+
+extern "C" int fmk_frame_devptrs(const fmk_frame *f, void **bar_block, void **level_block) {
+    if (bar_block) *bar_block = f->bar_block;
+    if (level_block) *level_block = f->level_block;
+    return FMK_OK;
+}
+
+extern "C" int fmk_frame_download(fmk_ctx *ctx, const fmk_frame *f, void *bar_block_host, void *level_block_host) {
+    FMK_ENTER(ctx);
+    if (bar_block_host && f->bar_bytes > 0)
+        FMK_CUDA(ctx, cudaMemcpyAsync(bar_block_host, f->bar_block, (size_t)f->bar_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (level_block_host && f->level_bytes > 0)
+        FMK_CUDA(ctx, cudaMemcpyAsync(level_block_host, f->level_block, (size_t)f->level_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMK_OK;
+}
+
+static inline int64_t frame_put(int64_t &cur, int64_t bytes) {
+    const int64_t o = cur;
+    cur += (bytes + 15) / 16 * 16;
+    return o;
+}
+
+extern "C" int fmk_bar_features_device(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, int flags,
+                                       const double *theta, int64_t n_theta, double theta_mult, double tick,
+                                       double factor, fmk_frame **out) {
+    FMK_ENTER(ctx);
+    *out = nullptr;
+    FMK_TRY(check_index(ctx, t, ix));
+    const int64_t nb = ix->m - 1;
+    const bool want_ohlcv = flags & FMK_F_OHLCV, want_med = flags & FMK_F_MEDIAN, want_dir = flags & FMK_F_DIRECTIONAL,
+               want_ts = flags & FMK_F_TRADE_SIZE, want_fp = flags & FMK_F_FOOTPRINT;
+    if (want_med && !want_ohlcv) return fmk_fail(ctx, FMK_ERR_ARG, "FMK_F_MEDIAN needs FMK_F_OHLCV");
+    if ((want_dir || want_fp) && !t->side) return fmk_fail(ctx, FMK_ERR_ARG, "trades have no 'side' column");
+    if (want_fp && !want_ohlcv) return fmk_fail(ctx, FMK_ERR_ARG, "FMK_F_FOOTPRINT needs FMK_F_OHLCV (bar lows / highs)");
+    if (want_fp && !(tick > 0)) return fmk_fail(ctx, FMK_ERR_ARG, "price_tick_size must be positive");
+    if (want_ts && theta && n_theta != nb)
+        return fmk_fail(ctx, FMK_ERR_ARG, "Theta should match the the number of bars (len(bar_close_indices) - 1).");
+    if (want_ts && !theta && !want_med) return fmk_fail(ctx, FMK_ERR_ARG, "theta == NULL needs FMK_F_MEDIAN");
+
+    fmk_frame *f = new (std::nothrow) fmk_frame();
+    if (!f) return FMK_ERR_ALLOC;
+    memset(f, 0, sizeof(*f));
+    f->n_bars = nb; f->flags = flags;
+    for (int k = 0; k < FMK_COL_COUNT; k++) f->col_off[k] = -1;
+    int64_t cur = 0;
+    if (ix->close_ts) f->col_off[FMK_COL_CLOSE_TS] = frame_put(cur, nb * 8);
+    f->col_off[FMK_COL_CLOSE_IDX] = frame_put(cur, nb * 8);
+    if (want_ohlcv) {
+        for (int k = FMK_COL_OPEN; k <= FMK_COL_VWAP; k++) f->col_off[k] = frame_put(cur, nb * 8);
+        if (want_med) f->col_off[FMK_COL_MEDIAN] = frame_put(cur, nb * 8);
+        f->col_off[FMK_COL_TRADES] = frame_put(cur, nb * 8);
+        f->col_off[FMK_COL_VOLUME] = frame_put(cur, nb * 4);
+    }
+    if (want_dir) {
+        for (int k = FMK_COL_TICKS_BUY; k <= FMK_COL_CUM_TICKS_MAX; k++) f->col_off[k] = frame_put(cur, nb * 8);
+        for (int k = FMK_COL_VOLUME_BUY; k <= FMK_COL_CUM_DOLLARS_MAX; k++) f->col_off[k] = frame_put(cur, nb * 4);
+    }
+    if (want_ts) for (int k = FMK_COL_MEAN_SIZE_REL; k <= FMK_COL_SIZE_GINI; k++) f->col_off[k] = frame_put(cur, nb * 4);
+    if (want_fp) {
+        f->col_off[FMK_COL_FP_LEVEL_OFFSETS] = frame_put(cur, (nb + 1) * 8);
+        f->col_off[FMK_COL_FP_VP_SKEW] = frame_put(cur, nb * 8);
+        f->col_off[FMK_COL_FP_VP_GINI] = frame_put(cur, nb * 8);
+        f->col_off[FMK_COL_FP_COT] = frame_put(cur, nb * 4);
+        f->col_off[FMK_COL_FP_BUY_IMB_SUM] = frame_put(cur, nb * 2);
+        f->col_off[FMK_COL_FP_SELL_IMB_SUM] = frame_put(cur, nb * 2);
+        f->col_off[FMK_COL_FP_RUN_SIGNED] = frame_put(cur, nb * 2);
+    }
+    f->bar_bytes = cur;
+    int rc = fmk_dalloc(ctx, &f->bar_block, cur);
+    if (rc) { delete f; return rc; }
+    char *B = f->bar_block;
+#define COLP(T, id) ((T *)(B + f->col_off[id]))
+    auto body = [&]() -> int {
+        if (ix->close_ts)
+            FMK_CUDA(ctx, cudaMemcpyAsync(COLP(int64_t, FMK_COL_CLOSE_TS), ix->close_ts + 1, (size_t)nb * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        FMK_CUDA(ctx, cudaMemcpyAsync(COLP(int64_t, FMK_COL_CLOSE_IDX), ix->close_idx + 1, (size_t)nb * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (want_ohlcv) {
+            OhlcvOut o{COLP(double, FMK_COL_OPEN), COLP(double, FMK_COL_HIGH), COLP(double, FMK_COL_LOW), COLP(double, FMK_COL_CLOSE),
+                       COLP(double, FMK_COL_VWAP), COLP(float, FMK_COL_VOLUME), COLP(int64_t, FMK_COL_TRADES)};
+            FMK_TRY(run_ohlcv(ctx, t, ix, o, want_med ? COLP(double, FMK_COL_MEDIAN) : nullptr));
+        }
+        if (want_dir) {
+            DirOut o{COLP(int64_t, FMK_COL_TICKS_BUY), COLP(int64_t, FMK_COL_TICKS_SELL), COLP(float, FMK_COL_VOLUME_BUY),
+                     COLP(float, FMK_COL_VOLUME_SELL), COLP(float, FMK_COL_DOLLARS_BUY), COLP(float, FMK_COL_DOLLARS_SELL),
+                     COLP(float, FMK_COL_MEAN_SPREAD), COLP(float, FMK_COL_MAX_SPREAD), COLP(int64_t, FMK_COL_CUM_TICKS_MIN),
+                     COLP(int64_t, FMK_COL_CUM_TICKS_MAX), COLP(float, FMK_COL_CUM_VOLUME_MIN), COLP(float, FMK_COL_CUM_VOLUME_MAX),
+                     COLP(float, FMK_COL_CUM_DOLLARS_MIN), COLP(float, FMK_COL_CUM_DOLLARS_MAX)};
+            int64_t blocks = cdiv(nb, 8);
+            const int64_t maxb = (int64_t)ctx->sm_count * 64;
+            if (blocks > maxb) blocks = maxb;
+            FMK_LAUNCH(ctx, k_bar_directional, (unsigned)blocks, 256, 0, t->price, t->amount, t->side, ix->close_idx, nb, t->n, o);
+        }
+        if (want_ts) {
+            Scratch<double> d(ctx);
+            FMK_TRY(d.alloc(2 * nb));
+            if (theta) FMK_CUDA(ctx, cudaMemcpyAsync(d.p, theta, (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+            else FMK_LAUNCH(ctx, k_copy_theta, (unsigned)cdiv(nb, 256), 256, 0, (const double *)COLP(double, FMK_COL_MEDIAN), nb, d.p);
+            FMK_TRY(launch_order_stats(ctx, t->amount, ix->close_idx, nb, 2, nullptr, d.p + nb));
+            int64_t blocks = cdiv(nb, 8);
+            const int64_t maxb = (int64_t)ctx->sm_count * 64;
+            if (blocks > maxb) blocks = maxb;
+            FMK_LAUNCH(ctx, k_bar_trade_size, (unsigned)blocks, 256, 0, t->amount, (const double *)d.p, ix->close_idx, nb, theta_mult,
+                       (const double *)(d.p + nb), COLP(float, FMK_COL_MEAN_SIZE_REL), COLP(float, FMK_COL_SIZE_95_REL),
+                       COLP(float, FMK_COL_PCT_BLOCK), COLP(float, FMK_COL_SIZE_GINI));
+        }
+        if (want_fp) {
+            Scratch<int> err(ctx);
+            FMK_TRY(err.alloc(1));
+            FMK_CUDA(ctx, cudaMemsetAsync(err.p, 0, sizeof(int), ctx->stream));
+            int64_t total = 0;
+            FMK_TRY(fp_offsets(ctx, nb, COLP(double, FMK_COL_LOW), COLP(double, FMK_COL_HIGH), tick, COLP(int64_t, FMK_COL_FP_LEVEL_OFFSETS), &total));
+            f->n_levels = total;
+            int64_t lc = 0;
+            f->col_off[FMK_COL_FP_PRICE_LEVELS] = frame_put(lc, total * 4);
+            f->col_off[FMK_COL_FP_BUY_VOL] = frame_put(lc, total * 4);
+            f->col_off[FMK_COL_FP_SELL_VOL] = frame_put(lc, total * 4);
+            f->col_off[FMK_COL_FP_BUY_TICKS] = frame_put(lc, total * 4);
+            f->col_off[FMK_COL_FP_SELL_TICKS] = frame_put(lc, total * 4);
+            f->col_off[FMK_COL_FP_BUY_IMB] = frame_put(lc, total);
+            f->col_off[FMK_COL_FP_SELL_IMB] = frame_put(lc, total);
+            f->level_bytes = lc;
+            FMK_TRY(fmk_dalloc(ctx, &f->level_block, lc));
+            char *Lb = f->level_block;
+            fmk_footprint v;
+            memset(&v, 0, sizeof(v));
+            v.n_bars = nb; v.n_levels = total;
+            v.level_offsets = COLP(int64_t, FMK_COL_FP_LEVEL_OFFSETS);
+            v.price_levels = (int32_t *)(Lb + f->col_off[FMK_COL_FP_PRICE_LEVELS]);
+            v.buy_vol = (float *)(Lb + f->col_off[FMK_COL_FP_BUY_VOL]);
+            v.sell_vol = (float *)(Lb + f->col_off[FMK_COL_FP_SELL_VOL]);
+            v.buy_ticks = (int32_t *)(Lb + f->col_off[FMK_COL_FP_BUY_TICKS]);
+            v.sell_ticks = (int32_t *)(Lb + f->col_off[FMK_COL_FP_SELL_TICKS]);
+            v.buy_imb = (uint8_t *)(Lb + f->col_off[FMK_COL_FP_BUY_IMB]);
+            v.sell_imb = (uint8_t *)(Lb + f->col_off[FMK_COL_FP_SELL_IMB]);
+            v.buy_imb_sum = COLP(uint16_t, FMK_COL_FP_BUY_IMB_SUM);
+            v.sell_imb_sum = COLP(uint16_t, FMK_COL_FP_SELL_IMB_SUM);
+            v.cot = COLP(int32_t, FMK_COL_FP_COT);
+            v.run_signed = COLP(int16_t, FMK_COL_FP_RUN_SIGNED);
+            v.vp_skew = COLP(double, FMK_COL_FP_VP_SKEW);
+            v.vp_gini = COLP(double, FMK_COL_FP_VP_GINI);
+            FMK_TRY(fp_fill(ctx, t, ix, COLP(double, FMK_COL_LOW), tick, factor, &v, err.p));
+            FMK_TRY(fp_check_err(ctx, err.p));
+        }
+        return FMK_OK;
+    };
+#undef COLP
+    rc = body();
+    if (rc) { fmk_frame_free(ctx, f); return rc; }
+    *out = f;
     return FMK_OK;
 }

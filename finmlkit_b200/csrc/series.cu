@@ -47,7 +47,9 @@ __global__ void __launch_bounds__(LR_THREADS) k_lagged_returns(const int64_t *__
     const int64_t i0 = (int64_t)blockIdx.x * LR_TILE;
     const int64_t b0 = br[2 * (int64_t)blockIdx.x], b1 = br[2 * (int64_t)blockIdx.x + 1];
     const int64_t span = b1 - b0;                   // per-tick insertion points lie in [b0, b1]: they read ts[b0 .. b1 - 1]
-    const bool staged = span <= LR_STAGE;
+    // the halving steps below sum to LR_STAGE - 1, so a staged search can advance at most LR_STAGE - 1 positions: a span of
+    // exactly LR_STAGE (insertion point b1 = b0 + LR_STAGE for the block's last tick) must take the global-memory search
+    const bool staged = span < LR_STAGE;
     if (staged)
         for (int64_t q = threadIdx.x; q < span; q += LR_THREADS) ts_s[q] = (double)__ldg(ts + b0 + q);
     __syncthreads();
@@ -271,6 +273,7 @@ static int run_ewmst(fmk_ctx *ctx, const int64_t *ts, const double *y, int64_t n
 
 extern "C" int fmk_lagged_returns(fmk_ctx *ctx, const int64_t *ts, const double *close, int64_t n, double window_sec,
                                   int is_log, double *out) {
+    FMK_ENTER(ctx);
     if (!(window_sec > 0)) return fmk_fail(ctx, FMK_ERR_ARG, "The return window must be greater than zero.");
     Scratch<int64_t> dts(ctx);
     Scratch<double> dc(ctx), dout(ctx);
@@ -287,6 +290,7 @@ extern "C" int fmk_lagged_returns(fmk_ctx *ctx, const int64_t *ts, const double 
 
 extern "C" int fmk_ewmst(fmk_ctx *ctx, const int64_t *ts, const double *y, int64_t n, double half_life,
                          double sigma_floor, double *out) {
+    FMK_ENTER(ctx);
     Scratch<int64_t> dts(ctx);
     Scratch<double> dy(ctx), dout(ctx);
     FMK_TRY(dts.alloc(n)); FMK_TRY(dy.alloc(n)); FMK_TRY(dout.alloc(n));
@@ -301,6 +305,7 @@ extern "C" int fmk_ewmst(fmk_ctx *ctx, const int64_t *ts, const double *y, int64
 }
 
 extern "C" int fmk_lagged_returns_dev(fmk_ctx *ctx, const fmk_trades *t, double window_sec, int is_log, fmk_buf **out) {
+    FMK_ENTER(ctx);
     if (!t->ts) return fmk_fail(ctx, FMK_ERR_ARG, "lagged returns need the timestamp column on the device");
     FMK_TRY(fmk_buf_alloc(ctx, t->n * 8, out));
     int rc = run_lagged_returns(ctx, t->ts, t->price, t->n, window_sec, is_log, (double *)(*out)->ptr);
@@ -310,6 +315,7 @@ extern "C" int fmk_lagged_returns_dev(fmk_ctx *ctx, const fmk_trades *t, double 
 
 extern "C" int fmk_ewmst_dev(fmk_ctx *ctx, const fmk_trades *t, const fmk_buf *y, double half_life, double sigma_floor,
                              fmk_buf **out) {
+    FMK_ENTER(ctx);
     if (!t->ts) return fmk_fail(ctx, FMK_ERR_ARG, "ewmst needs the timestamp column on the device");
     if (y->bytes < t->n * 8) return fmk_fail(ctx, FMK_ERR_ARG, "y is shorter than the trades");
     FMK_TRY(fmk_buf_alloc(ctx, t->n * 8, out));
@@ -410,6 +416,7 @@ extern "C" int fmk_triple_barrier(fmk_ctx *ctx, const fmk_trades *t, const int64
                                   double vertical_barrier_s, double min_close_time_s, const int8_t *side,
                                   int64_t n_side, double min_ret, int8_t *labels, int64_t *touch_idx, double *rets,
                                   double *ratios) {
+    FMK_ENTER(ctx);
     if (vertical_barrier_s <= 0) return fmk_fail(ctx, FMK_ERR_ARG, "The vertical barrier must be greater than zero.");
     if (min_ret < 0) return fmk_fail(ctx, FMK_ERR_ARG, "The minimum return must be non-negative.");
     if (ne != n_targets) return fmk_fail(ctx, FMK_ERR_ARG, "The lengths of event_idxs and targets must match.");

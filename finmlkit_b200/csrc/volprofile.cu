@@ -248,6 +248,7 @@ extern "C" int fmk_volume_profile_rolling_fp(fmk_ctx *ctx, const fmk_footprint *
                                              const double *highs, const double *lows, double window_sec, int64_t n_bins,
                                              double price_tick, double va_pct, int32_t *poc, int32_t *hva, int32_t *lva,
                                              float *pct_above_poc) {
+    FMK_ENTER(ctx);
     return vp_run(ctx, fp->level_offsets, fp->price_levels, fp->buy_vol, fp->sell_vol, fp->n_bars, bar_ts, highs, lows,
                   window_sec, n_bins, price_tick, va_pct, poc, hva, lva, pct_above_poc);
 }
@@ -258,6 +259,7 @@ extern "C" int fmk_volume_profile_rolling(fmk_ctx *ctx, const int64_t *level_off
                                           const int64_t *bar_ts, const double *highs, const double *lows, double window_sec,
                                           int64_t n_bins, double price_tick, double va_pct, int32_t *poc, int32_t *hva,
                                           int32_t *lva, float *pct_above_poc) {
+    FMK_ENTER(ctx);
     if (n_bars <= 0) return fmk_fail(ctx, FMK_ERR_ARG, "Input arrays should have the same length and be non-empty.");
     const int64_t total = level_offsets[n_bars];
     Scratch<int64_t> doff(ctx);

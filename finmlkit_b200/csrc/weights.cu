@@ -253,6 +253,7 @@ static int normalize_weights(fmk_ctx *ctx, double *w, int64_t ne) {
 
 extern "C" int fmk_average_uniqueness(fmk_ctx *ctx, int64_t n, const int64_t *event_idx, const int64_t *touch_idx,
                                       int64_t n_events, int64_t n_touch, double *weights, int16_t *concurrency) {
+    FMK_ENTER(ctx);
     if (n_events != n_touch)
         return fmk_fail(ctx, FMK_ERR_ARG, "Timestamps and lookahead indices must have the same length.");
     return run_weights(ctx, n, nullptr, event_idx, touch_idx, n_events, nullptr, weights, nullptr, concurrency);
@@ -261,6 +262,7 @@ extern "C" int fmk_average_uniqueness(fmk_ctx *ctx, int64_t n, const int64_t *ev
 extern "C" int fmk_return_attribution(fmk_ctx *ctx, const int64_t *event_idx, const int64_t *touch_idx, int64_t n_events,
                                       const double *close, const int16_t *concurrency, int64_t n, int normalize,
                                       double *weights) {
+    FMK_ENTER(ctx);
     Scratch<double> dclose(ctx);
     FMK_TRY(dclose.alloc(n));
     FMK_CUDA(ctx, cudaMemcpyAsync(dclose.p, close, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -271,6 +273,7 @@ extern "C" int fmk_return_attribution(fmk_ctx *ctx, const int64_t *event_idx, co
 extern "C" int fmk_sample_weights(fmk_ctx *ctx, const fmk_trades *t, const int64_t *event_idx, const int64_t *touch_idx,
                                   int64_t n_events, int normalize, double *avg_uniqueness, double *return_attribution,
                                   int16_t *concurrency) {
+    FMK_ENTER(ctx);
     FMK_TRY(run_weights(ctx, t->n, t->price, event_idx, touch_idx, n_events, nullptr, avg_uniqueness, return_attribution,
                         concurrency));
     return (normalize && return_attribution) ? normalize_weights(ctx, return_attribution, n_events) : FMK_OK;

@@ -1,10 +1,29 @@
 """
-Multi-GPU plumbing (one process per GPU, `torch.distributed`): independent symbol streams are sharded one per rank --
-there is no cross-GPU dependency inside a symbol (the reference holds one symbol per TradesData) -- and the finished
-bar frames are collected on rank 0 with ONE gather per step.  Works on NCCL (device tensors) and gloo (CPU tensors;
-used by the world_size-2 CPU tests).
+Multi-GPU plumbing: one process per GPU, independent symbol streams sharded one per rank -- there is no cross-GPU
+dependency inside a symbol (the reference holds one symbol per TradesData) -- and ONE gather of the finished bar frames
+to rank 0 per step.  The collective is libfmk's own (csrc/comm.cu: ``ncclAllGather`` of exact byte counts + grouped
+``ncclSend`` / ``ncclRecv``, NCCL loaded with dlopen); nothing here imports torch.
+
+Bootstrap: NCCL needs its 128-byte unique id handed from rank 0 to the other ranks once.  Under ``torchrun`` the
+environment gives RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT; all ranks of this tier run on ONE node, so
+the id travels through a file in a shared temp directory keyed on the job (MASTER_PORT + TORCHELASTIC_RUN_ID), written
+atomically by rank 0 and polled by the others.
+
+The host-side framing (``pack_frame`` / ``unpack_frame`` / ``shard_symbols`` / ``gather_frames_with``) is backend-agnostic
+and is what the world_size-2 CPU tests drive through gloo (tests/test_parallel_gloo.py); the GPU path is ``Comm``.
 """
-from typing import List, Optional, Sequence
+import ctypes as C
+import os
+import struct
+import tempfile
+import time
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from . import core
+
+MAGIC = 0x464D4B46   # "FMKF"
 
 
 def shard_symbols(symbols: Sequence, rank: int, world: int) -> List:
@@ -12,102 +31,163 @@ def shard_symbols(symbols: Sequence, rank: int, world: int) -> List:
     return [s for k, s in enumerate(symbols) if k % world == rank]
 
 
-def gather_frames(frame, dst: int = 0) -> Optional[List]:
-    """Gather variable-length 1-D uint8 tensors (serialised bar frames) to ``dst``.
-
-    ``torch.distributed.gather`` needs equal sizes, so sizes are all-gathered first and frames are padded to the
-    maximum (NCCL has no gather-v; the payload is MBs against 900 GB/s links).  Returns the list of exact-size frames
-    on ``dst`` and None elsewhere."""
-    import torch
-    import torch.distributed as dist
-    world, rank = dist.get_world_size(), dist.get_rank()
-    n = frame.numel()
-    sizes = torch.zeros(world, dtype=torch.int64, device=frame.device)
-    dist.all_gather_into_tensor(sizes, torch.tensor([n], dtype=torch.int64, device=frame.device))
-    mx = int(sizes.max().item())
-    padded = torch.zeros(mx, dtype=torch.uint8, device=frame.device)
-    padded[:n] = frame
-    out = [torch.empty(mx, dtype=torch.uint8, device=frame.device) for _ in range(world)] if rank == dst else None
-    dist.gather(padded, out, dst=dst)
-    if rank != dst:
-        return None
-    return [out[r][: int(sizes[r].item())] for r in range(world)]
+# ---- framing: a bar frame = named columns -> one byte string (header + 16-byte aligned payloads) ----------------------
+def pack_frame(columns: dict) -> np.ndarray:
+    """{name: 1-D array} -> uint8 array: magic, n_cols, then per column (name, dtype, count, offset), then payloads."""
+    metas, payload, off = [], [], 0
+    for name, a in columns.items():
+        a = np.ascontiguousarray(a)
+        nb, ds = name.encode(), a.dtype.str.encode()
+        metas.append(struct.pack("<H", len(nb)) + nb + struct.pack("<H", len(ds)) + ds + struct.pack("<qq", a.size, off))
+        pad = (-a.nbytes) % 16
+        payload.append(a.view(np.uint8).reshape(-1))
+        if pad:
+            payload.append(np.zeros(pad, np.uint8))
+        off += a.nbytes + pad
+    head = struct.pack("<II", MAGIC, len(metas)) + b"".join(metas)
+    head += b"\0" * ((-len(head) - 8) % 16)
+    head = struct.pack("<q", len(head) + 8) + head
+    return np.concatenate([np.frombuffer(head, np.uint8)] + payload) if payload else np.frombuffer(head, np.uint8).copy()
 
 
-class PipelinedFrameGather:
-    """Gather of variable-length frames to ``dst``, one per step, OVERLAPPED with the next step's compute.
+def unpack_frame(buf) -> dict:
+    b = np.ascontiguousarray(buf, dtype=np.uint8)
+    raw = b.tobytes()
+    (hlen,) = struct.unpack_from("<q", raw, 0)
+    magic, ncols = struct.unpack_from("<II", raw, 8)
+    if magic != MAGIC:
+        raise ValueError("not a finmlkit_b200 bar frame")
+    p, out = 16, {}
+    for _ in range(ncols):
+        (ln,) = struct.unpack_from("<H", raw, p); p += 2
+        name = raw[p:p + ln].decode(); p += ln
+        (ld,) = struct.unpack_from("<H", raw, p); p += 2
+        dt = np.dtype(raw[p:p + ld].decode()); p += ld
+        cnt, off = struct.unpack_from("<qq", raw, p); p += 16
+        out[name] = np.frombuffer(raw, dtype=dt, count=cnt, offset=hlen + off)
+    return out
 
-    The frame of step k is copied (device to device, on the caller's stream) into one of two fixed-capacity staging
-    buffers -- 16-byte header carrying the exact length, then the payload -- and gathered on a separate communication
-    stream; the kernels of step k+1 run meanwhile.  A staging buffer is reused only after the gather that read it has
-    finished (event).  No size exchange and no host synchronisation per step: every rank sends ``capacity + 16`` bytes.
-    ``finish()`` makes the caller's stream wait for the outstanding gathers, so a timer stopped on that stream covers
-    them, and returns the exact-size frames of the last step on ``dst``.  CPU tensors (gloo) take a synchronous path."""
 
-    HDR = 16
+def gather_frames_with(frame: np.ndarray, rank: int, world: int, dst: int, allgather_i64: Callable, sendrecv: Callable):
+    """Gather-v of one uint8 frame per rank to ``dst`` in the collective's own shape: exchange the exact byte counts, then
+    point-to-point transfers of exactly that many bytes.  ``allgather_i64(x) -> list of world ints``;
+    ``sendrecv(buf_or_None, count, src, dst)`` moves ``count`` bytes from ``src`` to ``dst`` and returns the received array
+    on ``dst``.  Returns the list of frames on ``dst`` and None elsewhere."""
+    sizes = [int(x) for x in allgather_i64(int(frame.size))]
+    out = [None] * world
+    for r in range(world):
+        if r == dst:
+            if rank == dst:
+                out[r] = frame
+            continue
+        got = sendrecv(frame if rank == r else None, sizes[r], r, dst)
+        if rank == dst:
+            out[r] = got
+    return out if rank == dst else None
 
-    def __init__(self, frame, dst: int = 0, slack: float = 1.25):
-        import torch
-        import torch.distributed as dist
-        self.torch, self.dist, self.dst = torch, dist, dst
-        self.world, self.rank = dist.get_world_size(), dist.get_rank()
-        self.cuda = frame.device.type == "cuda"
-        cap = torch.tensor([int(frame.numel() * slack) + 1024], dtype=torch.int64, device=frame.device)
-        dist.all_reduce(cap, op=dist.ReduceOp.MAX)          # one agreement on the capacity, at construction
-        self.capacity = int(cap.item())
-        mk = lambda: torch.zeros(self.capacity + self.HDR, dtype=torch.uint8, device=frame.device)   # noqa: E731
-        self.buf = [mk(), mk()]
-        self.out = [[mk() for _ in range(self.world)] for _ in range(2)] if self.rank == dst else [None, None]
-        self.done = [None, None]
-        self.k = 0
-        self.last = None
-        import os
-        self.overlap = os.environ.get("FMK_GATHER_OVERLAP", "1") != "0"
-        self.comm = torch.cuda.Stream(frame.device) if (self.cuda and self.overlap) else None
 
-    def submit(self, frame):
-        torch, dist = self.torch, self.dist
-        n = frame.numel()
-        if n > self.capacity:
-            raise ValueError(f"frame of {n} bytes exceeds the agreed capacity {self.capacity}")
-        s = self.k & 1
-        if self.cuda:
-            main = torch.cuda.current_stream(frame.device)
-            if self.done[s] is not None:
-                main.wait_event(self.done[s])               # the gather that read this buffer two steps ago is finished
-            self.buf[s][:8].view(torch.int64).fill_(n)
-            self.buf[s][self.HDR:self.HDR + n].copy_(frame, non_blocking=True)
-            if self.comm is None:                           # same-stream variant: no overlap, no size exchange
-                dist.gather(self.buf[s], self.out[s], dst=self.dst)
-            else:
-                ready = torch.cuda.Event()
-                ready.record(main)
-                with torch.cuda.stream(self.comm):
-                    self.comm.wait_event(ready)
-                    dist.gather(self.buf[s], self.out[s], dst=self.dst)
-                    ev = torch.cuda.Event()
-                    ev.record(self.comm)
-                self.done[s] = ev
-        else:
-            self.buf[s][:8].view(torch.int64).fill_(n)
-            self.buf[s][self.HDR:self.HDR + n].copy_(frame)
-            dist.gather(self.buf[s], self.out[s], dst=self.dst)
-        self.last = s
-        self.k += 1
+# ---- the GPU path: libfmk's NCCL communicator ---------------------------------------------------------------------------
+def _store_path():
+    job = f"{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', 'none')}"
+    return os.path.join(os.environ.get("FMK_STORE_DIR", tempfile.gettempdir()), f"fmk_nccl_id_{os.getuid()}_{job}")
 
-    def finish(self):
-        """Wait (stream-ordered) for the outstanding gathers; on ``dst`` return the frames of the last step."""
-        torch = self.torch
-        if self.cuda:
-            main = torch.cuda.current_stream(self.buf[0].device)
-            for ev in self.done:
-                if ev is not None:
-                    main.wait_event(ev)
-        if self.rank != self.dst or self.last is None:
-            return None
-        frames = []
+
+def exchange_unique_id(rank: int, world: int, make_id: Callable[[], bytes], timeout_s: float = 300.0, path: str = None) -> bytes:
+    """Rank 0 creates the id and publishes it (atomic rename); the others poll for it.  The last reader removes the file."""
+    path = path or _store_path()
+    if rank == 0:
+        for stale in (path, path + ".acks"):
+            try:
+                os.remove(stale)
+            except FileNotFoundError:
+                pass
+        uid = make_id()
+        tmp = f"{path}.tmp{os.getpid()}"
+        with open(tmp, "wb") as f:
+            f.write(uid)
+        os.rename(tmp, path)
+        return uid
+    t0 = time.time()
+    while True:
+        try:
+            with open(path, "rb") as f:
+                uid = f.read()
+            if len(uid) == 128:
+                return uid
+        except FileNotFoundError:
+            pass
+        if time.time() - t0 > timeout_s:
+            raise TimeoutError(f"rank {rank}: no NCCL unique id at {path} after {timeout_s} s")
+        time.sleep(0.01)
+
+
+class Comm:
+    """libfmk's communicator on a Context's device (one per process).  ``Comm.from_env(ctx)`` reads torchrun's variables."""
+
+    def __init__(self, ctx: core.Context, rank: int, world: int, uid: bytes, max_ctas: int = 4):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        L = ctx._L
+        h = C.c_void_p()
+        buf = C.create_string_buffer(uid, 128)
+        ctx.check(L.fmk_comm_init(ctx.h, buf, rank, world, int(max_ctas), C.byref(h)))
+        self.h = h
+        self._L = L
+
+    @classmethod
+    def from_env(cls, ctx: core.Context, max_ctas: int = 4):
+        rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+        L = ctx._L
+
+        def make_id():
+            b = C.create_string_buffer(128)
+            if L.fmk_comm_unique_id(b) != 0:
+                raise core.FmkError("ncclGetUniqueId failed (libnccl.so.2 missing?)")
+            return b.raw
+        uid = exchange_unique_id(rank, world, make_id)
+        c = cls(ctx, rank, world, uid, max_ctas)
+        c.barrier()
+        if rank == 0:
+            try:
+                os.remove(_store_path())
+            except OSError:
+                pass
+        return c
+
+    def barrier(self):
+        self.ctx.check(self._L.fmk_comm_barrier(self.h))
+
+    def allreduce(self, values, op="max"):
+        a = np.ascontiguousarray(values, dtype=np.float64).reshape(-1).copy()
+        self.ctx.check(self._L.fmk_comm_allreduce_f64(self.h, a.ctypes.data_as(C.c_void_p), len(a), {"max": 0, "min": 1, "sum": 2}[op]))
+        return a
+
+    def gather_submit(self, segments, dst=0):
+        """segments: [(device pointer, bytes)] valid on the ctx stream; returns at once (overlaps the next step)."""
+        n = len(segments)
+        ptrs = (C.c_void_p * max(n, 1))(*[C.c_void_p(p) for p, _ in segments])
+        sizes = (C.c_int64 * max(n, 1))(*[int(b) for _, b in segments])
+        self.ctx.check(self._L.fmk_comm_gather_submit(self.h, ptrs, sizes, n, int(dst)))
+
+    def gather_finish(self):
+        self.ctx.check(self._L.fmk_comm_gather_finish(self.h))
+
+    def gathered_bytes(self):
+        """exact byte count of every rank's frame in the last finished gather"""
+        out = []
         for r in range(self.world):
-            o = self.out[self.last][r]
-            n = int(o[:8].view(torch.int64).item())
-            frames.append(o[self.HDR:self.HDR + n])
-        return frames
+            p, b = C.c_void_p(), C.c_int64()
+            self.ctx.check(self._L.fmk_comm_gather_result(self.h, r, C.byref(p), C.byref(b)))
+            out.append(int(b.value))
+        return out
+
+    def gathered_frame(self, r) -> Optional[np.ndarray]:
+        """host copy of rank r's frame of the last step (destination rank only)"""
+        n = self.gathered_bytes()[r]
+        out = np.empty(n, np.uint8)
+        self.ctx.check(self._L.fmk_comm_gather_download(self.h, r, out.ctypes.data_as(C.c_void_p), n))
+        return out
+
+    def destroy(self):
+        if self.h:
+            self._L.fmk_comm_destroy(self.h)
+            self.h = None

@@ -65,6 +65,10 @@ void fmk_host_free(void *p);
  * array (ts[close_idx]), which saves a third of the H2D traffic; time/CUSUM bars, lagged returns, ewmst and TBM need ts. */
 int fmk_trades_upload(fmk_ctx *ctx, const int64_t *ts, const double *price, const double *amount, const int8_t *side,
                       int64_t n, fmk_trades **out);
+/* Same with float32 amounts (TradesData after the reference's split-trade merge holds float32 amounts,
+ * bar/data_model.py:326-344): 4 B/tick over PCIe, widened exactly to float64 on the device. */
+int fmk_trades_upload_f32amt(fmk_ctx *ctx, const int64_t *ts, const double *price, const float *amount, const int8_t *side,
+                             int64_t n, fmk_trades **out);
 /* Device-side synthetic BTCUSDT-like stream (SURVEY 8d shape) for bench-size runs. */
 int fmk_trades_synth(fmk_ctx *ctx, int64_t n, uint64_t seed, fmk_trades **out);
 /* Re-fill an existing handle from host arrays (async H2D on the ctx stream; arrays should be pinned). */
@@ -81,6 +85,9 @@ int fmk_buf_download(fmk_ctx *ctx, const fmk_buf *b, void *host, int64_t bytes);
 int64_t fmk_buf_bytes(const fmk_buf *b);
 void *fmk_buf_devptr(const fmk_buf *b);
 void fmk_buf_free(fmk_ctx *ctx, fmk_buf *b);
+/* out[k] = src[idx[k]] for m host indices into a device array of 8-byte elements (negative indices wrap like NumPy);
+ * e.g. CUSUMBarKit.get_sigma, bar/kit.py:176-181 (sigma[bar_close_indices]) without downloading sigma. */
+int fmk_buf_gather8(fmk_ctx *ctx, const fmk_buf *src, const int64_t *idx, int64_t m, void *out);
 
 /* ---- bar indexers (bar/logic.py) -> device index handle ----------------------------------------------------------
  * close_idx follows the reference exactly: element 0 is the "open" marker (-1 possible for time bars). */
@@ -123,6 +130,72 @@ int fmk_footprint_download(fmk_ctx *ctx, const fmk_footprint *fp, int64_t *level
                            uint16_t *sell_imb_sum, int32_t *cot_price_level, int16_t *imb_max_run_signed,
                            double *vp_skew, double *vp_gini);
 void fmk_footprint_free(fmk_ctx *ctx, fmk_footprint *fp);
+
+/* ---- device-resident bar frame: every per-bar output of BarBuilderBase (bar/base.py:132-300) in one pass ------------
+ * build_ohlcv + build_directional_features + build_trade_size_features + build_footprints against one index, results
+ * kept on the device in two blocks (per-bar columns, per-level CSR columns) so that a host can download them with two
+ * copies or hand them to fmk_comm_gather_submit.  flags select the feature groups; FMK_F_FOOTPRINT needs FMK_F_OHLCV
+ * (bar lows / highs are taken from the OHLCV columns on the device, base.py:257-259) and FMK_F_TRADE_SIZE with
+ * theta == NULL uses each bar's own median trade size as theta (needs FMK_F_MEDIAN). */
+typedef struct fmk_frame fmk_frame;
+enum {
+    FMK_F_OHLCV = 1, FMK_F_MEDIAN = 2, FMK_F_DIRECTIONAL = 4, FMK_F_TRADE_SIZE = 8, FMK_F_FOOTPRINT = 16
+};
+typedef enum {
+    /* per-bar block */
+    FMK_COL_CLOSE_TS = 0, FMK_COL_CLOSE_IDX,                                                  /* i64 */
+    FMK_COL_OPEN, FMK_COL_HIGH, FMK_COL_LOW, FMK_COL_CLOSE, FMK_COL_VWAP, FMK_COL_MEDIAN,     /* f64 */
+    FMK_COL_TRADES,                                                                           /* i64 */
+    FMK_COL_VOLUME,                                                                           /* f32 */
+    FMK_COL_TICKS_BUY, FMK_COL_TICKS_SELL, FMK_COL_CUM_TICKS_MIN, FMK_COL_CUM_TICKS_MAX,      /* i64 */
+    FMK_COL_VOLUME_BUY, FMK_COL_VOLUME_SELL, FMK_COL_DOLLARS_BUY, FMK_COL_DOLLARS_SELL, FMK_COL_MEAN_SPREAD,
+    FMK_COL_MAX_SPREAD, FMK_COL_CUM_VOLUME_MIN, FMK_COL_CUM_VOLUME_MAX, FMK_COL_CUM_DOLLARS_MIN,
+    FMK_COL_CUM_DOLLARS_MAX,                                                                  /* f32 */
+    FMK_COL_MEAN_SIZE_REL, FMK_COL_SIZE_95_REL, FMK_COL_PCT_BLOCK, FMK_COL_SIZE_GINI,         /* f32 */
+    FMK_COL_FP_LEVEL_OFFSETS,                                                                 /* i64[n_bars + 1] */
+    FMK_COL_FP_VP_SKEW, FMK_COL_FP_VP_GINI,                                                   /* f64 */
+    FMK_COL_FP_COT,                                                                           /* i32 */
+    FMK_COL_FP_BUY_IMB_SUM, FMK_COL_FP_SELL_IMB_SUM,                                          /* u16 */
+    FMK_COL_FP_RUN_SIGNED,                                                                    /* i16 */
+    /* per-level block (CSR rows) */
+    FMK_COL_FP_PRICE_LEVELS,                                                                  /* i32 */
+    FMK_COL_FP_BUY_VOL, FMK_COL_FP_SELL_VOL,                                                  /* f32 */
+    FMK_COL_FP_BUY_TICKS, FMK_COL_FP_SELL_TICKS,                                              /* i32 */
+    FMK_COL_FP_BUY_IMB, FMK_COL_FP_SELL_IMB,                                                  /* u8 */
+    FMK_COL_COUNT
+} fmk_col;
+int fmk_bar_features_device(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, int flags, const double *theta,
+                            int64_t n_theta, double theta_mult, double price_tick_size, double imbalance_factor,
+                            fmk_frame **out);
+/* n_bars, n_levels, byte sizes of the two blocks, and col_offsets[FMK_COL_COUNT] (byte offset of each column inside its
+ * block, -1 when the column is absent) */
+int fmk_frame_info(const fmk_frame *f, int64_t *n_bars, int64_t *n_levels, int64_t *bar_block_bytes,
+                   int64_t *level_block_bytes, int64_t *col_offsets);
+int fmk_frame_devptrs(const fmk_frame *f, void **bar_block, void **level_block);
+/* either host pointer may be NULL */
+int fmk_frame_download(fmk_ctx *ctx, const fmk_frame *f, void *bar_block_host, void *level_block_host);
+void fmk_frame_free(fmk_ctx *ctx, fmk_frame *f);
+
+/* ---- multi-GPU: one gather-v of the finished frames to one rank over NCCL ------------------
+ * One process per GPU.  Rank 0 calls fmk_comm_unique_id and hands the 128 bytes to the other ranks (any side channel);
+ * every rank then calls fmk_comm_init with its own ctx.  libnccl.so.2 is loaded with dlopen at that point.
+ * max_ctas > 0 caps the SMs NCCL may occupy.  A gather step packs up to 8 device segments into this rank's frame and
+ * sends exactly that many bytes (ncclAllGather of the byte counts, then grouped ncclSend / ncclRecv); the transfer of
+ * step k overlaps the kernels of step k+1.  fmk_comm_gather_finish makes the ctx stream wait for all transfers. */
+typedef struct fmk_comm fmk_comm;
+int fmk_comm_unique_id(void *out128);
+int fmk_comm_init(fmk_ctx *ctx, const void *id128, int rank, int world, int max_ctas, fmk_comm **out);
+void fmk_comm_destroy(fmk_comm *c);
+int fmk_comm_rank(const fmk_comm *c);
+int fmk_comm_world(const fmk_comm *c);
+int fmk_comm_nccl_version(void);
+int fmk_comm_barrier(fmk_comm *c);
+/* op: 0 = max, 1 = min, 2 = sum over ranks of n <= 64 host doubles (in place) */
+int fmk_comm_allreduce_f64(fmk_comm *c, double *inout, int n, int op);
+int fmk_comm_gather_submit(fmk_comm *c, const void *const *seg_ptrs, const int64_t *seg_bytes, int nseg, int dst);
+int fmk_comm_gather_finish(fmk_comm *c);
+int fmk_comm_gather_result(fmk_comm *c, int rank, void **dev_ptr, int64_t *bytes);
+int fmk_comm_gather_download(fmk_comm *c, int rank, void *host, int64_t cap);
 
 /* ---- tick-level series (feature/core) --------------------------------------------------------------------------- */
 /* comp_lagged_returns, feature/core/utils.py:12-64: host in / host out */

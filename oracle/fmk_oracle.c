@@ -216,9 +216,35 @@ int64_t fmko_cusum_bar_indexer(const int64_t *ts, const double *p, double *sigma
     return m;
 }
 
-static int cmp_double(const void *a, const void *b) {
-    double x = *(const double *)a, y = *(const double *)b;
-    return (x > y) - (x < y);
+/* nth_element (quickselect, median-of-three pivot, insertion sort on short ranges): after the call a[k] holds the k-th
+ * order statistic, a[0..k) <= a[k] <= a(k..n).  Numba's np.median / np.percentile are selections too (introselect in
+ * numba/np/arraymath.py); an order statistic does not depend on the algorithm, so any exact selection is a faithful
+ * restatement -- and, unlike the qsort this replaced, it costs what the reference's costs (bench cpu_baseline). */
+static void nth_element_f64(double *a, int64_t n, int64_t k) {
+    int64_t lo = 0, hi = n - 1;
+    while (hi - lo > 16) {
+        int64_t mid = lo + ((hi - lo) >> 1);
+        double x = a[lo], y = a[mid], z = a[hi], t;
+        if (y < x) { t = x; x = y; y = t; }
+        if (z < y) { t = y; y = z; z = t; if (y < x) { t = x; x = y; y = t; } }
+        a[lo] = x; a[mid] = y; a[hi] = z;
+        const double pv = y;
+        int64_t i = lo, j = hi;
+        for (;;) {
+            do i++; while (a[i] < pv);
+            do j--; while (a[j] > pv);
+            if (i >= j) break;
+            t = a[i]; a[i] = a[j]; a[j] = t;
+        }
+        /* a[lo..j] <= pv <= a[j+1..hi] */
+        if (k <= j) hi = j; else lo = j + 1;
+    }
+    for (int64_t i = lo + 1; i <= hi; i++) {
+        double x = a[i];
+        int64_t j = i - 1;
+        while (j >= lo && a[j] > x) { a[j + 1] = a[j]; j--; }
+        a[j + 1] = x;
+    }
 }
 
 /* ---- a7: bar/base.py:306-407 comp_bar_ohlcv ------------------------------------------------- */
@@ -255,9 +281,12 @@ int fmko_bar_ohlcv(const double *p, const double *v, int64_t n, int64_t nv, cons
         vwap[i] = tv > 0 ? td / tv : 0.0;
         trades[i] = cnt;
         if (cnt > 0) {
-            qsort(sizes, (size_t)cnt, sizeof(double), cmp_double);
-            if ((cnt & 1) == 0) median[i] = (sizes[cnt / 2 - 1] + sizes[cnt / 2]) / 2;  /* numba _median_inner */
-            else median[i] = sizes[cnt / 2];
+            nth_element_f64(sizes, cnt, cnt / 2);
+            if ((cnt & 1) == 0) {                                   /* numba _median_inner: (a[n/2-1] + a[n/2]) / 2 */
+                double lowmid = sizes[0];
+                for (int64_t q = 1; q < cnt / 2; q++) if (sizes[q] > lowmid) lowmid = sizes[q];
+                median[i] = (lowmid + sizes[cnt / 2]) / 2;
+            } else median[i] = sizes[cnt / 2];
         } else median[i] = 0.0;
         free(sizes);
     }
@@ -345,11 +374,15 @@ int fmko_bar_trade_size(const double *a, int64_t n, const double *theta, int64_t
         else {
             double *tmp = (double *)malloc(sizeof(double) * (size_t)cnt);
             memcpy(tmp, ab, sizeof(double) * (size_t)cnt);
-            qsort(tmp, (size_t)cnt, sizeof(double), cmp_double);
             double rank = 1 + (double)(cnt - 1) * (95.0 / 100.0);
             double f = floor(rank), m = rank - f;
             int64_t k = (int64_t)(f - 1);
-            double lower = tmp[k], upper = tmp[k + 1 < cnt ? k + 1 : k];
+            nth_element_f64(tmp, cnt, k);
+            double lower = tmp[k], upper = tmp[k];
+            if (k + 1 < cnt) {                                      /* (k+1)-th statistic = min of the right part */
+                upper = tmp[k + 1];
+                for (int64_t q = k + 2; q < cnt; q++) if (tmp[q] < upper) upper = tmp[q];
+            }
             pv = lower * (1 - m) + upper * m;
             free(tmp);
         }

@@ -15,7 +15,9 @@ def _run(args, env=None):
 
 
 def test_reference_arm_prints_one_json_line():
-    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--ticks", "2e5", "--cpu-sample", "2e5"])
+    # the C port (declared fallback) keeps this test fast: the Numba arm pays ~30 s of JIT (covered by the next test)
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--ticks", "2e5", "--cpu-sample", "2e5", "--cpu-sub-sample", "2e5"],
+             env={"FMK_BENCH_FORCE_PORT": "1"})
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.split("\n") if l.strip()]
     assert len(lines) == 1
@@ -28,10 +30,27 @@ def test_reference_arm_prints_one_json_line():
     assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
+    # every BASELINE config the CPU can run is in the line
+    for k in ("config1", "config3", "config4", "time_bars_1min"):
+        assert k in d, k
+    assert d["config3"]["value"] > 0 and d["config4"]["value"] > 0 and d["config1"]["kernels"]["value"] > 0
+
+
+def test_reference_arm_times_the_real_reference_when_installed():
+    """baseline/_ref (scripts/install_ref.sh) holds the unmodified finmlkit: the arm must then time Numba, not the port."""
+    import pytest
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "finmlkit")):
+        pytest.skip("baseline/_ref not installed here")
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--ticks", "2e5", "--cpu-sample", "2e5", "--no-sub"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.split("\n") if l.strip()][0])
+    assert d["cpu_baseline"]["kind"] == "reference" and "Numba" in d["cpu_baseline"]["impl"]
+    assert d["e2e"]["value"] == d["value"] > 0
 
 
 def test_reference_arm_other_ranks_are_silent():
-    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--ticks", "2e5", "--cpu-sample", "2e5"], env={"RANK": "1", "WORLD_SIZE": "2"})
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--ticks", "2e5", "--cpu-sample", "2e5", "--no-sub"],
+             env={"RANK": "1", "WORLD_SIZE": "2"})
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 

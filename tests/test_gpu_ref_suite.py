@@ -1,0 +1,57 @@
+"""GPU: the reference's OWN test files (copied next to the installed reference by scripts/install_ref.sh -- never committed)
+run against the drop-in: `finmlkit_b200.dropin.install()` rebinds the reference's hot-path functions and kits to the GPU
+implementations and the reference's unmodified tests must pass.  One pytest process per file, like the reference's
+local_test.sh:57-65.  KNOWN lists the reference tests that cannot pass against any implementation other than the Numba
+build itself, each with the reason."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_TESTS = os.path.join(ROOT, "baseline", "_ref", "ref_tests")
+
+FILES = [
+    "bars/test_comp_ohlcv.py", "bars/test_comp_bar_directional_features.py", "bars/test_comp_bar_footprints.py",
+    "bars/test_footprint_features.py", "bars/test_bar_trade_size_features.py", "bars/test_time_bar_indexer.py",
+    "bars/test_bar_builder_footprints.py", "bars/test_utils.py",
+    "labels/test_triple_barrier.py", "labels/test_average_uniqueness.py", "labels/test_return_attribution.py",
+    "labels/test_label_concurrency.py",
+    "features/test_vpin.py", "features/test_realized_volatility.py", "features/test_ewms.py", "features/test_core_utils.py",
+    "features/test_compute_returns.py", "features/test_volume_profile_rolling.py", "features/test_compose_pipeline.py",
+    "sampling/test_cusum_filter.py",
+]
+
+# reference test id -> why it is allowed to fail here
+KNOWN = {
+}
+
+
+def _run(rel):
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests"), ROOT, os.path.join(ROOT, "baseline", "_ref"), env.get("PYTHONPATH", "")])
+    env["FMK_CONSOLE_LOGGER_LEVEL"] = "ERROR"
+    cmd = [sys.executable, "-m", "pytest", "-p", "ref_suite_plugin", "-p", "no:cacheprovider", "-q", "-rf", "--tb=short",
+           os.path.join(REF_TESTS, rel)]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd="/tmp", timeout=1200)
+    out = r.stdout + r.stderr
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "ref_suite_" + rel.replace("/", "_") + ".log"), "w") as f:
+        f.write(out)
+    failed = re.findall(r"^FAILED (\S+)", out, flags=re.M)
+    m = re.search(r"(\d+) passed", out)
+    return r.returncode, int(m.group(1)) if m else 0, failed, out
+
+
+@pytest.mark.parametrize("rel", FILES)
+def test_reference_test_file_passes_on_the_dropin(rel):
+    if not os.path.isfile(os.path.join(REF_TESTS, rel)):
+        pytest.skip("baseline/_ref/ref_tests absent (scripts/install_ref.sh copies the reference's tests where /root/reference exists)")
+    rc, passed, failed, out = _run(rel)
+    assert "reference bindings rebound" in out and " 0 reference bindings" not in out, out[-1500:]
+    unexpected = [f for f in failed if f.split("ref_tests/")[-1] not in KNOWN]
+    assert passed > 0, out[-3000:]
+    assert not unexpected, f"{len(unexpected)} reference tests fail on the drop-in:\n" + "\n".join(unexpected) + "\n" + out[-4000:]

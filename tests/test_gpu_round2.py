@@ -1,0 +1,220 @@
+"""GPU: round-2 additions -- the device-resident bar frame, float32 amount ingest, device gathers, index validation, the
+lagged-returns bracket edge (span == staging size), NaN volumes in flow acceleration, and libfmk's NCCL communicator."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import assert_exact, assert_f64, check_directional, check_footprint_csr, check_ohlcv, check_trade_size
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _stream(n=200_000, seed=11):
+    from finmlkit_b200.synth import synth_trades
+    return synth_trades(n, seed=seed)
+
+
+def test_lagged_returns_bracket_span_equals_stage(ctx):
+    """a 1024-tick block whose bracket [b0, b1] spans exactly 4096 staged timestamps -- the block's last tick
+    has its insertion point at b1 = b0 + 4096, one more than the halving steps 2048..1 can reach."""
+    from finmlkit_b200 import core
+    dense = np.arange(20480, dtype=np.int64)                                   # 1 ns apart
+    blk = 30000 + np.round(np.linspace(0, 4096, 1024)).astype(np.int64)       # one aligned block spanning 4096 ns
+    tail = blk[-1] + 5 + np.arange(700, dtype=np.int64) * 3
+    ts = np.concatenate([dense, blk, tail])
+    px = 100.0 + np.cumsum(np.random.default_rng(3).normal(0, 0.01, len(ts)))
+    w_sec = 2e-5
+    w = w_sec * 1e9
+    tf = ts.astype(np.float64)
+    b0 = np.searchsorted(tf, tf[20480] - w, "right")
+    b1 = np.searchsorted(tf, tf[20480 + 1023] - w, "right")
+    assert b1 - b0 == 4096, (b0, b1)                                           # the case the test is about
+    for is_log in (True, False):
+        got = core.lagged_returns(ts, px, w_sec, is_log, ctx=ctx)
+        ref = oracle.comp_lagged_returns(ts, px, w_sec, is_log)
+        assert_f64(got, ref, f"lagged returns span 4096 log={is_log}", rtol=1e-12, atol=1e-15)
+    # and the neighbouring spans (4095, 4097) for good measure
+    for extra in (-1, 1):
+        blk2 = 30000 + np.round(np.linspace(0, 4096 + extra, 1024)).astype(np.int64)
+        ts2 = np.concatenate([dense, blk2, blk2[-1] + 5 + np.arange(700, dtype=np.int64) * 3])
+        assert_f64(core.lagged_returns(ts2, px, w_sec, True, ctx=ctx), oracle.comp_lagged_returns(ts2, px, w_sec, True),
+                   f"span {4096 + extra}", rtol=1e-12, atol=1e-15)
+
+
+def test_flow_acceleration_nan_poisons_later_bars(ctx):
+    """comp_flow_acceleration (volume.py:572-607) has no NaN handling -- a NaN volume makes every later output NaN."""
+    from finmlkit_b200.feature.core.volume import comp_flow_acceleration
+    v = np.abs(np.random.default_rng(5).normal(10, 2, 5000))
+    v[1234] = np.nan
+    got = comp_flow_acceleration(v, 20, 5, ctx=ctx)
+    ref = oracle.comp_flow_acceleration(v, 20, 5)
+    assert np.isnan(got[1234:]).all() and np.isfinite(got[19:1234]).all()
+    assert_f64(got, ref, "flow acceleration with a NaN volume")
+
+
+def test_caller_indices_are_validated(ctx):
+    """comp_bar_* with an index >= n, < -1 or a decreasing pair must raise, not read out of bounds."""
+    from finmlkit_b200.bar.base import comp_bar_directional_features, comp_bar_ohlcv
+    ts, px, qty, side = _stream(5000)
+    for bad in ([0, 100, 5000], [-2, 10, 20], [0, 300, 200, 400]):
+        with pytest.raises(ValueError):
+            comp_bar_ohlcv(px, qty, np.array(bad, np.int64), ctx=ctx)
+        with pytest.raises(ValueError):
+            comp_bar_directional_features(px, qty, np.array(bad, np.int64), side, ctx=ctx)
+    # -1 (time bars) and repeated indices (empty bars) are legal
+    o = comp_bar_ohlcv(px, qty, np.array([-1, 10, 10, 4999], np.int64), ctx=ctx)
+    check_ohlcv(o, oracle.comp_bar_ohlcv(px, qty, np.array([-1, 10, 10, 4999], np.int64)), "legal indices")
+    # the context is still healthy afterwards
+    ctx.sync()
+
+
+def test_float32_amount_upload(ctx):
+    """TradesData after the reference's split-trade merge holds float32 amounts (data_model.py:326-344): they cross PCIe as
+    float32 and every result equals the float64 path on the widened values."""
+    from finmlkit_b200 import core
+    ts, px, qty, side = _stream(120_000)
+    q32 = qty.astype(np.float32)
+    tr = core.DeviceTrades.upload(ts, px, q32, side, ctx=ctx)
+    back = tr.download()
+    assert back[2].dtype == np.float64 and np.array_equal(back[2], q32.astype(np.float64))
+    q64 = q32.astype(np.float64)
+    ix = core.dollar_bar_index(tr, 2e5)
+    ref = oracle.dollar_bar_indexer(px, q64, 2e5)
+    assert_exact(ix.download()[1], ref, "dollar idx on float32 amounts")
+    check_ohlcv(core.bar_ohlcv(tr, ix), oracle.comp_bar_ohlcv(px, q64, ref), "ohlcv on float32 amounts")
+
+
+def test_buf_gather(ctx):
+    from finmlkit_b200 import core
+    x = np.random.default_rng(1).normal(size=10_000)
+    b = core.DeviceBuf.upload(ctx, x)
+    idx = np.array([0, 9999, 17, 17, 4242, -1], np.int64)
+    assert np.array_equal(b.gather(idx), x[idx])
+    assert len(b.gather(np.zeros(0, np.int64))) == 0
+
+
+@pytest.mark.parametrize("kind", ["dollar", "volume", "time"])
+def test_frame_equals_the_individual_builders(ctx, kind):
+    """fmk_bar_features_device = build_ohlcv + build_directional_features + build_trade_size_features + build_footprints in
+    one call with every column kept on the device: bit-identical to the one-at-a-time C-ABI calls, and parity with the oracle."""
+    from finmlkit_b200 import core
+    ts, px, qty, side = _stream(300_000, seed=21)
+    side[::97] = 0                                                # some side-0 ticks
+    tr = core.DeviceTrades.upload(ts, px, qty, side, ctx=ctx)
+    ix = {"dollar": lambda: core.dollar_bar_index(tr, 1.5e5), "volume": lambda: core.volume_bar_index(tr, 4.0),
+          "time": lambda: core.time_bar_index(tr, 60.0)}[kind]()
+    cts, cidx = ix.download()
+    fr = core.bar_features_device(tr, ix, core.F_ALL, theta=None, theta_mult=5.0, price_tick_size=0.1, imbalance_factor=3.0)
+    c = fr.download()
+    nb = len(cidx) - 1
+    assert fr.n_bars == nb and np.array_equal(c["close_idx"], cidx[1:]) and np.array_equal(c["close_ts"], cts[1:])
+    o = core.bar_ohlcv(tr, ix)
+    for k, name in enumerate(["open", "high", "low", "close", "volume", "vwap", "trades", "median_trade_size"]):
+        assert_exact(c[name], o[k], f"frame.{name}")
+    d = core.bar_directional(tr, ix)
+    names = ["ticks_buy", "ticks_sell", "volume_buy", "volume_sell", "dollars_buy", "dollars_sell", "mean_spread", "max_spread",
+             "cum_ticks_min", "cum_ticks_max", "cum_volume_min", "cum_volume_max", "cum_dollars_min", "cum_dollars_max"]
+    for k, name in enumerate(names):
+        assert_exact(c[name], d[k], f"frame.{name}")
+    t = core.bar_trade_size(tr, ix, o[7], 5.0)
+    for k, name in enumerate(["mean_size_rel", "size_95_rel", "pct_block", "size_gini"]):
+        assert_exact(c[name], t[k], f"frame.{name}")
+    f = core.bar_footprints_csr(tr, ix, 0.1, o[2], o[1], 3.0)
+    fnames = ["fp_level_offsets", "fp_price_levels", "fp_buy_vol", "fp_sell_vol", "fp_buy_ticks", "fp_sell_ticks", "fp_buy_imb",
+              "fp_sell_imb", "fp_buy_imb_sum", "fp_sell_imb_sum", "fp_cot", "fp_run_signed", "fp_vp_skew", "fp_vp_gini"]
+    for k, name in enumerate(fnames):
+        assert_exact(c[name], f[k], f"frame.{name}")
+    # and against the oracle (the reference's own evaluation order)
+    check_ohlcv(o, oracle.comp_bar_ohlcv(px, qty, cidx), kind)
+    check_directional(d, oracle.comp_bar_directional_features(px, qty, cidx, side), kind)
+    check_trade_size(t, oracle.comp_bar_trade_size_features(qty, o[7], cidx, 5.0), kind)
+    fo = oracle.comp_bar_footprints_csr(px, qty, cidx, side, 0.1, o[2], o[1], 3.0)
+    check_footprint_csr(f, fo[0], list(fo[1:]), float(np.max(np.abs(fo[1]))), kind)
+    # partial frames: absent columns are absent, present ones unchanged
+    fr2 = core.bar_features_device(tr, ix, core.F_OHLCV)
+    c2 = fr2.download()
+    assert "median_trade_size" not in c2 and "ticks_buy" not in c2 and fr2.level_bytes == 0
+    assert_exact(c2["high"], o[1], "partial frame high")
+    with pytest.raises(ValueError):
+        core.bar_features_device(tr, ix, core.F_FOOTPRINT)      # needs OHLCV for the lows / highs
+
+
+def test_trade_size_tolerance_is_one_ulp(ctx):
+    """the trade-size features are float64 computations cast to float32 -> within ONE float32 ulp."""
+    from finmlkit_b200 import core
+    from helpers import assert_f32_ulp
+    ts, px, qty, side = _stream(400_000, seed=33)
+    tr = core.DeviceTrades.upload(ts, px, qty, side, ctx=ctx)
+    for T in (2e4, 2e5, 3e6):
+        ix = core.dollar_bar_index(tr, T)
+        cidx = ix.download()[1]
+        theta = oracle.comp_bar_ohlcv(px, qty, cidx)[7]
+        got = core.bar_trade_size(tr, ix, theta, 5.0)
+        ref = oracle.comp_bar_trade_size_features(qty, theta, cidx, 5.0)
+        for k in range(4):
+            assert_f32_ulp(got[k], ref[k], f"T={T} tsize[{k}]", ulps=1)
+
+
+def _frame_bytes(core, ctx, fr):
+    bar = np.zeros((fr.bar_bytes + 15) // 16 * 16, np.uint8)
+    lvl = np.zeros((fr.level_bytes + 15) // 16 * 16, np.uint8)
+    ctx.check(ctx._L.fmk_frame_download(ctx.h, fr.h, bar.ctypes.data_as(__import__("ctypes").c_void_p),
+                                        lvl.ctypes.data_as(__import__("ctypes").c_void_p) if fr.level_bytes else None))
+    return np.concatenate([bar, lvl]) if fr.level_bytes else bar
+
+
+def test_comm_single_rank_gather(ctx):
+    """libfmk's communicator with world = 1 (NCCL loaded with dlopen, no torch): the gathered frame on rank 0 is byte for
+    byte the packed frame, across pipelined steps of changing size."""
+    import ctypes as C
+    from finmlkit_b200 import core
+    from finmlkit_b200.parallel import Comm
+    L = ctx._L
+    uid = C.create_string_buffer(128)
+    assert L.fmk_comm_unique_id(uid) == 0 and L.fmk_comm_nccl_version() > 20000
+    comm = Comm(ctx, 0, 1, uid.raw, max_ctas=4)
+    try:
+        comm.barrier()
+        assert np.array_equal(comm.allreduce([1.5, -2.0], "max"), [1.5, -2.0])
+        ts, px, qty, side = _stream(150_000, seed=5)
+        tr = core.DeviceTrades.upload(ts, px, qty, side, ctx=ctx)
+        expect = None
+        for T in (1e5, 3e5, 5e4):
+            ix = core.dollar_bar_index(tr, T)
+            fr = core.bar_features_device(tr, ix, core.F_ALL, price_tick_size=0.1)
+            expect = _frame_bytes(core, ctx, fr)
+            comm.gather_submit(fr.segments(), dst=0)
+            del fr, ix
+        comm.gather_finish()
+        ctx.sync()
+        got = comm.gathered_frame(0)
+        assert comm.gathered_bytes() == [len(expect)]
+        assert np.array_equal(got, expect)
+    finally:
+        comm.destroy()
+
+
+def test_comm_two_ranks_gather_equals_each_ranks_frame(tmp_path):
+    """world = 2 on two GPUs (skipped on a one-GPU box; run with `gpurun --gpus 2`): rank 0 receives exactly the bytes rank 1
+    packed, for frames of different sizes, with the transfer of step k overlapping step k+1."""
+    from finmlkit_b200 import _lib
+    if _lib.lib().fmk_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    env = dict(os.environ)
+    env.update({"WORLD_SIZE": "2", "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": "29617", "FMK_STORE_DIR": str(tmp_path),
+                "FMK_COMM_TEST_DIR": str(tmp_path)})
+    procs = []
+    for r in range(2):
+        e = dict(env)
+        e.update({"RANK": str(r), "LOCAL_RANK": str(r)})
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_comm_worker.py")], env=e,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for r, p in enumerate(procs):
+        assert p.returncode == 0, f"rank {r}:\n{outs[r][-3000:]}"
+    assert "GATHER_OK" in outs[0]
