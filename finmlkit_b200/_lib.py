@@ -25,6 +25,7 @@ SIGNATURES = {
     "fmk_result_cols": (INT, [P, C.POINTER(P), C.POINTER(I64), C.POINTER(I64)]),
     "fmk_last_error": (C.c_char_p, [P]),
     "fmk_ctx_sync": (INT, [P]),
+    "fmk_ctx_trim": (INT, [P]),
     "fmk_timer_start": (INT, [P]),
     "fmk_timer_stop": (INT, [P, C.POINTER(C.c_float)]),
     "fmk_launch_count": (I64, [P]),
@@ -50,6 +51,7 @@ SIGNATURES = {
     "fmk_volume_bar_index": (INT, [P, P, F64, C.POINTER(P)]),
     "fmk_dollar_bar_index": (INT, [P, P, F64, C.POINTER(P)]),
     "fmk_cusum_bar_index": (INT, [P, P, P, F64, F64, C.POINTER(P)]),
+    "fmk_imbalance_bar_index": (INT, [P, P, F64, INT, INT, C.POINTER(P)]),
     "fmk_index_from_host": (INT, [P, P, P, I64, C.POINTER(P)]),
     "fmk_index_size": (I64, [P]),
     "fmk_index_download": (INT, [P, P, P, P]),

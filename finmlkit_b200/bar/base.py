@@ -50,12 +50,18 @@ def comp_bar_trade_size_features(amounts, theta, bar_close_indices, theta_mult, 
     if len(theta) != len(bar_close_indices) - 1:
         raise ValueError("Theta should match the the number of bars (len(bar_close_indices) - 1).")
     tr = _device_trades(None, amounts, ctx=ctx)
-    return core.bar_trade_size(tr, core.DeviceIndex.from_host(tr, bar_close_indices), theta, theta_mult)
+    # the reference takes each bar as the SLICE amounts[start:end + 1] (base.py:585), and Python slices clamp: a close index
+    # of len(amounts) -- the reference's own tests use one -- means "through the last trade"
+    idx = np.minimum(np.asarray(bar_close_indices, dtype=np.int64), len(amounts) - 1)
+    return core.bar_trade_size(tr, core.DeviceIndex.from_host(tr, idx), theta, theta_mult)
 
 
 def comp_bar_footprints(prices, amounts, bar_close_indices, trade_sides, price_tick_size, bar_lows, bar_highs,
                         imbalance_factor, ctx=None):
     """base.py:615-752 -> 7 ragged lists (one array per bar) + 6 per-bar arrays, in the reference's order."""
+    if len(bar_close_indices) < 2:       # no bars: the reference's loop does not run and every output is empty (base.py:676)
+        e = lambda dt: np.zeros(0, dt)   # noqa: E731
+        return ([], [], [], [], [], [], [], e(np.uint16), e(np.uint16), e(np.int32), e(np.int16), e(np.float64), e(np.float64))
     tr = _device_trades(prices, amounts, np.asarray(trade_sides).astype(np.int8), ctx=ctx)
     csr = core.bar_footprints_csr(tr, core.DeviceIndex.from_host(tr, bar_close_indices), price_tick_size, bar_lows,
                                   bar_highs, imbalance_factor)

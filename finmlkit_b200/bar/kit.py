@@ -83,3 +83,26 @@ class CUSUMBarKit(BarBuilderBase):
 
     def get_sigma(self):
         return self._sigma[self.bar_close_indices]
+
+
+class ImbalanceBarKit(BarBuilderBase):
+    """Tick-imbalance bars: ``ImbalanceBarKit(trades, threshold)``.  The reference imports ``_imbalance_bar_indexer`` in
+    bar/kit.py:5 but has no kit and the indexer is a stub (logic.py:224-241) -- own semantics, **parity unpinned**: ``b_t`` is
+    the ``side`` column when the trades carry one (``use_side``), else the tick rule on the prices."""
+
+    _kind = 0
+
+    def __init__(self, trades, threshold: float, use_side: bool = True, ctx=None):
+        super().__init__(trades, ctx)
+        self.threshold = threshold
+        self.use_side = use_side
+
+    def _comp_bar_close(self):
+        self._dev_index = core.imbalance_bar_index(self._device(), self.threshold, self.use_side, self._kind)
+        return self._download_index()
+
+
+class RunBarKit(ImbalanceBarKit):
+    """Tick-run bars (stub in the reference, logic.py:244-261) -- own semantics, **parity unpinned**."""
+
+    _kind = 1

@@ -53,11 +53,27 @@ def _cusum_bar_indexer(timestamps, prices, sigma, sigma_floor, sigma_mult, ctx=N
     return idx
 
 
-def _imbalance_bar_indexer(timestamps, prices, volumes, threshold):
-    """logic.py:224-241: not implemented in the reference either."""
-    raise NotImplementedError("Imbalance bar indexer is not implemented yet.")
+def _imbalance_bar_indexer(timestamps, prices, volumes, threshold, sides=None, ctx=None):
+    """Tick-imbalance bars.  The reference's function is a stub that raises ``NotImplementedError`` (logic.py:224-241), so the
+    semantics here are this package's own and are checked only against its own CPU oracle (**parity unpinned**):
+    ``b_t`` = ``sides`` when given, else the tick rule on ``prices`` (the reference's ``comp_trade_side_vector``,
+    bar/utils.py:12-46); the list starts with index 0 like logic.py:73-84; the bar closes at the first tick with
+    ``|sum of b_t since the previous close| >= threshold`` and the sum restarts from 0 (AFML 2.3.2.1 with a fixed expected
+    imbalance; the stub's signature ``(timestamps, prices, volumes, threshold)`` is kept, ``volumes`` is not read)."""
+    return _signed_tick_bars(timestamps, prices, threshold, sides, 0, ctx)
 
 
-def _run_bar_indexer(timestamps, prices, volumes, threshold):
-    """logic.py:244-261: not implemented in the reference either."""
-    raise NotImplementedError("Run bar indexer is not implemented yet.")
+def _run_bar_indexer(timestamps, prices, volumes, threshold, sides=None, ctx=None):
+    """Tick-run bars (stub in the reference, logic.py:244-261; own semantics, **parity unpinned**): buys and sells are counted
+    since the previous close and the bar closes at the first tick with ``max(#buys, #sells) >= threshold`` (AFML 2.3.2.2 with
+    a fixed expected run length)."""
+    return _signed_tick_bars(timestamps, prices, threshold, sides, 1, ctx)
+
+
+def _signed_tick_bars(timestamps, prices, threshold, sides, kind, ctx):
+    if len(timestamps) != len(prices):
+        raise ValueError("Prices and timestamps arrays must have the same length.")
+    n = len(prices)
+    tr = core.DeviceTrades.upload(timestamps, prices, np.zeros(n, np.float64),
+                                  np.asarray(sides).astype(np.int8) if sides is not None else None, ctx=ctx)
+    return core.imbalance_bar_index(tr, threshold, use_side=sides is not None, kind=kind).download()[1]

@@ -242,6 +242,11 @@ def cusum_bar_index(trades: DeviceTrades, sigma: DeviceBuf, sigma_floor: float, 
     return _mk_index(trades, trades.ctx._L.fmk_cusum_bar_index, sigma.h, float(sigma_floor), float(sigma_mult))
 
 
+def imbalance_bar_index(trades: DeviceTrades, threshold: float, use_side: bool = True, kind: int = 0) -> DeviceIndex:
+    """tick-imbalance (kind 0) / tick-run (kind 1) bars -- own semantics, parity unpinned (include/fmk.h)"""
+    return _mk_index(trades, trades.ctx._L.fmk_imbalance_bar_index, float(threshold), int(bool(use_side)), int(kind))
+
+
 # ---- per-bar reductions ---------------------------------------------------------------------------------------------
 def bar_ohlcv(trades: DeviceTrades, index: DeviceIndex, median=True, out=None):
     """(open, high, low, close, volume f32, vwap, trades i64, median) -- tuple order of comp_bar_ohlcv (base.py:407).

@@ -28,6 +28,9 @@ static int ctx_create(int device, void *ext_stream, int use_ext, fmk_ctx **out) 
     ctx->device = device;
     ctx->prof = new std::vector<fmk_prof_rec>();
     ctx->ev_pool = new std::vector<cudaEvent_t>();
+    ctx->cache_free = new std::vector<std::pair<void *, size_t>>();
+    ctx->cache_live = new std::unordered_map<void *, size_t>();
+    ctx->cache_free_cap = (int64_t)48 << 30;
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return FMK_ERR_CUDA; }
     if (use_ext) { ctx->stream = (cudaStream_t)ext_stream; ctx->owns_stream = 0; }
     else {
@@ -37,6 +40,10 @@ static int ctx_create(int device, void *ext_stream, int use_ext, fmk_ctx **out) 
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    {
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && tot > 0) ctx->cache_free_cap = (int64_t)(tot / 2);
+    }
     // keep freed blocks in the stream-ordered pool: scratch allocation inside a step must not hit the driver
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -55,6 +62,10 @@ void fmk_ctx_destroy(fmk_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->res_cols) cudaFree(ctx->res_cols);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    fmk_cache_trim(ctx);
+    for (auto &kv : *ctx->cache_live) cudaFree(kv.first);      // handles the caller never freed
+    delete ctx->cache_free;
+    delete ctx->cache_live;
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     for (auto &r : *ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -134,6 +145,13 @@ int fmk_result_cols(fmk_ctx *ctx, void **ptr, int64_t *n_bars, int64_t *bytes) {
 int fmk_index_stats(fmk_ctx *ctx, int64_t *s) {
     FMK_ENTER(ctx);
     s[0] = ctx->stats[0]; s[1] = ctx->stats[1]; s[2] = ctx->stats[2];
+    return FMK_OK;
+}
+
+// gives the cached large scratch blocks back to the driver (they are otherwise kept for the next call of the same size)
+int fmk_ctx_trim(fmk_ctx *ctx) {
+    FMK_ENTER(ctx);
+    fmk_cache_trim(ctx);
     return FMK_OK;
 }
 

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include "../../include/fmk.h"
 
@@ -28,6 +29,11 @@ struct fmk_ctx {
     std::vector<fmk_prof_rec> *prof;
     std::vector<cudaEvent_t> *ev_pool;
     int64_t res_nb;                       // number of bars held in res_cols
+    // large-block cache (see fmk_dalloc): free blocks and the sizes of the live ones
+    std::vector<std::pair<void *, size_t>> *cache_free;
+    std::unordered_map<void *, size_t> *cache_live;
+    int64_t cache_bytes;                  // bytes held by the cache (free + live)
+    int64_t cache_free_bytes, cache_free_cap;   // free-list total and its cap (half the device memory): oldest blocks go first
 };
 
 static inline cudaEvent_t fmk_prof_event(fmk_ctx *ctx) {
@@ -131,15 +137,82 @@ static inline int fmk_fail(fmk_ctx *ctx, int code, const char *msg) {
         FMK_CUDA((ctx), cudaGetLastError());                                             \
     } while (0)
 
-template <typename T>
-static inline int fmk_dalloc(fmk_ctx *ctx, T **p, int64_t count) {
+// Device scratch.  Small blocks come from the stream-ordered pool (cudaMallocAsync, release threshold = infinity).  LARGE
+// blocks (column-sized scratch: prefix sums, next[] tables, r / lambda series, CSR blocks -- gigabytes at 1e9 ticks) are kept in
+// a per-context cache instead: measured on B200, the pool re-maps physical pages between virtual ranges when differently
+// sized multi-GB blocks are freed and re-allocated, which stalled single steps by 40 - 900 ms.  A step asks for the same sizes
+// in the same order every time, so after the first step every request is an exact-size hit.  Everything of a context runs on
+// one stream, so handing a freed block to a later request needs no synchronisation (stream order is reuse order).
+constexpr size_t FMK_CACHE_MIN_BYTES = (size_t)4 << 20;
+
+static inline void fmk_cache_trim(fmk_ctx *ctx) {
+    if (!ctx->cache_free || ctx->cache_free->empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &b : *ctx->cache_free) { cudaFree(b.first); ctx->cache_bytes -= (int64_t)b.second; }
+    ctx->cache_free->clear();
+    ctx->cache_free_bytes = 0;
+}
+
+static inline int fmk_dalloc_bytes(fmk_ctx *ctx, void **p, size_t bytes) {
     *p = nullptr;
-    if (count <= 0) count = 1;
-    FMK_CUDA(ctx, cudaMallocAsync((void **)p, (size_t)count * sizeof(T), ctx->stream));
+    if (bytes < FMK_CACHE_MIN_BYTES || !ctx->cache_free) {
+        FMK_CUDA(ctx, cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream));
+        return FMK_OK;
+    }
+    auto &fr = *ctx->cache_free;
+    int best = -1;
+    for (int k = 0; k < (int)fr.size(); k++)
+        if (fr[k].second >= bytes && fr[k].second <= bytes + bytes / 4 + ((size_t)1 << 20) && (best < 0 || fr[k].second < fr[best].second)) best = k;
+    if (best >= 0) {
+        *p = fr[best].first;
+        (*ctx->cache_live)[*p] = fr[best].second;
+        ctx->cache_free_bytes -= (int64_t)fr[best].second;
+        fr.erase(fr.begin() + best);
+        return FMK_OK;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {            // out of memory: give the cached blocks back to the driver and retry once
+        cudaGetLastError();
+        fmk_cache_trim(ctx);
+        e = cudaMalloc(p, bytes);
+    }
+    if (e != cudaSuccess) {
+        char b[200];
+        snprintf(b, sizeof(b), "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return fmk_fail(ctx, FMK_ERR_ALLOC, b);
+    }
+    (*ctx->cache_live)[*p] = bytes;
+    ctx->cache_bytes += (int64_t)bytes;
     return FMK_OK;
 }
+
+template <typename T>
+static inline int fmk_dalloc(fmk_ctx *ctx, T **p, int64_t count) {
+    if (count <= 0) count = 1;
+    return fmk_dalloc_bytes(ctx, (void **)p, (size_t)count * sizeof(T));
+}
 static inline void fmk_dfree(fmk_ctx *ctx, void *p) {
-    if (p) cudaFreeAsync(p, ctx->stream);
+    if (!p) return;
+    if (ctx->cache_live) {
+        auto it = ctx->cache_live->find(p);
+        if (it != ctx->cache_live->end()) {
+            ctx->cache_free->push_back({p, it->second});
+            ctx->cache_free_bytes += (int64_t)it->second;
+            ctx->cache_live->erase(it);
+            // the free list is capped: workloads that keep changing sizes must not hoard the device (oldest blocks go first)
+            while (ctx->cache_free_bytes > ctx->cache_free_cap && ctx->cache_free->size() > 1) {
+                auto b = ctx->cache_free->front();
+                cudaStreamSynchronize(ctx->stream);
+                cudaFree(b.first);
+                ctx->cache_bytes -= (int64_t)b.second;
+                ctx->cache_free_bytes -= (int64_t)b.second;
+                ctx->cache_free->erase(ctx->cache_free->begin());
+            }
+            return;
+        }
+    }
+    cudaFreeAsync(p, ctx->stream);
 }
 // RAII scratch buffer freed (stream-ordered) at scope exit
 template <typename T>

@@ -32,6 +32,12 @@ struct SideOut {
     __device__ void operator()(int64_t i, const SideC &c) const { s[i] = (int8_t)c.v; }
 };
 
+// tick rule on a device-resident price column (used by the imbalance / run bar indexers)
+int fmk_tick_rule_device(fmk_ctx *ctx, const double *price_dev, int64_t n, int8_t *sides_dev) {
+    if (n <= 0) return FMK_OK;
+    return device_inclusive_scan<SideC>(ctx, SideIn{price_dev}, SideOut{sides_dev}, n, (SideC *)nullptr);
+}
+
 extern "C" int fmk_trade_side_vector(fmk_ctx *ctx, const double *prices, int64_t n, int8_t *sides_out) {
     FMK_ENTER(ctx);
     if (n <= 0) return FMK_OK;

@@ -209,18 +209,28 @@ __global__ void __launch_bounds__(EW_THREADS) k_ewm_reduce(const int64_t *__rest
     if (threadIdx.x == 0) tile_f[blockIdx.x] = tot;
 }
 
-// single block: in-place exclusive scan of tile composites
+// single block: in-place exclusive scan of tile composites.  Each thread owns EWT_ITEMS consecutive composites, so one
+// block-scan round covers 4096 tiles (1e9 ticks are 488k tiles: 120 rounds instead of 1900)
+constexpr int EWT_ITEMS = 16;
 __global__ void __launch_bounds__(EW_THREADS) k_ewm_tiles(Ewm *tile_f, int64_t ntiles) {
     __shared__ Ewm carry;
     if (threadIdx.x == 0) carry = ewm_identity();
     __syncthreads();
-    for (int64_t b = 0; b < ntiles; b += EW_THREADS) {
-        const int64_t k = b + threadIdx.x;
-        Ewm x = k < ntiles ? tile_f[k] : ewm_identity();
+    for (int64_t b = 0; b < ntiles; b += (int64_t)EW_THREADS * EWT_ITEMS) {
+        const int64_t k0 = b + (int64_t)threadIdx.x * EWT_ITEMS;
+        Ewm x = ewm_identity();
+        for (int q = 0; q < EWT_ITEMS; q++)
+            if (k0 + q < ntiles) x = ewm_compose(x, tile_f[k0 + q]);
         Ewm tot;
         Ewm ex = ew_block_excl(x, &tot);
-        Ewm c = carry;
-        if (k < ntiles) tile_f[k] = ewm_compose(c, ex);
+        const Ewm c = carry;
+        Ewm run = ewm_compose(c, ex);
+        for (int q = 0; q < EWT_ITEMS; q++)
+            if (k0 + q < ntiles) {
+                const Ewm t = tile_f[k0 + q];
+                tile_f[k0 + q] = run;
+                run = ewm_compose(run, t);
+            }
         __syncthreads();
         if (threadIdx.x == 0) carry = ewm_compose(c, tot);
         __syncthreads();

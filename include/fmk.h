@@ -43,6 +43,8 @@ int fmk_ctx_create_on_stream(int device, void *stream, fmk_ctx **out);
 void fmk_ctx_destroy(fmk_ctx *ctx);
 const char *fmk_last_error(fmk_ctx *ctx);
 int fmk_ctx_sync(fmk_ctx *ctx);
+/* Large device scratch blocks are cached per ctx between calls (a repeated build never allocates); this releases them. */
+int fmk_ctx_trim(fmk_ctx *ctx);
 /* CUDA-event timer on the ctx stream (the stream every kernel of this ctx is launched on). */
 int fmk_timer_start(fmk_ctx *ctx);
 int fmk_timer_stop(fmk_ctx *ctx, float *ms_out);
@@ -98,6 +100,12 @@ int fmk_dollar_bar_index(fmk_ctx *ctx, const fmk_trades *t, double threshold, fm
 /* sigma: device f64[n] buffer; it is forward-filled in place like the reference (logic.py:181-189). */
 int fmk_cusum_bar_index(fmk_ctx *ctx, const fmk_trades *t, fmk_buf *sigma, double sigma_floor, double sigma_mult,
                         fmk_index **out);                                                             /* logic.py:152-221 */
+/* Tick-imbalance (kind 0) / tick-run (kind 1) bars.  The reference only has stubs (logic.py:224-261 raise
+ * NotImplementedError), so the semantics are this library's own and are pinned by its own CPU oracle only ("parity
+ * unpinned"): b_t = side column (use_side != 0 and present) or the tick rule on the prices (bar/utils.py:12-46); the index
+ * list starts with 0; kind 0 closes at the first tick with |sum b_t since the last close| >= threshold, kind 1 at the first
+ * tick with max(#buys, #sells since the last close) >= threshold; the accumulators restart from 0 after a close. */
+int fmk_imbalance_bar_index(fmk_ctx *ctx, const fmk_trades *t, double threshold, int use_side, int kind, fmk_index **out);
 /* wrap caller-provided close indices (comp_bar_* called directly, MockBarBuilder-style tests) */
 int fmk_index_from_host(fmk_ctx *ctx, const fmk_trades *t, const int64_t *close_idx, int64_t m, fmk_index **out);
 int64_t fmk_index_size(const fmk_index *ix);      /* m = n_bars + 1 */

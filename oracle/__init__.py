@@ -41,6 +41,8 @@ def lib():
         _lib.fmko_bar_footprints.restype = C.c_int64
         _lib.fmko_cusum_filter.restype = C.c_int64
         _lib.fmko_merge_split_trades.restype = C.c_int64
+        _lib.fmko_imbalance_bar_indexer.restype = C.c_int64
+        _lib.fmko_imbalance_bar_indexer_ema.restype = C.c_int64
     return _lib
 
 
@@ -334,3 +336,22 @@ def volume_profile_rolling_csr(ts, highs, lows, level_offsets, price_levels, buy
                                       C.c_int64(int(n_bins) if n_bins else 0), C.c_double(price_tick), C.c_double(va_pct),
                                       _p(poc), _p(hva), _p(lva), _p(pct))
     return poc, hva, lva, pct
+
+
+# ---- a6: tick-imbalance / tick-run bars: OWN semantics, parity UNPINNED (the reference only has stubs, logic.py:224-261) ----
+def imbalance_bar_indexer(sides, threshold, kind=0):
+    """kind 0: |running sum of b_t| >= threshold closes; kind 1: max(#buys, #sells) >= threshold closes.  idx[0] = 0."""
+    b = _i8(sides)
+    return _two_phase(lib().fmko_imbalance_bar_indexer, _p(b), C.c_int64(len(b)), C.c_double(float(threshold)), C.c_int(int(kind)))
+
+
+def imbalance_bar_indexer_ema(sides, expected_ticks_init, expected_imbalance_init, span_bars, thr_min, thr_max):
+    """EMA-adaptive tick-imbalance bars (AFML 2.3.2.1, ewma in the adjust=True form of ma.py:7-43) -> (idx, thresholds)."""
+    b = _i8(sides)
+    args = (_p(b), C.c_int64(len(b)), C.c_double(float(expected_ticks_init)), C.c_double(float(expected_imbalance_init)),
+            C.c_int64(int(span_bars)), C.c_double(float(thr_min)), C.c_double(float(thr_max)))
+    m = lib().fmko_imbalance_bar_indexer_ema(*args, None, None, C.c_int64(0))
+    idx = np.zeros(m, np.int64)
+    thr = np.full(m, np.nan)
+    lib().fmko_imbalance_bar_indexer_ema(*args, _p(idx), _p(thr), C.c_int64(m))
+    return idx, thr

@@ -931,3 +931,71 @@ int fmko_volume_profile_rolling(const int64_t *ts, const double *highs, const do
     }
     return FMKO_OK;
 }
+
+/* ---- a6: tick-imbalance / tick-run bars -- OWN SEMANTICS, PARITY UNPINNED -------------------------------------------
+ * The reference only has stubs (bar/logic.py:224-261 raise NotImplementedError), so there is nothing to pin these against:
+ * they restate the definitions of DESIGN.md section 5.5 (AFML 2.3.2.1 / 2.3.2.2 in the reference's conventions: int8 +-1
+ * sides as b_t, close-index list starting with 0 like logic.py:73-84, accumulators restarting from 0 after a close) as plain
+ * sequential loops, and the GPU path is checked against THEM.
+ * kind 0: theta += b_t, close when |theta| >= threshold.  kind 1: count buys / sells, close when max >= threshold. */
+int64_t fmko_imbalance_bar_indexer(const int8_t *b, int64_t n, double threshold, int kind, int64_t *idx, int64_t cap) {
+    int64_t m = 0;
+    if (n <= 0) return 0;
+    if (idx) { if (m < cap) idx[m] = 0; }
+    m++;
+    int64_t theta = 0, nb = 0, ns = 0;
+    for (int64_t i = 1; i < n; i++) {
+        int hit;
+        if (kind == 0) {
+            theta += b[i] > 0 ? 1 : (b[i] < 0 ? -1 : 0);
+            hit = (double)(theta < 0 ? -theta : theta) >= threshold;
+        } else {
+            if (b[i] > 0) nb++; else if (b[i] < 0) ns++;
+            hit = (double)(nb > ns ? nb : ns) >= threshold;
+        }
+        if (hit) {
+            if (idx) { if (m < cap) idx[m] = i; else return FMKO_ERR_CAP; }
+            m++;
+            theta = 0; nb = 0; ns = 0;
+        }
+    }
+    return m;
+}
+
+/* EMA-adaptive tick-imbalance bars (AFML 2.3.2.1): the bar closes at the first tick with |theta| >= E[T] * |E[b]|, where
+ * E[T] is the EWMA (adjust=True form of feature/core/ma.py:7-43, span = span_bars) of the lengths of the completed bars and
+ * E[b] the same EWMA of their mean tick sign theta_close / T; before the first close E[T] = expected_ticks_init and
+ * |E[b]| = expected_imbalance_init.  The threshold is clamped to [thr_min, thr_max] (AFML's definition is known to run away).
+ * ewma state (u, v): u = x + (1 - alpha) u, v = 1 + (1 - alpha) v, value u / v. */
+int64_t fmko_imbalance_bar_indexer_ema(const int8_t *b, int64_t n, double expected_ticks_init, double expected_imbalance_init,
+                                       int64_t span_bars, double thr_min, double thr_max, int64_t *idx, double *thr_out,
+                                       int64_t cap) {
+    int64_t m = 0;
+    if (n <= 0) return 0;
+    if (idx) { if (m < cap) idx[m] = 0; }
+    m++;
+    const double alpha = 2.0 / ((double)span_bars + 1.0), om = 1.0 - alpha;
+    double uT = 0.0, vT = 0.0, uB = 0.0, vB = 0.0;
+    double ET = expected_ticks_init, EB = expected_imbalance_init;
+    double thr = ET * fabs(EB);
+    if (thr < thr_min) thr = thr_min;
+    if (thr > thr_max) thr = thr_max;
+    int64_t theta = 0, last = 0;
+    for (int64_t i = 1; i < n; i++) {
+        theta += b[i] > 0 ? 1 : (b[i] < 0 ? -1 : 0);
+        if ((double)(theta < 0 ? -theta : theta) >= thr) {
+            if (idx) { if (m < cap) { idx[m] = i; if (thr_out) thr_out[m] = thr; } else return FMKO_ERR_CAP; }
+            m++;
+            const double T = (double)(i - last);
+            const double mb = (double)theta / T;
+            if (vT == 0.0) { uT = T; vT = 1.0; uB = mb; vB = 1.0; }
+            else { uT = T + om * uT; vT = 1.0 + om * vT; uB = mb + om * uB; vB = 1.0 + om * vB; }
+            ET = uT / vT; EB = uB / vB;
+            thr = ET * fabs(EB);
+            if (thr < thr_min) thr = thr_min;
+            if (thr > thr_max) thr = thr_max;
+            theta = 0; last = i;
+        }
+    }
+    return m;
+}

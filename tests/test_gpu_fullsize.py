@@ -91,17 +91,27 @@ def test_cusum_fixpoint_small_chunks(ctx, monkeypatch):
     parallel fix-point needs many rounds -- the result must still be the sequential trajectory (golden reference)."""
     from finmlkit_b200 import core
     from helpers import STREAM_CASES, load_case
-    for ch in ("32", "96"):
+    # every combination of: chunk size, lane-per-chunk kernel only / warp walkers only / default hand-over, walker reach,
+    # integer-compare fast chain on / off
+    for ch, walk_below, walk_max, no_fast in (("32", None, None, None), ("96", None, None, None), ("32", "0", None, None),
+                                              ("96", "1000000000", "1", None), ("32", "1000000000", "7", None),
+                                              ("96", "1000000000", "2", "1"), ("32", "0", None, "1")):
         monkeypatch.setenv("FMK_CUSUM_CH", ch)
+        for var, val in (("FMK_CUSUM_WALK_BELOW", walk_below), ("FMK_CUSUM_WALK_MAX", walk_max), ("FMK_CUSUM_NO_FAST", no_fast)):
+            if val is None:
+                monkeypatch.delenv(var, raising=False)
+            else:
+                monkeypatch.setenv(var, val)
         for name in STREAM_CASES:
             g = load_case(name)
             tr = core.DeviceTrades.upload(g["in_ts"], g["in_px"], g["in_qty"], g["in_side"], ctx=ctx)
             sig = core.DeviceBuf.upload(ctx, g["in_cusum_sigma"])
             idx = core.cusum_bar_index(tr, sig, 5e-4, 2.0).download()[1]
-            assert np.array_equal(idx, g["ref_cusum_idx"]), f"{name} CH={ch}"
+            assert np.array_equal(idx, g["ref_cusum_idx"]), f"{name} CH={ch} walk_below={walk_below} walk_max={walk_max} no_fast={no_fast}"
             st = ctx.index_stats()
             assert st["tasks"] > 30
-    monkeypatch.delenv("FMK_CUSUM_CH")
+    for var in ("FMK_CUSUM_CH", "FMK_CUSUM_WALK_BELOW", "FMK_CUSUM_WALK_MAX", "FMK_CUSUM_NO_FAST"):
+        monkeypatch.delenv(var, raising=False)
 
 
 def test_cusum_1e7_vs_oracle(ctx):
@@ -118,7 +128,7 @@ def test_cusum_1e7_vs_oracle(ctx):
     ctx.check(L.fmk_ewmst_dev(ctx.h, tr.h, r, 3600.0, 1e-12, C.byref(s)))
     L.fmk_buf_free(ctx.h, r)
     sigma = core.DeviceBuf(ctx, s).download(np.float64, n)
-    for floor, mult in ((5e-4, 2.0), (1e-5, 0.05)):
+    for floor, mult in ((5e-4, 2.0), (1e-5, 0.05), (0.0, 1.0), (-1.0, 1.5)):     # floor < 0: the generic (double-compare) chain
         sb = core.DeviceBuf.upload(ctx, sigma)
         idx = core.cusum_bar_index(tr, sb, floor, mult).download()[1]
         ref = oracle.cusum_bar_indexer(ts, px, sigma.copy(), floor, mult)

@@ -27,6 +27,10 @@ FILES = [
 
 # reference test id -> why it is allowed to fail here
 KNOWN = {
+    "features/test_compute_returns.py::test_returns_equivalence":
+        "environment, fails on the unmodified reference too: pandas 3 date_range is datetime64[us], so the reference's own "
+        "index.values.astype(int64) yields microseconds (SURVEY section 0.3)",
+    "features/test_compute_returns.py::test_returns_data_with_nans": "same pandas-3 microsecond index, fails on the unmodified reference too",
 }
 
 
@@ -51,7 +55,8 @@ def test_reference_test_file_passes_on_the_dropin(rel):
     if not os.path.isfile(os.path.join(REF_TESTS, rel)):
         pytest.skip("baseline/_ref/ref_tests absent (scripts/install_ref.sh copies the reference's tests where /root/reference exists)")
     rc, passed, failed, out = _run(rel)
-    assert "reference bindings rebound" in out and " 0 reference bindings" not in out, out[-1500:]
+    m = re.search(r"dropin: (\d+) bindings now run on the GPU", out)
+    assert m and int(m.group(1)) >= 30, out[-1500:]          # the reference's names really were rebound
     unexpected = [f for f in failed if f.split("ref_tests/")[-1] not in KNOWN]
     assert passed > 0, out[-3000:]
     assert not unexpected, f"{len(unexpected)} reference tests fail on the drop-in:\n" + "\n".join(unexpected) + "\n" + out[-4000:]

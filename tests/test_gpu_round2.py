@@ -218,3 +218,64 @@ def test_comm_two_ranks_gather_equals_each_ranks_frame(tmp_path):
     for r, p in enumerate(procs):
         assert p.returncode == 0, f"rank {r}:\n{outs[r][-3000:]}"
     assert "GATHER_OK" in outs[0]
+
+
+@pytest.mark.parametrize("kind,thr", [(0, 7.0), (0, 60.0), (0, 2.5), (1, 40.0), (1, 900.0)])
+def test_imbalance_and_run_bars_match_the_own_oracle(ctx, kind, thr, monkeypatch):
+    """a6 (own semantics, PARITY UNPINNED -- the reference only has stubs): the GPU chunk chain against our sequential
+    oracle, with the side column and with the tick rule, small chunks (many fix-point rounds / walkers) and the default."""
+    from finmlkit_b200 import core
+    from finmlkit_b200.bar.logic import _imbalance_bar_indexer, _run_bar_indexer
+    ts, px, qty, side = _stream(400_000, seed=9)
+    side[::53] = 0
+    tr = core.DeviceTrades.upload(ts, px, qty, side, ctx=ctx)
+    ref = oracle.imbalance_bar_indexer(side, thr, kind)
+    for ch in (None, "64", "4096"):
+        for walk in ("0", "1000000000"):
+            if ch:
+                monkeypatch.setenv("FMK_CUSUM_CH", ch)
+            else:
+                monkeypatch.delenv("FMK_CUSUM_CH", raising=False)
+            monkeypatch.setenv("FMK_CUSUM_WALK_BELOW", walk)
+            got = core.imbalance_bar_index(tr, thr, use_side=True, kind=kind).download()
+            assert_exact(got[1], ref, f"kind {kind} thr {thr} CH {ch} walk {walk}")
+            assert np.array_equal(got[0], ts[ref])
+    monkeypatch.delenv("FMK_CUSUM_CH", raising=False)
+    monkeypatch.delenv("FMK_CUSUM_WALK_BELOW", raising=False)
+    # tick rule (the stub's signature has no side argument): b_t from the prices
+    tick_sides = oracle.comp_trade_side_vector(px)
+    f = _imbalance_bar_indexer if kind == 0 else _run_bar_indexer
+    assert_exact(f(ts, px, qty, thr, ctx=ctx), oracle.imbalance_bar_indexer(tick_sides, thr, kind), "tick rule")
+    assert_exact(f(ts, px, qty, thr, sides=side, ctx=ctx), ref, "explicit sides")
+
+
+def test_imbalance_bars_adversarial_never_coalescing(ctx, monkeypatch):
+    """all buys: trajectories from different start states never coalesce (phase of the reset depends on the start), the
+    worst case of the chunk chain -- rounds = number of chunks -- must still give the sequential answer."""
+    from finmlkit_b200 import core
+    n = 60_000
+    ts = np.arange(n, dtype=np.int64) * 1000
+    side = np.ones(n, np.int8)
+    tr = core.DeviceTrades.upload(ts, np.full(n, 100.0), np.ones(n), side, ctx=ctx)
+    monkeypatch.setenv("FMK_CUSUM_CH", "96")
+    for walk in ("0", "1000000000"):
+        monkeypatch.setenv("FMK_CUSUM_WALK_BELOW", walk)
+        got = core.imbalance_bar_index(tr, 7.0, use_side=True, kind=0).download()[1]
+        assert_exact(got, oracle.imbalance_bar_indexer(side, 7.0, 0), f"all buys walk {walk}")
+    monkeypatch.delenv("FMK_CUSUM_CH")
+    monkeypatch.delenv("FMK_CUSUM_WALK_BELOW")
+
+
+def test_imbalance_bar_kit(ctx):
+    from finmlkit_b200.bar.data_model import TradesData
+    from finmlkit_b200.bar.kit import ImbalanceBarKit, RunBarKit
+    ts, px, qty, side = _stream(100_000, seed=2)
+    td = TradesData(ts, px, qty, side=side)
+    kit = ImbalanceBarKit(td, 30.0, ctx=ctx)
+    df = kit.build_ohlcv()
+    ref = oracle.imbalance_bar_indexer(side, 30.0, 0)
+    assert np.array_equal(kit.bar_close_indices, ref[1:]) and len(df) == len(ref) - 1
+    check_ohlcv([df[c].values for c in ("open", "high", "low", "close", "volume", "vwap", "trades", "median_trade_size")],
+                oracle.comp_bar_ohlcv(px, qty, ref), "imbalance kit")
+    rk = RunBarKit(td, 200.0, use_side=False, ctx=ctx)
+    assert np.array_equal(rk.bar_close_indices, oracle.imbalance_bar_indexer(oracle.comp_trade_side_vector(px), 200.0, 1)[1:])
