@@ -34,6 +34,7 @@ SIGNATURES = {
     "fmk_host_free": (None, [P]),
     "fmk_trades_upload": (INT, [P, P, P, P, P, I64, C.POINTER(P)]),
     "fmk_trades_upload_f32amt": (INT, [P, P, P, P, P, I64, C.POINTER(P)]),
+    "fmk_trades_add_column": (INT, [P, P, INT, P]),
     "fmk_trades_synth": (INT, [P, I64, C.c_uint64, C.POINTER(P)]),
     "fmk_trades_refill": (INT, [P, P, P, P, P, P, I64]),
     "fmk_trades_download": (INT, [P, P, P, P, P, P]),
@@ -52,6 +53,7 @@ SIGNATURES = {
     "fmk_dollar_bar_index": (INT, [P, P, F64, C.POINTER(P)]),
     "fmk_cusum_bar_index": (INT, [P, P, P, F64, F64, C.POINTER(P)]),
     "fmk_imbalance_bar_index": (INT, [P, P, F64, INT, INT, C.POINTER(P)]),
+    "fmk_cusum_filled_count": (I64, [P]),
     "fmk_index_from_host": (INT, [P, P, P, I64, C.POINTER(P)]),
     "fmk_index_size": (I64, [P]),
     "fmk_index_download": (INT, [P, P, P, P]),

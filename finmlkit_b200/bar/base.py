@@ -117,14 +117,13 @@ class BarBuilderBase(ABC):
     def _host_ts(self):
         return self.trades_df['timestamp'].astype(np.int64).values
 
-    def _device(self) -> core.DeviceTrades:
-        """Upload the trade columns once (device SoA: [ts i64,] price f64, amount f64, side i8).  Kits whose indexer
-        only needs ts[close_idx] keep the timestamps on the host (a third less H2D traffic)."""
-        if self._dev_trades is None:
-            df = self.trades_df
-            ts = self._host_ts() if self._needs_device_ts else None
-            side = df['side'].values.astype(np.int8) if 'side' in df.columns else None
-            self._dev_trades = core.DeviceTrades.upload(ts, df['price'].values, df['amount'].values, side, ctx=self._ctx)
+    def _device(self, need_side: bool = False) -> core.DeviceTrades:
+        """The device SoA copy of the trade columns, uploaded ONCE per trades frame and shared with every other builder,
+        transform and label call on the same frame (core.device_trades_for).  Price and amount go up first; timestamps only
+        for the kits whose indexer reads them on the device, the side column when a directional / footprint build asks."""
+        if self._dev_trades is None or (need_side and not getattr(self._dev_trades, "has_side", True)):
+            self._dev_trades = core.device_trades_for(self.trades_df, need_ts=self._needs_device_ts, need_side=need_side,
+                                                      ctx=self._ctx)
         return self._dev_trades
 
     def _download_index(self):
@@ -175,7 +174,7 @@ class BarBuilderBase(ABC):
         ix = self._index()
         if 'side' not in self.trades_df.columns:
             raise KeyError('side')
-        d = core.bar_directional(self._device(), ix)
+        d = core.bar_directional(self._device(need_side=True), ix)
         names = ['ticks_buy', 'ticks_sell', 'volume_buy', 'volume_sell', 'dollars_buy', 'dollars_sell', 'mean_spread',
                  'max_spread', 'cum_ticks_min', 'cum_ticks_max', 'cum_volume_min', 'cum_volume_max', 'cum_dollars_min',
                  'cum_dollars_max']
@@ -203,7 +202,7 @@ class BarBuilderBase(ABC):
             self.build_ohlcv()
         if price_tick_size is None:
             price_tick_size = comp_price_tick_size(self.trades_df['price'].values)
-        csr = core.bar_footprints_csr(self._device(), ix, price_tick_size, self._lows, self._highs, imbalance_factor)
+        csr = core.bar_footprints_csr(self._device(need_side=True), ix, price_tick_size, self._lows, self._highs, imbalance_factor)
         fp = FootprintData.from_csr(self.bar_close_timestamps, price_tick_size, csr)
         fp.cast_to_numba_list()
         return fp

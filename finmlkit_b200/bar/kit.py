@@ -73,12 +73,21 @@ class CUSUMBarKit(BarBuilderBase):
         if not (len(self.trades_df) == len(self._sigma)):
             raise ValueError("Prices, timestamps, and sigma arrays must have the same length.")
         dev = self._device()
-        sg = core.DeviceBuf.upload(dev.ctx, np.ascontiguousarray(self._sigma, dtype=np.float64))
+        host = self._sigma.values if isinstance(self._sigma, pd.Series) else self._sigma
+        sg = core.device_copy_of(host)           # the sigma a fused Compose(ReturnT, EWMST) left on the device: no second upload
+        if isinstance(sg, tuple):
+            sg = sg[0]
+        if sg is None:
+            sg = core.DeviceBuf.upload(dev.ctx, np.ascontiguousarray(host, dtype=np.float64))
         self._dev_index = core.cusum_bar_index(dev, sg, self.sigma_floor, self.lambda_mult)
-        if isinstance(self._sigma, np.ndarray) and self._sigma.dtype == np.float64 and self._sigma.flags.writeable:
-            self._sigma[...] = sg.download(np.float64, len(self._sigma))
-        else:
-            self._sigma = sg.download(np.float64, len(self._sigma))
+        # the reference forward-fills NaNs of sigma IN PLACE (logic.py:181-189): mirror it on the caller's array -- only when
+        # the device actually filled something (otherwise the 8 B/tick download is skipped)
+        if int(dev.ctx._L.fmk_cusum_filled_count(dev.ctx.h)) > 0:
+            filled = sg.download(np.float64, len(host))
+            if isinstance(host, np.ndarray) and host.dtype == np.float64 and host.flags.writeable:
+                host[...] = filled
+            else:
+                self._sigma = filled
         return self._dev_index.download()
 
     def get_sigma(self):
@@ -98,7 +107,8 @@ class ImbalanceBarKit(BarBuilderBase):
         self.use_side = use_side
 
     def _comp_bar_close(self):
-        self._dev_index = core.imbalance_bar_index(self._device(), self.threshold, self.use_side, self._kind)
+        self._dev_index = core.imbalance_bar_index(self._device(need_side=self.use_side and 'side' in self.trades_df.columns),
+                                                   self.threshold, self.use_side, self._kind)
         return self._download_index()
 
 

@@ -186,6 +186,89 @@ class DeviceTrades:
         return ts, px, qty, side
 
 
+# ---- one upload per TradesData frame, shared by every kit / transform / label call that is handed the same frame -------------
+_TRADES_CACHE = {}      # id(frame) -> (weakref to the frame, price buffer address, n, ctx, DeviceTrades, has_side)
+_SERIES_CACHE = {}      # id(ndarray) -> (weakref to the array, DeviceBuf): device copies of tick-length series (returns, sigma)
+
+
+def device_trades_for(df, need_ts=False, need_side=False, ctx: Context = None) -> DeviceTrades:
+    """The device SoA copy of a trades frame (``TradesData.data``: columns timestamp, price, amount[, side]), uploaded ONCE
+    and shared by every builder, transform and label call that receives the same frame object; the timestamp and side columns
+    are attached lazily, when a caller first needs them.  The entry dies with the frame (weak reference)."""
+    ctx = ctx or default_context()
+    px = df['price'].values
+    key = id(df)
+    hit = _TRADES_CACHE.get(key)
+    if hit is not None:
+        ref, addr, n, hctx, tr, _ = hit
+        if ref() is df and addr == px.ctypes.data and n == len(px) and hctx is ctx:
+            pass
+        else:
+            hit = None
+    if hit is None:
+        tr = DeviceTrades.upload(None, px, df['amount'].values, None, ctx=ctx)
+        tr.has_ts, tr.has_side = False, False
+
+        def _drop(_r, key=key):
+            _TRADES_CACHE.pop(key, None)
+        _TRADES_CACHE[key] = (weakref.ref(df, _drop), px.ctypes.data, len(px), ctx, tr, False)
+    tr = _TRADES_CACHE[key][4]
+    if need_ts and not tr.has_ts:
+        ts = _c(df['timestamp'].values.astype(np.int64, copy=False), np.int64)
+        ctx.check(ctx._L.fmk_trades_add_column(ctx.h, tr.h, 0, _ptr(ts)))
+        ctx.sync()
+        tr.has_ts = True
+    if need_side and not getattr(tr, "has_side", False):
+        if 'side' not in df.columns:
+            raise KeyError('side')
+        sd = _c(df['side'].values, np.int8)
+        ctx.check(ctx._L.fmk_trades_add_column(ctx.h, tr.h, 1, _ptr(sd)))
+        ctx.sync()
+        tr.has_side = True
+    return tr
+
+
+def _root_array(arr):
+    """the ndarray that owns the memory ``arr`` views (pandas hands out a fresh read-only view per ``Series.values`` call)"""
+    while isinstance(getattr(arr, "base", None), np.ndarray):
+        arr = arr.base
+    return arr
+
+
+def register_device_copy(arr, payload):
+    """Remember that ``payload`` (a DeviceBuf, or (DeviceBuf, DeviceTrades)) is the device copy of the host series ``arr`` --
+    e.g. the sigma a fused Compose returned: a later call that is handed the same memory (CUSUMBarKit(trades, sigma), EWMST on
+    the returns) skips the upload.  ``arr`` may be a Series: the entry is keyed on the array that OWNS the memory and dies with
+    it (weak reference), so recycled memory can never alias a stale entry.  In-place edits by the caller are not detected."""
+    vals = arr.values if hasattr(arr, "values") and not isinstance(arr, np.ndarray) else arr
+    if not isinstance(vals, np.ndarray):
+        return
+    root = _root_array(vals)
+    key = id(root)
+
+    def _drop(_r, key=key):
+        _SERIES_CACHE.pop(key, None)
+    try:
+        _SERIES_CACHE[key] = (weakref.ref(root, _drop), vals.ctypes.data, vals.nbytes, payload)
+    except TypeError:
+        pass
+
+
+def device_copy_of(arr):
+    if not isinstance(arr, np.ndarray):
+        return None
+    root = _root_array(arr)
+    hit = _SERIES_CACHE.get(id(root))
+    if hit is not None and hit[0]() is root and hit[1] == arr.ctypes.data and hit[2] == arr.nbytes:
+        return hit[3]
+    return None
+
+
+def clear_device_cache():
+    _TRADES_CACHE.clear()
+    _SERIES_CACHE.clear()
+
+
 class DeviceIndex:
     """Bar close timestamps / indices on the device (fmk_index), m = n_bars + 1 elements."""
 

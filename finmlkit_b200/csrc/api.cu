@@ -4,6 +4,131 @@
 #include "common.cuh"
 #include "scan.cuh"
 
+#include <algorithm>
+#include <atomic>
+#include <thread>
+
+// ---------------------------------------------------------------------------------------------------------------
+// staged multi-threaded copies of pageable host memory
+// ---------------------------------------------------------------------------------------------------------------
+constexpr size_t COPY_CHUNK = (size_t)8 << 20;       // largest staged chunk (= size of a pinned bounce buffer)
+constexpr size_t COPY_DIRECT_BELOW = (size_t)4 << 20;
+struct fmk_copier {
+    int nthreads;
+    std::vector<void *> slots;            // 2 pinned bounce buffers per thread
+    std::vector<cudaStream_t> streams;
+    std::vector<cudaEvent_t> events;      // one per slot
+};
+
+static fmk_copier *copier_get(fmk_ctx *ctx) {
+    if (ctx->copier) return ctx->copier;
+    fmk_copier *c = new (std::nothrow) fmk_copier();
+    if (!c) return nullptr;
+    int want = 8;
+    if (const char *e = getenv("FMK_COPY_THREADS")) want = atoi(e);
+    const int hw = (int)std::thread::hardware_concurrency();
+    c->nthreads = std::max(1, std::min(want, hw > 0 ? hw : 4));
+    for (int t = 0; t < c->nthreads; t++) {
+        cudaStream_t st;
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { c->nthreads = t; break; }
+        c->streams.push_back(st);
+        for (int b = 0; b < 2; b++) {
+            void *p = nullptr;
+            cudaEvent_t ev;
+            if (cudaHostAlloc(&p, COPY_CHUNK, cudaHostAllocDefault) != cudaSuccess || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                delete c;          // (leaks what was created so far only in this out-of-pinned-memory corner)
+                return nullptr;
+            }
+            c->slots.push_back(p);
+            c->events.push_back(ev);
+        }
+    }
+    if (c->nthreads < 1) { delete c; return nullptr; }
+    ctx->copier = c;
+    return c;
+}
+
+static void copier_destroy(fmk_ctx *ctx) {
+    fmk_copier *c = ctx->copier;
+    if (!c) return;
+    for (auto st : c->streams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (auto p : c->slots) cudaFreeHost(p);
+    for (auto e : c->events) cudaEventDestroy(e);
+    delete c;
+    ctx->copier = nullptr;
+}
+
+static bool host_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static int copy_staged(fmk_ctx *ctx, char *dev, char *host, size_t bytes, bool to_device) {
+    fmk_copier *c = copier_get(ctx);
+    if (!c) return -1;
+    // the device range may still be in use by work queued on the ctx stream (cached blocks are reused in stream order)
+    cudaEvent_t ready = fmk_prof_event(ctx);
+    cudaEventRecord(ready, ctx->stream);
+    // medium-sized columns (a 1e6-tick wrapper call moves 8 MB per column) still want every thread busy: shrink the chunk
+    size_t chunk = bytes / (2 * (size_t)c->nthreads);
+    chunk = std::max((size_t)1 << 20, std::min(COPY_CHUNK, (chunk + 4095) / 4096 * 4096));
+    const size_t nchunks = (bytes + chunk - 1) / chunk;
+    std::atomic<size_t> next(0);
+    std::atomic<int> failed(0);
+    const int device = ctx->device;
+    auto worker = [&](int t) {
+        cudaSetDevice(device);
+        cudaStream_t st = c->streams[t];
+        cudaStreamWaitEvent(st, ready, 0);
+        int used[2] = {0, 0};
+        for (int b = 0;; b ^= 1) {
+            const size_t k = next.fetch_add(1);
+            if (k >= nchunks) break;
+            const size_t off = k * chunk, len = std::min(chunk, bytes - off);
+            void *slot = c->slots[2 * t + b];
+            cudaEvent_t ev = c->events[2 * t + b];
+            if (used[b] && cudaEventSynchronize(ev) != cudaSuccess) { failed = 1; break; }   // the DMA that used this slot is done
+            if (to_device) {
+                memcpy(slot, host + off, len);
+                if (cudaMemcpyAsync(dev + off, slot, len, cudaMemcpyHostToDevice, st) != cudaSuccess) { failed = 1; break; }
+                cudaEventRecord(ev, st);
+                used[b] = 1;
+            } else {
+                if (cudaMemcpyAsync(slot, dev + off, len, cudaMemcpyDeviceToHost, st) != cudaSuccess) { failed = 1; break; }
+                if (cudaStreamSynchronize(st) != cudaSuccess) { failed = 1; break; }
+                memcpy(host + off, slot, len);
+            }
+        }
+        if (cudaStreamSynchronize(st) != cudaSuccess) failed = 1;
+    };
+    std::vector<std::thread> th;
+    const int nt = (int)std::min<size_t>((size_t)c->nthreads, nchunks);
+    for (int t = 1; t < nt; t++) th.emplace_back(worker, t);
+    worker(0);
+    for (auto &x : th) x.join();
+    ctx->ev_pool->push_back(ready);
+    if (failed) { cudaGetLastError(); return -1; }
+    return 0;
+}
+
+int fmk_copy_h2d(fmk_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+    if (bytes == 0) return FMK_OK;
+    if (bytes >= COPY_DIRECT_BELOW && !host_is_pinned(src_host) && copy_staged(ctx, (char *)dst_dev, (char *)src_host, bytes, true) == 0)
+        return FMK_OK;
+    FMK_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return FMK_OK;
+}
+
+int fmk_copy_d2h(fmk_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+    if (bytes == 0) return FMK_OK;
+    if (bytes >= COPY_DIRECT_BELOW && !host_is_pinned(dst_host) && copy_staged(ctx, (char *)src_dev, (char *)dst_host, bytes, false) == 0)
+        return FMK_OK;
+    FMK_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return FMK_OK;
+}
+
 extern "C" {
 
 const char *fmk_version(void) { return "finmlkit_b200 0.1 (sm_100a)"; }
@@ -62,6 +187,7 @@ void fmk_ctx_destroy(fmk_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->res_cols) cudaFree(ctx->res_cols);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    copier_destroy(ctx);
     fmk_cache_trim(ctx);
     for (auto &kv : *ctx->cache_live) cudaFree(kv.first);      // handles the caller never freed
     delete ctx->cache_free;
@@ -201,14 +327,14 @@ int fmk_buf_alloc(fmk_ctx *ctx, int64_t bytes, fmk_buf **out) {
 int fmk_buf_upload(fmk_ctx *ctx, const void *host, int64_t bytes, fmk_buf **out) {
     FMK_ENTER(ctx);
     FMK_TRY(fmk_buf_alloc(ctx, bytes, out));
-    if (bytes > 0) FMK_CUDA(ctx, cudaMemcpyAsync((*out)->ptr, host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (bytes > 0) FMK_TRY(fmk_copy_h2d(ctx, (*out)->ptr, host, (size_t)bytes));
     return FMK_OK;
 }
 
 int fmk_buf_download(fmk_ctx *ctx, const fmk_buf *b, void *host, int64_t bytes) {
     FMK_ENTER(ctx);
     if (bytes > b->bytes) return fmk_fail(ctx, FMK_ERR_CAPACITY, "download larger than buffer");
-    if (bytes > 0) FMK_CUDA(ctx, cudaMemcpyAsync(host, b->ptr, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bytes > 0) FMK_TRY(fmk_copy_d2h(ctx, host, b->ptr, (size_t)bytes));
     FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FMK_OK;
 }
@@ -243,10 +369,10 @@ int fmk_trades_refill(fmk_ctx *ctx, fmk_trades *t, const int64_t *ts, const doub
     FMK_ENTER(ctx);
     if (n != t->n) return fmk_fail(ctx, FMK_ERR_ARG, "refill length differs from handle length");
     if (n == 0) return FMK_OK;
-    if (ts && t->ts) FMK_CUDA(ctx, cudaMemcpyAsync(t->ts, ts, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    FMK_CUDA(ctx, cudaMemcpyAsync(t->price, price, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    FMK_CUDA(ctx, cudaMemcpyAsync(t->amount, amount, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    if (side && t->side) FMK_CUDA(ctx, cudaMemcpyAsync(t->side, side, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if (ts && t->ts) FMK_TRY(fmk_copy_h2d(ctx, t->ts, ts, (size_t)n * 8));
+    FMK_TRY(fmk_copy_h2d(ctx, t->price, price, (size_t)n * 8));
+    FMK_TRY(fmk_copy_h2d(ctx, t->amount, amount, (size_t)n * 8));
+    if (side && t->side) FMK_TRY(fmk_copy_h2d(ctx, t->side, side, (size_t)n));
     if (t->log_price) { fmk_dfree(ctx, t->log_price); t->log_price = nullptr; }
     return FMK_OK;
 }
@@ -266,10 +392,10 @@ int fmk_trades_upload(fmk_ctx *ctx, const int64_t *ts, const double *price, cons
 int fmk_trades_download(fmk_ctx *ctx, const fmk_trades *t, int64_t *ts, double *price, double *amount, int8_t *side) {
     FMK_ENTER(ctx);
     const size_t n = (size_t)t->n;
-    if (ts && t->ts) FMK_CUDA(ctx, cudaMemcpyAsync(ts, t->ts, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (price) FMK_CUDA(ctx, cudaMemcpyAsync(price, t->price, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (amount) FMK_CUDA(ctx, cudaMemcpyAsync(amount, t->amount, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (side && t->side) FMK_CUDA(ctx, cudaMemcpyAsync(side, t->side, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ts && t->ts) FMK_TRY(fmk_copy_d2h(ctx, ts, t->ts, n * 8));
+    if (price) FMK_TRY(fmk_copy_d2h(ctx, price, t->price, n * 8));
+    if (amount) FMK_TRY(fmk_copy_d2h(ctx, amount, t->amount, n * 8));
+    if (side && t->side) FMK_TRY(fmk_copy_d2h(ctx, side, t->side, n));
     FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FMK_OK;
 }
@@ -305,16 +431,30 @@ int fmk_trades_upload_f32amt(fmk_ctx *ctx, const int64_t *ts, const double *pric
         if (n == 0) return FMK_OK;
         Scratch<float> f(ctx);
         FMK_TRY(f.alloc(n));
-        if (ts) FMK_CUDA(ctx, cudaMemcpyAsync(t->ts, ts, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-        FMK_CUDA(ctx, cudaMemcpyAsync(t->price, price, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-        FMK_CUDA(ctx, cudaMemcpyAsync(f.p, amount, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-        if (side) FMK_CUDA(ctx, cudaMemcpyAsync(t->side, side, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        if (ts) FMK_TRY(fmk_copy_h2d(ctx, t->ts, ts, (size_t)n * 8));
+        FMK_TRY(fmk_copy_h2d(ctx, t->price, price, (size_t)n * 8));
+        FMK_TRY(fmk_copy_h2d(ctx, f.p, amount, (size_t)n * 4));
+        if (side) FMK_TRY(fmk_copy_h2d(ctx, t->side, side, (size_t)n));
         FMK_LAUNCH(ctx, k_widen_f32, ctx->sm_count * 8, 256, 0, (const float *)f.p, n, t->amount);
         return FMK_OK;
     };
     const int rc = body();
     if (rc) { fmk_trades_free(ctx, t); *out = nullptr; }
     return rc;
+}
+
+// Adds a column to a handle that was uploaded without it (which: 0 = timestamps int64, 1 = side int8): the wrappers upload
+// lazily -- DollarBarKit.build_ohlcv needs neither, a later TBMLabel / build_directional_features on the same trades does.
+int fmk_trades_add_column(fmk_ctx *ctx, fmk_trades *t, int which, const void *host) {
+    FMK_ENTER(ctx);
+    if (which == 0) {
+        if (!t->ts) FMK_TRY(fmk_dalloc(ctx, &t->ts, t->n));
+        FMK_TRY(fmk_copy_h2d(ctx, t->ts, host, (size_t)t->n * 8));
+    } else if (which == 1) {
+        if (!t->side) FMK_TRY(fmk_dalloc(ctx, &t->side, t->n));
+        FMK_TRY(fmk_copy_h2d(ctx, t->side, host, (size_t)t->n));
+    } else return fmk_fail(ctx, FMK_ERR_ARG, "which must be 0 (timestamps) or 1 (side)");
+    return FMK_OK;
 }
 
 int fmk_buf_gather8(fmk_ctx *ctx, const fmk_buf *src, const int64_t *idx, int64_t m, void *out) {

@@ -24,6 +24,7 @@ struct fmk_ctx {
     void *flush_buf;
     int64_t flush_bytes;
     int64_t stats[3];
+    int64_t cusum_filled;                 // NaNs of sigma forward-filled by the last fmk_cusum_bar_index call
     int owns_stream;
     int prof_on;                          // per-kernel CUDA-event timing (bench.py roofline leg)
     std::vector<fmk_prof_rec> *prof;
@@ -33,6 +34,7 @@ struct fmk_ctx {
     std::vector<std::pair<void *, size_t>> *cache_free;
     std::unordered_map<void *, size_t> *cache_live;
     int64_t cache_bytes;                  // bytes held by the cache (free + live)
+    struct fmk_copier *copier;            // lazily created staging threads for pageable copies (api.cu)
     int64_t cache_free_bytes, cache_free_cap;   // free-list total and its cap (half the device memory): oldest blocks go first
 };
 
@@ -226,6 +228,14 @@ struct Scratch {
 };
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Host <-> device copies of column-sized buffers.  Pinned (or registered) host memory goes straight to cudaMemcpyAsync on the
+// ctx stream.  PAGEABLE memory -- the NumPy / pandas columns every wrapper call hands over -- is staged by the runtime
+// through one internal bounce buffer at ~9 GB/s (measured, e2e_wrapper of round 1); here several host threads copy chunks
+// into their own pinned bounce buffers and issue the DMA on their own streams, which takes the copy to the PCIe rate.
+// Both return with the copy ordered on the ctx stream (pinned) or complete (pageable), like cudaMemcpy would.
+int fmk_copy_h2d(fmk_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int fmk_copy_d2h(fmk_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
 
 // internal cross-TU entry points
 int fmk_dollar_index_impl(fmk_ctx *ctx, const fmk_trades *t, double threshold, fmk_index **out);

@@ -60,6 +60,15 @@ __global__ void k_cusum_first(const double *__restrict__ sigma, int64_t lo, int6
     if (ok && (threadIdx.x & 31) == (unsigned)(__ffs(ok) - 1)) atomicMin(first, (unsigned long long)i);
 }
 
+__global__ void k_count_nan(const double *__restrict__ x, int64_t lo, int64_t n, unsigned long long *count) {
+    unsigned long long c = 0;
+    for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        c += x[i] != x[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
 // "May close" is folded into lam: where the reference skips the close test (ts[i] == ts[i+1], logic.py:206-209) lam is NaN,
 // and both tests `s+ >= lam`, `s- <= -lam` are false for a NaN -- exactly the skip.  (A NaN lam from a NaN sigma behaves the
 // same way in the reference: the comparisons are false.)  One array less to stream per tick.
@@ -521,7 +530,20 @@ int fmk_cusum_index_impl(fmk_ctx *ctx, const fmk_trades *t, fmk_buf *sigma, doub
         FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     const int64_t first = hfirst == ~0ull ? 0 : (int64_t)hfirst;
-    if (hfirst != ~0ull) FMK_TRY((device_inclusive_scan<FF>(ctx, FFIn{sg}, FFOut{sg, first}, n, (FF *)nullptr)));
+    ctx->cusum_filled = 0;
+    if (hfirst != ~0ull) {
+        // NaNs after the first valid element are what the reference's in-place forward fill changes (logic.py:186-189); when
+        // there are none the fill is skipped, and a host wrapper that mirrors the mutation knows it has nothing to copy back
+        Scratch<unsigned long long> dn(ctx);
+        FMK_TRY(dn.alloc(1));
+        FMK_CUDA(ctx, cudaMemsetAsync(dn.p, 0, 8, ctx->stream));
+        FMK_LAUNCH(ctx, k_count_nan, ctx->sm_count * 16, 256, 0, (const double *)sg, first, n, dn.p);
+        unsigned long long hn = 0;
+        FMK_CUDA(ctx, cudaMemcpyAsync(&hn, dn.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->cusum_filled = (int64_t)hn;
+        if (hn) FMK_TRY((device_inclusive_scan<FF>(ctx, FFIn{sg}, FFOut{sg, first}, n, (FF *)nullptr)));
+    }
 
     Scratch<double> r(ctx), lam(ctx);
     Scratch<int> nonfinite(ctx);
@@ -557,6 +579,8 @@ int fmk_cusum_index_impl(fmk_ctx *ctx, const fmk_trades *t, fmk_buf *sigma, doub
     return FMK_OK;
 }
 
+
+extern "C" int64_t fmk_cusum_filled_count(fmk_ctx *ctx) { return ctx->cusum_filled; }
 
 // cusum_filter (sampling/filters.py:6-70): host series / thresholds in, device buffer of int64 event indices out.
 extern "C" int fmk_cusum_filter(fmk_ctx *ctx, const double *series, int64_t n, const double *threshold, int64_t n_thr,

@@ -635,7 +635,7 @@ static int run_ohlcv(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, Ohl
 
 template <typename T>
 static int d2h(fmk_ctx *ctx, T *host, const T *dev, int64_t count) {
-    if (host && count > 0) FMK_CUDA(ctx, cudaMemcpyAsync(host, dev, (size_t)count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    if (host && count > 0) FMK_TRY(fmk_copy_d2h(ctx, host, dev, (size_t)count * sizeof(T)));
     return FMK_OK;
 }
 
@@ -1234,10 +1234,8 @@ extern "C" int fmk_frame_devptrs(const fmk_frame *f, void **bar_block, void **le
 
 extern "C" int fmk_frame_download(fmk_ctx *ctx, const fmk_frame *f, void *bar_block_host, void *level_block_host) {
     FMK_ENTER(ctx);
-    if (bar_block_host && f->bar_bytes > 0)
-        FMK_CUDA(ctx, cudaMemcpyAsync(bar_block_host, f->bar_block, (size_t)f->bar_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    if (level_block_host && f->level_bytes > 0)
-        FMK_CUDA(ctx, cudaMemcpyAsync(level_block_host, f->level_block, (size_t)f->level_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bar_block_host && f->bar_bytes > 0) FMK_TRY(fmk_copy_d2h(ctx, bar_block_host, f->bar_block, (size_t)f->bar_bytes));
+    if (level_block_host && f->level_bytes > 0) FMK_TRY(fmk_copy_d2h(ctx, level_block_host, f->level_block, (size_t)f->level_bytes));
     FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FMK_OK;
 }

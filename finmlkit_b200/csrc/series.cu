@@ -289,10 +289,10 @@ extern "C" int fmk_lagged_returns(fmk_ctx *ctx, const int64_t *ts, const double 
     Scratch<double> dc(ctx), dout(ctx);
     FMK_TRY(dts.alloc(n)); FMK_TRY(dc.alloc(n)); FMK_TRY(dout.alloc(n));
     if (n > 0) {
-        FMK_CUDA(ctx, cudaMemcpyAsync(dts.p, ts, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-        FMK_CUDA(ctx, cudaMemcpyAsync(dc.p, close, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        FMK_TRY(fmk_copy_h2d(ctx, dts.p, ts, (size_t)n * 8));
+        FMK_TRY(fmk_copy_h2d(ctx, dc.p, close, (size_t)n * 8));
         FMK_TRY(run_lagged_returns(ctx, dts.p, dc.p, n, window_sec, is_log, dout.p));
-        FMK_CUDA(ctx, cudaMemcpyAsync(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        FMK_TRY(fmk_copy_d2h(ctx, out, dout.p, (size_t)n * 8));
     }
     FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FMK_OK;
@@ -305,10 +305,10 @@ extern "C" int fmk_ewmst(fmk_ctx *ctx, const int64_t *ts, const double *y, int64
     Scratch<double> dy(ctx), dout(ctx);
     FMK_TRY(dts.alloc(n)); FMK_TRY(dy.alloc(n)); FMK_TRY(dout.alloc(n));
     if (n > 0) {
-        FMK_CUDA(ctx, cudaMemcpyAsync(dts.p, ts, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-        FMK_CUDA(ctx, cudaMemcpyAsync(dy.p, y, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        FMK_TRY(fmk_copy_h2d(ctx, dts.p, ts, (size_t)n * 8));
+        FMK_TRY(fmk_copy_h2d(ctx, dy.p, y, (size_t)n * 8));
         FMK_TRY(run_ewmst(ctx, dts.p, dy.p, n, half_life, sigma_floor, dout.p));
-        FMK_CUDA(ctx, cudaMemcpyAsync(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        FMK_TRY(fmk_copy_d2h(ctx, out, dout.p, (size_t)n * 8));
     }
     FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FMK_OK;

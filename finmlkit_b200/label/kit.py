@@ -89,11 +89,14 @@ class TBMLabel:
             event_idx = self._features.event_idx.values
         else:
             event_idx = np.searchsorted(ts, self._features.index.as_unit("ns").asi8)
+        from .. import core
+        # the trades frame's ONE device copy (shared with the bar kits and the sigma transforms): no second upload
+        dev = core.device_trades_for(trades.data, need_ts=True)
         labels, touch_idx, rets, ratios = triple_barrier(
             timestamps=ts, close=trades.data.price.values, event_idxs=event_idx, targets=self.target_returns.values,
             horizontal_barriers=self.horizontal_barriers, vertical_barrier=self.vertical_barrier,
             min_close_time_sec=self.min_close_time_sec,
-            side=self.features['side'].values.astype(np.int8) if self.is_meta else None, min_ret=self.min_ret)
+            side=self.features['side'].values.astype(np.int8) if self.is_meta else None, min_ret=self.min_ret, _dev_trades=dev)
         self._out = pd.DataFrame({'touch_time': pd.to_datetime(ts[touch_idx]), 'event_idx': event_idx, 'touch_idx': touch_idx,
                                   'labels': labels, 'returns': rets, 'vertical_touch_weights': ratios}, index=self.features.index)
         return self.features, self.full_output
@@ -116,8 +119,7 @@ class SampleWeights:
         if 'event_idx' not in labels.columns or 'touch_idx' not in labels.columns:
             raise ValueError("Events DataFrame must contain 'event_idx' and 'touch_idxs' columns.")
         from .. import core
-        px = trades.data.price.values
-        tr = core.DeviceTrades.upload(None, px, px)            # only the price column is read
+        tr = core.device_trades_for(trades.data)               # the shared device copy of the frame; only price is read
         avg_u, info_w = core.sample_weights_dev(tr, labels.event_idx.values, labels.touch_idx.values, normalize=normalize)
         out_df = pd.DataFrame({'avg_uniqueness': avg_u}, index=labels.index)
         out_df["return_attribution"] = info_w

@@ -71,6 +71,8 @@ int fmk_trades_upload(fmk_ctx *ctx, const int64_t *ts, const double *price, cons
  * bar/data_model.py:326-344): 4 B/tick over PCIe, widened exactly to float64 on the device. */
 int fmk_trades_upload_f32amt(fmk_ctx *ctx, const int64_t *ts, const double *price, const float *amount, const int8_t *side,
                              int64_t n, fmk_trades **out);
+/* Adds a column to a handle uploaded without it (which: 0 = timestamps int64[n], 1 = side int8[n]). */
+int fmk_trades_add_column(fmk_ctx *ctx, fmk_trades *t, int which, const void *host);
 /* Device-side synthetic BTCUSDT-like stream (SURVEY 8d shape) for bench-size runs. */
 int fmk_trades_synth(fmk_ctx *ctx, int64_t n, uint64_t seed, fmk_trades **out);
 /* Re-fill an existing handle from host arrays (async H2D on the ctx stream; arrays should be pinned). */
@@ -100,6 +102,8 @@ int fmk_dollar_bar_index(fmk_ctx *ctx, const fmk_trades *t, double threshold, fm
 /* sigma: device f64[n] buffer; it is forward-filled in place like the reference (logic.py:181-189). */
 int fmk_cusum_bar_index(fmk_ctx *ctx, const fmk_trades *t, fmk_buf *sigma, double sigma_floor, double sigma_mult,
                         fmk_index **out);                                                             /* logic.py:152-221 */
+/* number of NaNs of sigma the last fmk_cusum_bar_index call forward-filled (0: the buffer was left untouched) */
+int64_t fmk_cusum_filled_count(fmk_ctx *ctx);
 /* Tick-imbalance (kind 0) / tick-run (kind 1) bars.  The reference only has stubs (logic.py:224-261 raise
  * NotImplementedError), so the semantics are this library's own and are pinned by its own CPU oracle only ("parity
  * unpinned"): b_t = side column (use_side != 0 and present) or the tick rule on the prices (bar/utils.py:12-46); the index
