@@ -34,6 +34,8 @@ SIGNATURES = {
     "fmk_host_free": (None, [P]),
     "fmk_trades_upload": (INT, [P, P, P, P, P, I64, C.POINTER(P)]),
     "fmk_trades_upload_f32amt": (INT, [P, P, P, P, P, I64, C.POINTER(P)]),
+    "fmk_trades_alloc": (INT, [P, I64, INT, INT, C.POINTER(P)]),
+    "fmk_trades_write": (INT, [P, P, I64, I64, P, P, P, INT, P]),
     "fmk_trades_add_column": (INT, [P, P, INT, P]),
     "fmk_trades_synth": (INT, [P, I64, C.c_uint64, C.POINTER(P)]),
     "fmk_trades_refill": (INT, [P, P, P, P, P, P, I64]),

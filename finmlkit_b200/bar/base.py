@@ -92,7 +92,11 @@ class BarBuilderBase(ABC):
     """Template for bar builders (reference: base.py:24-300)."""
 
     def __init__(self, trades, ctx=None):
-        self.trades_df = trades.data
+        # ``trades``: a TradesData (this package's or the reference's: only ``.data`` is read, base.py:71) or a
+        # ``bar.io.StoreTrades`` whose columns already sit on the device (its pandas frame is then never built here)
+        self._trades = trades
+        self._store = trades if hasattr(trades, "device_trades") else None
+        self._frame = None if self._store is not None else trades.data
         self._ctx = ctx or core.default_context()
         self._close_ts: Optional[np.ndarray] = None
         self._close_indices: Optional[np.ndarray] = None
@@ -111,6 +115,15 @@ class BarBuilderBase(ABC):
             info = "<unavailable>"
         return f"Class: {self.__class__.__name__} with members:\n{members}\nRaw trades data:\n{info}"
 
+    @property
+    def trades_df(self) -> pd.DataFrame:
+        if self._frame is None:
+            self._frame = self._trades.data
+        return self._frame
+
+    def _has_side(self) -> bool:
+        return self._store.has_side if self._store is not None else 'side' in self.trades_df.columns
+
     # -- device residency -------------------------------------------------------------------------------------------
     _needs_device_ts = False   # time / CUSUM kits override: their indexers read the timestamps on the device
 
@@ -121,13 +134,16 @@ class BarBuilderBase(ABC):
         """The device SoA copy of the trade columns, uploaded ONCE per trades frame and shared with every other builder,
         transform and label call on the same frame (core.device_trades_for).  Price and amount go up first; timestamps only
         for the kits whose indexer reads them on the device, the side column when a directional / footprint build asks."""
+        if self._store is not None:
+            return self._store.device_trades(need_ts=self._needs_device_ts, need_side=need_side, ctx=self._ctx)
         if self._dev_trades is None or (need_side and not getattr(self._dev_trades, "has_side", True)):
             self._dev_trades = core.device_trades_for(self.trades_df, need_ts=self._needs_device_ts, need_side=need_side,
                                                       ctx=self._ctx)
         return self._dev_trades
 
     def _download_index(self):
-        return self._dev_index.download(host_ts=None if self._needs_device_ts else self._host_ts())
+        on_device = self._needs_device_ts or self._store is not None or getattr(self._device(), "has_ts", False)
+        return self._dev_index.download(host_ts=None if on_device else self._host_ts())
 
     @abstractmethod
     def _comp_bar_close(self) -> Tuple[np.ndarray, np.ndarray]:
@@ -172,7 +188,7 @@ class BarBuilderBase(ABC):
     def build_directional_features(self) -> pd.DataFrame:
         """base.py:171-212."""
         ix = self._index()
-        if 'side' not in self.trades_df.columns:
+        if not self._has_side():
             raise KeyError('side')
         d = core.bar_directional(self._device(need_side=True), ix)
         names = ['ticks_buy', 'ticks_sell', 'volume_buy', 'volume_sell', 'dollars_buy', 'dollars_sell', 'mean_spread',
@@ -201,7 +217,8 @@ class BarBuilderBase(ABC):
         if self._highs is None or self._lows is None:
             self.build_ohlcv()
         if price_tick_size is None:
-            price_tick_size = comp_price_tick_size(self.trades_df['price'].values)
+            price_tick_size = comp_price_tick_size(self._store.column("price")[:10000] if self._store is not None
+                                                   else self.trades_df['price'].values)
         csr = core.bar_footprints_csr(self._device(need_side=True), ix, price_tick_size, self._lows, self._highs, imbalance_factor)
         fp = FootprintData.from_csr(self.bar_close_timestamps, price_tick_size, csr)
         fp.cast_to_numba_list()

@@ -70,7 +70,7 @@ class CUSUMBarKit(BarBuilderBase):
         self.sigma_floor = sigma_floor
 
     def _comp_bar_close(self):
-        if not (len(self.trades_df) == len(self._sigma)):
+        if not (self._device().n == len(self._sigma)):
             raise ValueError("Prices, timestamps, and sigma arrays must have the same length.")
         dev = self._device()
         host = self._sigma.values if isinstance(self._sigma, pd.Series) else self._sigma
@@ -107,7 +107,7 @@ class ImbalanceBarKit(BarBuilderBase):
         self.use_side = use_side
 
     def _comp_bar_close(self):
-        self._dev_index = core.imbalance_bar_index(self._device(need_side=self.use_side and 'side' in self.trades_df.columns),
+        self._dev_index = core.imbalance_bar_index(self._device(need_side=self.use_side and self._has_side()),
                                                    self.threshold, self.use_side, self._kind)
         return self._download_index()
 

@@ -228,6 +228,18 @@ def device_trades_for(df, need_ts=False, need_side=False, ctx: Context = None) -
     return tr
 
 
+def adopt_device_trades(df, tr: DeviceTrades, has_ts=True, has_side=False):
+    """Register an existing device handle as THE device copy of the frame ``df`` (bar.io.StoreTrades: the columns were loaded
+    from the month store straight into the device, the pandas frame was built from the same files afterwards)."""
+    px = df['price'].values
+    key = id(df)
+    tr.has_ts, tr.has_side = has_ts, has_side
+
+    def _drop(_r, key=key):
+        _TRADES_CACHE.pop(key, None)
+    _TRADES_CACHE[key] = (weakref.ref(df, _drop), px.ctypes.data, len(px), tr.ctx, tr, has_side)
+
+
 def _root_array(arr):
     """the ndarray that owns the memory ``arr`` views (pandas hands out a fresh read-only view per ``Series.values`` call)"""
     while isinstance(getattr(arr, "base", None), np.ndarray):
@@ -605,6 +617,24 @@ def frame_views(bar_block: np.ndarray, level_block, n_bars, n_levels, col_offset
             continue
         out[name] = np.frombuffer(src, dtype=dt, count=cnt, offset=off)
     return out
+
+
+FRAME_HEADER_BYTES = 512
+FRAME_MAGIC = 0x464D4B4652414D45
+
+
+def frame_views_from_bytes(buf) -> dict:
+    """{column: array} from the raw bytes of a frame as it crosses the wire (fmk_comm_gather_submit of
+    ``DeviceFrame.segments()``: the self-describing per-bar block, then the per-level block at the next 16-byte boundary)."""
+    b = np.ascontiguousarray(buf, dtype=np.uint8)
+    hdr = np.frombuffer(b, np.int64, FRAME_HEADER_BYTES // 8)
+    if int(hdr[0]) != FRAME_MAGIC:
+        raise ValueError("not a finmlkit_b200 bar frame")
+    nb, nl, bar_bytes, lvl_bytes, ncols = int(hdr[1]), int(hdr[2]), int(hdr[3]), int(hdr[4]), int(hdr[6])
+    lvl0 = (bar_bytes + 15) // 16 * 16
+    cols = np.full(len(FRAME_COLS), -1, np.int64)
+    cols[:min(ncols, len(FRAME_COLS))] = hdr[8:8 + min(ncols, len(FRAME_COLS))]
+    return frame_views(b[:bar_bytes], b[lvl0:lvl0 + lvl_bytes] if lvl_bytes else None, nb, nl, cols)
 
 
 class DeviceFrame:

@@ -457,6 +457,35 @@ int fmk_trades_add_column(fmk_ctx *ctx, fmk_trades *t, int which, const void *ho
     return FMK_OK;
 }
 
+// Month-store loader (the reference keeps /trades/YYYY-MM tables, bar/data_model.py:420-574, and concatenates
+// them on the host): one device SoA handle is allocated for the whole range and every month's columns are written straight
+// into it at their offset -- no concatenated host frame is ever built.
+int fmk_trades_alloc(fmk_ctx *ctx, int64_t n, int with_ts, int with_side, fmk_trades **out) {
+    FMK_ENTER(ctx);
+    if (n < 0) return fmk_fail(ctx, FMK_ERR_ARG, "negative length");
+    return trades_alloc(ctx, n, with_ts, with_side, out);
+}
+
+int fmk_trades_write(fmk_ctx *ctx, fmk_trades *t, int64_t offset, int64_t count, const int64_t *ts, const double *price,
+                     const void *amount, int amount_is_f32, const int8_t *side) {
+    FMK_ENTER(ctx);
+    if (offset < 0 || count < 0 || offset + count > t->n) return fmk_fail(ctx, FMK_ERR_ARG, "segment outside the handle");
+    if (count == 0) return FMK_OK;
+    if (ts && t->ts) FMK_TRY(fmk_copy_h2d(ctx, t->ts + offset, ts, (size_t)count * 8));
+    if (price) FMK_TRY(fmk_copy_h2d(ctx, t->price + offset, price, (size_t)count * 8));
+    if (amount) {
+        if (amount_is_f32) {
+            Scratch<float> f(ctx);
+            FMK_TRY(f.alloc(count));
+            FMK_TRY(fmk_copy_h2d(ctx, f.p, amount, (size_t)count * 4));
+            FMK_LAUNCH(ctx, k_widen_f32, ctx->sm_count * 8, 256, 0, (const float *)f.p, count, t->amount + offset);
+        } else FMK_TRY(fmk_copy_h2d(ctx, t->amount + offset, amount, (size_t)count * 8));
+    }
+    if (side && t->side) FMK_TRY(fmk_copy_h2d(ctx, t->side + offset, side, (size_t)count));
+    if (t->log_price) { fmk_dfree(ctx, t->log_price); t->log_price = nullptr; }
+    return FMK_OK;
+}
+
 int fmk_buf_gather8(fmk_ctx *ctx, const fmk_buf *src, const int64_t *idx, int64_t m, void *out) {
     FMK_ENTER(ctx);
     if (m <= 0) return FMK_OK;

@@ -380,6 +380,10 @@ struct CountOut {
 };
 
 __global__ void k_set_first(int64_t *out, int64_t v) { out[0] = v; }
+__global__ void k_iota_i64(int64_t *out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
 
 // Shared driver of the chunk chain: speculative pass, parallel fix-point, bitmap -> ordered index list.
 // idx_out[0] is left for the caller (open marker); idx_out[1..total] are the closing / event ticks.
@@ -400,8 +404,17 @@ __global__ void k_set_first(int64_t *out, int64_t v) { out[0] = v; }
         else FMK_LAUNCH(ctx, k_cusum_walk<4>, grid, block, smem, __VA_ARGS__);                   \
     } while (0)
 
+// exact_starts (imbalance bars): a callback that, given the chunking, fills pe[0 .. nchunks] with the TRUE state in front of
+// every chunk (pe[k] = state before chunk k); the chain then needs no speculation and no repair rounds -- one replay pass.
+struct ExactStarts {
+    const int8_t *sides;
+    int m;
+};
+static int imbalance_exact_starts(fmk_ctx *ctx, const ExactStarts &es, int64_t n, int64_t base0, int64_t CH, int64_t nchunks,
+                                  CusumState *pe);
+
 static int cusum_chain(fmk_ctx *ctx, const Scratch<double> &r, const Scratch<double> &lam, int64_t n, int64_t first, int mode,
-                       int64_t **idx_out, int64_t *total_out, double thr = 0.0) {
+                       int64_t **idx_out, int64_t *total_out, double thr = 0.0, const ExactStarts *exact = nullptr) {
     const int64_t m_ticks = n - (first + 1);   // ticks that can close a bar
     int64_t total = 0;
     int64_t *idx = nullptr;
@@ -455,11 +468,22 @@ static int cusum_chain(fmk_ctx *ctx, const Scratch<double> &r, const Scratch<dou
         }
         FMK_CUDA(ctx, cudaMemsetAsync(touched.p, 0, (size_t)nchunks, ctx->stream));
         FMK_CUDA(ctx, cudaMemsetAsync(is_head.p, 0, (size_t)nchunks, ctx->stream));
+        int64_t hrep = 0, rounds = 0;
+        if (exact) {
+            Scratch<CusumState> pe(ctx);
+            FMK_TRY(pe.alloc(nchunks + 1));
+            FMK_TRY(imbalance_exact_starts(ctx, *exact, n, first + 1, CH, nchunks, pe.p));
+            FMK_LAUNCH(ctx, k_iota_i64, (unsigned)cdiv(nchunks, 256), 256, 0, work.p, nchunks);
+            // "replay the listed chunks from prev_end[k - 1]" with prev_end = pe + 1: chunk k starts from pe[k]
+            CUSUM_TASKS((unsigned)cdiv(cdiv(nchunks, 32), CT_WARPS), CT_WARPS * 32, 0, (const double *)r.p, (const double *)lam.p, n,
+                        first, CH, nchunks, bitmap.p, ss.p, se.p, (uint8_t *)nullptr, (const int64_t *)work.p, nchunks,
+                        (const CusumState *)(pe.p + 1), thr);
+        } else {
         CUSUM_TASKS((unsigned)cdiv(cdiv(nchunks, 32), CT_WARPS), CT_WARPS * 32, 0, (const double *)r.p, (const double *)lam.p, n,
                     first, CH, nchunks, bitmap.p, ss.p, se.p, (uint8_t *)nullptr, (const int64_t *)nullptr, (int64_t)0,
                     (const CusumState *)nullptr, thr);
-        int64_t hrep = 0, rounds = 0;
-        for (;;) {
+        }
+        for (; !exact;) {
             unsigned long long hcount = 0;
             FMK_CUDA(ctx, cudaMemsetAsync(dcount.p, 0, 8, ctx->stream));
             if (nchunks > 1)
@@ -632,6 +656,94 @@ __global__ void k_sides_to_r(const int8_t *__restrict__ side, int64_t n, double 
 
 int fmk_tick_rule_device(fmk_ctx *ctx, const double *price_dev, int64_t n, int8_t *sides_dev);   // ingest.cu
 
+// ---- exact chunk start states for tick-imbalance bars -------------------------------------------------------------------
+// theta lives in (-m, m) (m = ceil(threshold)) and every chunk acts on it as a MAP G_k: start state -> end state.  Trajectories
+// from different start states do not coalesce on their own (all-buy data: never), so speculation + repair rounds can take as
+// many rounds as there are chunks (measured: 155 s at 1e9 ticks, threshold 200).  The map itself, however, costs O(1) per tick
+// when it is built BACKWARDS: G_{t-1}(x) = G_t(x + b_t) for |x + b_t| < m, and = G_t(0) for the one x that hits +-m.  Stored
+// in a circular buffer that is a pure re-indexing (offset += b_t) plus ONE element write per tick.  A lane builds the map of
+// its chunk (2m - 1 entries in shared memory), the maps are composed in two levels (thread per start state inside a group of
+// chunks, a short serial hop over groups), and every chunk's TRUE start state drops out -- the forward pass then replays each
+// chunk exactly once.  Integer arithmetic throughout: exact by construction.
+__global__ void k_imb_backmap(const int8_t *__restrict__ side, int64_t n, int64_t base0, int64_t CH, int64_t nchunks, int m,
+                              int Wp, uint16_t *__restrict__ maps) {
+    extern __shared__ uint16_t imb_sm[];
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nchunks) return;
+    uint16_t *buf = imb_sm + (size_t)threadIdx.x * (Wp + 2);
+    const int mask = Wp - 1, W = 2 * m - 1;
+    for (int x = -(m - 1); x <= m - 1; x++) buf[x & mask] = (uint16_t)(x + m - 1);     // G at the chunk end: identity
+    int off = 0;
+    const int64_t lo = base0 + k * CH;
+    const int64_t hi = lo + CH < n ? lo + CH : n;
+    for (int64_t i = hi - 1; i >= lo; i--) {
+        const int sd = side[i];
+        if (sd == 0) continue;
+        const int b = sd > 0 ? 1 : -1;
+        const uint16_t v0 = buf[off & mask];            // G_t(0)
+        off += b;
+        buf[((b > 0 ? m - 1 : -(m - 1)) + off) & mask] = v0;
+    }
+    uint16_t *out = maps + k * W;
+    for (int x = -(m - 1); x <= m - 1; x++) out[x + m - 1] = buf[(x + off) & mask];
+}
+
+// group composite: thread per start state walks the group's chunk maps
+__global__ void k_imb_group(const uint16_t *__restrict__ maps, int64_t nchunks, int W, int gs, uint16_t *__restrict__ gmaps) {
+    const int64_t g = blockIdx.x;
+    const int64_t c0 = g * gs, c1 = c0 + gs < nchunks ? c0 + gs : nchunks;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        int v = x;
+        for (int64_t c = c0; c < c1; c++) v = maps[c * W + v];
+        gmaps[g * W + x] = (uint16_t)v;
+    }
+}
+// one thread: true state in front of every group
+__global__ void k_imb_groups_serial(const uint16_t *__restrict__ gmaps, int64_t ngroups, int W, int zero, int *__restrict__ gstart) {
+    int v = zero;
+    for (int64_t g = 0; g < ngroups; g++) { gstart[g] = v; v = gmaps[g * W + v]; }
+}
+// thread per group: true state in front of every chunk -> the chain's state records (theta carried exactly in a double)
+__global__ void k_imb_starts(const uint16_t *__restrict__ maps, int64_t nchunks, int W, int gs, int m, const int *__restrict__ gstart,
+                             int64_t ngroups, CusumState *__restrict__ pe) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    const int64_t c0 = g * gs, c1 = c0 + gs < nchunks ? c0 + gs : nchunks;
+    int v = gstart[g];
+    for (int64_t c = c0; c < c1; c++) {
+        CusumState st;
+        st.sp = (double)(v - (m - 1));
+        st.sn = 0.0;
+        pe[c] = st;
+        v = maps[c * W + v];
+    }
+    if (c1 == nchunks) { CusumState st; st.sp = (double)(v - (m - 1)); st.sn = 0.0; pe[nchunks] = st; }
+}
+
+constexpr int IMB_MAX_M = 2048;     // 2m - 1 map entries per chunk; beyond that the generic chain is used
+static int imbalance_exact_starts(fmk_ctx *ctx, const ExactStarts &es, int64_t n, int64_t base0, int64_t CH, int64_t nchunks,
+                                  CusumState *pe) {
+    const int m = es.m, W = 2 * m - 1;
+    int Wp = 2;
+    while (Wp < 2 * m) Wp <<= 1;
+    // lanes per block: as many private maps as fit ~96 KB of shared memory
+    int lanes = (int)((96 * 1024) / ((size_t)(Wp + 2) * sizeof(uint16_t)));
+    lanes = lanes >= 128 ? 128 : (lanes >= 64 ? 64 : (lanes >= 32 ? 32 : (lanes >= 8 ? 8 : 1)));
+    const size_t smem = (size_t)lanes * (Wp + 2) * sizeof(uint16_t);
+    FMK_CUDA(ctx, cudaFuncSetAttribute(k_imb_backmap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int gs = 256;
+    const int64_t ngroups = cdiv(nchunks, gs);
+    Scratch<uint16_t> maps(ctx), gmaps(ctx);
+    Scratch<int> gstart(ctx);
+    FMK_TRY(maps.alloc(nchunks * W)); FMK_TRY(gmaps.alloc(ngroups * W)); FMK_TRY(gstart.alloc(ngroups));
+    FMK_LAUNCH(ctx, k_imb_backmap, (unsigned)cdiv(nchunks, lanes), lanes, smem, es.sides, n, base0, CH, nchunks, m, Wp, maps.p);
+    FMK_LAUNCH(ctx, k_imb_group, (unsigned)ngroups, 256, 0, (const uint16_t *)maps.p, nchunks, W, gs, gmaps.p);
+    FMK_LAUNCH(ctx, k_imb_groups_serial, 1, 1, 0, (const uint16_t *)gmaps.p, ngroups, W, m - 1, gstart.p);
+    FMK_LAUNCH(ctx, k_imb_starts, (unsigned)cdiv(ngroups, 64), 64, 0, (const uint16_t *)maps.p, nchunks, W, gs, m, (const int *)gstart.p,
+               ngroups, pe);
+    return FMK_OK;
+}
+
 extern "C" int fmk_imbalance_bar_index(fmk_ctx *ctx, const fmk_trades *t, double threshold, int use_side, int kind,
                                        fmk_index **out_ix) {
     FMK_ENTER(ctx);
@@ -653,7 +765,13 @@ extern "C" int fmk_imbalance_bar_index(fmk_ctx *ctx, const fmk_trades *t, double
     FMK_LAUNCH(ctx, k_sides_to_r, ctx->sm_count * 16, 256, 0, sides, n, r.p);
     int64_t total = 0;
     int64_t *idx = nullptr;
-    FMK_TRY(cusum_chain(ctx, r, lam, n, 0, 2 + kind, &idx, &total, threshold));
+    // tick-imbalance bars with a moderate threshold: exact chunk start states from the backward maps, one replay pass;
+    // run bars (two counters) and very large thresholds go through the speculative chain
+    const double mceil = ceil(threshold);
+    ExactStarts es{sides, (int)mceil};
+    const bool no_exact = getenv("FMK_IMBALANCE_NO_EXACT") != nullptr;             // test hook: force the speculative chain
+    const bool use_exact = kind == 0 && mceil >= 1.0 && mceil <= (double)IMB_MAX_M && !no_exact;
+    FMK_TRY(cusum_chain(ctx, r, lam, n, 0, 2 + kind, &idx, &total, threshold, use_exact ? &es : nullptr));
     {
         auto launch = [&]() -> int { FMK_LAUNCH(ctx, k_set_first, 1, 1, 0, idx, (int64_t)0); return FMK_OK; };
         const int lrc = launch();

@@ -120,17 +120,20 @@ __global__ void __launch_bounds__(VN_THREADS) k_volume_next(const double *__rest
 // L2 moved 270 GB at 1e9 ticks (94 ms).  Neighbouring entries sum over almost the same ticks, so a warp now owns a
 // 1024-tick segment of starts: it collects the segment's entries, and for 32 of them at a time streams the union of their
 // ranges through a shared-memory tile (coalesced loads, once) while every lane runs its own sequential sum from the tile.
+// Occupancy: every lane runs one long dependent chain of float64 adds, so throughput comes from resident warps, and those are
+// bounded by shared memory: 6 KB per warp (512-tick tile + 16-bit entry list) keeps ~36 warps per SM resident (the r01
+// layout, 12 KB per warp, ran at 15 -- ncu `warps active 24 %`).
 constexpr int VR_WARPS = 4;
 constexpr int VR_SEG = 1024;      // starts per warp-segment
-constexpr int VR_TILE = 1024;     // ticks per staged tile
+constexpr int VR_TILE = 512;      // ticks per staged tile
 __global__ void __launch_bounds__(VR_WARPS * 32) k_volume_replay_seg(const double *__restrict__ v, int64_t n, double T,
                                                                      int32_t *__restrict__ next,
                                                                      unsigned long long *nreplays) {
     __shared__ double tile_s[VR_WARPS][VR_TILE];
-    __shared__ int32_t list_s[VR_WARPS][VR_SEG];
+    __shared__ uint16_t list_s[VR_WARPS][VR_SEG];     // entry offsets inside the segment
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double *tile = tile_s[w];
-    int32_t *list = list_s[w];
+    uint16_t *list = list_s[w];
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t nseg = (n + VR_SEG - 1) / VR_SEG;
     for (int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < nseg; seg += nwarps) {
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(VR_WARPS * 32) k_volume_replay_seg(const doubl
             const int64_t i = base + g * 32 + lane;
             const bool amb = i < n && next[i] == -1;
             const unsigned m = __ballot_sync(0xffffffffu, amb);
-            if (amb) list[cnt + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+            if (amb) list[cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(i - base);
             cnt += __popc(m);
         }
         __syncwarp();
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(VR_WARPS * 32) k_volume_replay_seg(const doubl
         if (lane == 0) atomicAdd(nreplays, (unsigned long long)cnt);
         for (int b0 = 0; b0 < cnt; b0 += 32) {
             const bool have = b0 + lane < cnt;
-            const int64_t i = have ? list[b0 + lane] : n;
+            const int64_t i = have ? base + list[b0 + lane] : n;
             int64_t pos = i + 1;                    // next tick this lane adds
             double cum = 0.0;
             int64_t res = n;
@@ -161,7 +164,8 @@ __global__ void __launch_bounds__(VR_WARPS * 32) k_volume_replay_seg(const doubl
 #pragma unroll 8
                 for (int q = lane; q < VR_TILE; q += 32) tile[q] = a + q < n ? __ldg(v + a + q) : 0.0;
                 __syncwarp();
-                if (active) {
+                // a lane whose first tick lies beyond this tile (the tile is shorter than the segment of starts) just waits
+                if (active && pos < a + VR_TILE) {
                     int64_t end = a + VR_TILE < n ? a + VR_TILE : n;
                     int64_t t = pos > a ? pos : a;
                     // sizes are >= 0 on this path (anything else took the serial fallback), so the running sum is
@@ -264,7 +268,9 @@ __global__ void k_volume_chase2(const int32_t *__restrict__ exit1, const int64_t
     int64_t e = *first;
     while (e < n) {
         entryS[e / VSC] = e;
-        e = exit1[e];
+        const int64_t nx = exit1[e];
+        if (nx <= e) break;          // next() always moves forward; never spin on a corrupt table
+        e = nx;
     }
 }
 
@@ -278,7 +284,9 @@ __global__ void k_volume_chase1(const int32_t *__restrict__ exit0, const int64_t
     const int64_t send = (S + 1) * VSC < n ? (S + 1) * VSC : n;
     while (e < send) {
         entryC[e / VC0] = e;
-        e = exit0[e];
+        const int64_t nx = exit0[e];
+        if (nx <= e) break;
+        e = nx;
     }
 }
 
@@ -288,7 +296,7 @@ __global__ void k_volume_count(const int32_t *__restrict__ next, const int64_t *
     if (c >= nC) return;
     int64_t e = entryC[c], cnt = 0;
     const int64_t cend = (c + 1) * VC0 < n ? (c + 1) * VC0 : n;
-    while (e >= 0 && e < cend) { cnt++; e = next[e]; }
+    while (e >= 0 && e < cend) { cnt++; const int64_t nx = next[e]; if (nx <= e) break; e = nx; }
     counts[c] = cnt;
 }
 
@@ -308,7 +316,7 @@ __global__ void k_volume_emit(const int32_t *__restrict__ next, const int64_t *_
     int64_t e = entryC[c];
     int64_t w = 1 + off[c];            // out[0] = 0 is the open marker
     const int64_t cend = (c + 1) * VC0 < n ? (c + 1) * VC0 : n;
-    while (e >= 0 && e < cend) { out[w++] = e; e = next[e]; }
+    while (e >= 0 && e < cend) { out[w++] = e; const int64_t nx = next[e]; if (nx <= e) break; e = nx; }
     if (c == 0) out[0] = 0;
 }
 
@@ -408,7 +416,7 @@ int fmk_volume_index_impl(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index
     }
     {
         int64_t blocks = cdiv(cdiv(n, VR_SEG), VR_WARPS);
-        const int64_t maxb = (int64_t)ctx->sm_count * 16;
+        const int64_t maxb = (int64_t)ctx->sm_count * 32;
         if (blocks > maxb) blocks = maxb;
         FMK_LAUNCH(ctx, k_volume_replay_seg, (unsigned)blocks, VR_WARPS * 32, 0, t->amount, n, T, next.p,
                    (unsigned long long *)replays.p);

@@ -1268,7 +1268,9 @@ extern "C" int fmk_bar_features_device(fmk_ctx *ctx, const fmk_trades *t, const 
     memset(f, 0, sizeof(*f));
     f->n_bars = nb; f->flags = flags;
     for (int k = 0; k < FMK_COL_COUNT; k++) f->col_off[k] = -1;
-    int64_t cur = 0;
+    // the per-bar block starts with a 512-byte header (magic, n_bars, n_levels, block sizes, flags, column offsets), so a
+    // frame that crossed NVLink / PCIe as raw bytes describes itself (fmk.h: FMK_FRAME_HEADER_BYTES)
+    int64_t cur = FMK_FRAME_HEADER_BYTES;
     if (ix->close_ts) f->col_off[FMK_COL_CLOSE_TS] = frame_put(cur, nb * 8);
     f->col_off[FMK_COL_CLOSE_IDX] = frame_put(cur, nb * 8);
     if (want_ohlcv) {
@@ -1371,6 +1373,15 @@ extern "C" int fmk_bar_features_device(fmk_ctx *ctx, const fmk_trades *t, const 
     };
 #undef COLP
     rc = body();
+    if (!rc) {
+        int64_t hdr[FMK_FRAME_HEADER_BYTES / 8];
+        memset(hdr, 0, sizeof(hdr));
+        hdr[0] = FMK_FRAME_MAGIC; hdr[1] = f->n_bars; hdr[2] = f->n_levels; hdr[3] = f->bar_bytes; hdr[4] = f->level_bytes;
+        hdr[5] = f->flags; hdr[6] = FMK_COL_COUNT;
+        for (int k = 0; k < FMK_COL_COUNT; k++) hdr[8 + k] = f->col_off[k];
+        cudaError_t e = cudaMemcpyAsync(f->bar_block, hdr, sizeof(hdr), cudaMemcpyHostToDevice, ctx->stream);   // pageable: staged before return
+        if (e != cudaSuccess) rc = fmk_fail(ctx, FMK_ERR_CUDA, cudaGetErrorString(e));
+    }
     if (rc) { fmk_frame_free(ctx, f); return rc; }
     *out = f;
     return FMK_OK;

@@ -158,13 +158,27 @@ __device__ __forceinline__ Ewm ew_elem(const EwTick &t) {
 }
 
 // composite of the thread's EW_ITEMS ticks (ticks i = 1..n-1 only; tick 0 is the identity)
+// alpha_io: the reduce pass stores every tick's alpha there and the apply pass reads it back instead of evaluating exp and the
+// two IEEE divisions a second time (8 B/tick more traffic on an fp64-compute-bound kernel; same bits either way)
+template <bool CACHED>
 __device__ __forceinline__ Ewm ew_thread_composite(const int64_t *ts, const double *y, int64_t base, int64_t n,
-                                                   double half_life) {
+                                                   double half_life, double *alpha_io, EwTick (&ticks)[EW_ITEMS]) {
     Ewm f = ewm_identity();
 #pragma unroll
     for (int k = 0; k < EW_ITEMS; k++) {
         const int64_t i = base + k;
-        if (i >= 1 && i < n) f = ewm_compose(f, ew_elem(ew_tick(ts, y, i, half_life)));
+        if (i >= 1 && i < n) {
+            EwTick t;
+            if (CACHED) {
+                const double alpha = alpha_io[i];
+                t = EwTick{alpha, __dadd_rn(1.0, -alpha), y[i]};
+            } else {
+                t = ew_tick(ts, y, i, half_life);
+                alpha_io[i] = t.alpha;
+            }
+            ticks[k] = t;
+            f = ewm_compose(f, ew_elem(t));
+        }
     }
     return f;
 }
@@ -201,47 +215,54 @@ __device__ __forceinline__ Ewm ew_block_excl(const Ewm &x, Ewm *tot) {
 }
 
 __global__ void __launch_bounds__(EW_THREADS) k_ewm_reduce(const int64_t *__restrict__ ts, const double *__restrict__ y,
-                                                           int64_t n, double half_life, Ewm *tile_f) {
+                                                           int64_t n, double half_life, Ewm *tile_f, double *alpha_out) {
     const int64_t base = (int64_t)blockIdx.x * EW_TILE + (int64_t)threadIdx.x * EW_ITEMS;
-    Ewm f = ew_thread_composite(ts, y, base, n, half_life);
+    EwTick ticks[EW_ITEMS];
+    Ewm f = ew_thread_composite<false>(ts, y, base, n, half_life, alpha_out, ticks);
     Ewm tot;
     ew_block_excl(f, &tot);
     if (threadIdx.x == 0) tile_f[blockIdx.x] = tot;
 }
 
-// single block: in-place exclusive scan of tile composites.  Each thread owns EWT_ITEMS consecutive composites, so one
-// block-scan round covers 4096 tiles (1e9 ticks are 488k tiles: 120 rounds instead of 1900)
-constexpr int EWT_ITEMS = 16;
-__global__ void __launch_bounds__(EW_THREADS) k_ewm_tiles(Ewm *tile_f, int64_t ntiles) {
+// Exclusive scan of the tile composites in three small grid-wide steps (1e9 ticks are 488k tiles; a single block walking them
+// took 4 - 6 ms): per group of EW_THREADS tiles a block scan that also emits the group composite, one block scanning the
+// group composites, and a pass that prepends the group prefix.
+__global__ void __launch_bounds__(EW_THREADS) k_ewm_tiles_local(Ewm *tile_f, int64_t ntiles, Ewm *group_f) {
+    const int64_t k = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x;
+    const Ewm x = k < ntiles ? tile_f[k] : ewm_identity();
+    Ewm tot;
+    const Ewm ex = ew_block_excl(x, &tot);
+    if (k < ntiles) tile_f[k] = ex;
+    if (threadIdx.x == 0) group_f[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(EW_THREADS) k_ewm_tiles_top(Ewm *group_f, int64_t ngroups) {
     __shared__ Ewm carry;
     if (threadIdx.x == 0) carry = ewm_identity();
     __syncthreads();
-    for (int64_t b = 0; b < ntiles; b += (int64_t)EW_THREADS * EWT_ITEMS) {
-        const int64_t k0 = b + (int64_t)threadIdx.x * EWT_ITEMS;
-        Ewm x = ewm_identity();
-        for (int q = 0; q < EWT_ITEMS; q++)
-            if (k0 + q < ntiles) x = ewm_compose(x, tile_f[k0 + q]);
+    for (int64_t b = 0; b < ngroups; b += EW_THREADS) {
+        const int64_t k = b + threadIdx.x;
+        Ewm x = k < ngroups ? group_f[k] : ewm_identity();
         Ewm tot;
         Ewm ex = ew_block_excl(x, &tot);
-        const Ewm c = carry;
-        Ewm run = ewm_compose(c, ex);
-        for (int q = 0; q < EWT_ITEMS; q++)
-            if (k0 + q < ntiles) {
-                const Ewm t = tile_f[k0 + q];
-                tile_f[k0 + q] = run;
-                run = ewm_compose(run, t);
-            }
+        Ewm c = carry;
+        if (k < ngroups) group_f[k] = ewm_compose(c, ex);
         __syncthreads();
         if (threadIdx.x == 0) carry = ewm_compose(c, tot);
         __syncthreads();
     }
 }
+__global__ void __launch_bounds__(EW_THREADS) k_ewm_tiles_add(Ewm *tile_f, int64_t ntiles, const Ewm *__restrict__ group_f) {
+    const int64_t k = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x;
+    if (k < ntiles && blockIdx.x > 0) tile_f[k] = ewm_compose(group_f[blockIdx.x], tile_f[k]);
+}
 
 __global__ void __launch_bounds__(EW_THREADS) k_ewm_apply(const int64_t *__restrict__ ts, const double *__restrict__ y,
                                                           int64_t n, double half_life, double sigma_floor,
-                                                          const Ewm *__restrict__ tile_f, double *__restrict__ out) {
+                                                          const Ewm *__restrict__ tile_f, double *__restrict__ out,
+                                                          double *alpha_in) {
     const int64_t base = (int64_t)blockIdx.x * EW_TILE + (int64_t)threadIdx.x * EW_ITEMS;
-    Ewm f = ew_thread_composite(ts, y, base, n, half_life);
+    EwTick ticks[EW_ITEMS];
+    Ewm f = ew_thread_composite<true>(ts, y, base, n, half_life, alpha_in, ticks);
     Ewm tot;
     Ewm ex = ew_block_excl(f, &tot);
     Ewm pre = ewm_compose(tile_f[blockIdx.x], ex);
@@ -253,7 +274,7 @@ __global__ void __launch_bounds__(EW_THREADS) k_ewm_apply(const int64_t *__restr
         const int64_t i = base + k;
         if (i >= n) break;
         if (i == 0) { out[0] = nan; continue; }
-        ew_step(V, V2, Sy, Syy, ew_tick(ts, y, i, half_life));
+        ew_step(V, V2, Sy, Syy, ticks[k]);
         double o;
         if (V > 0.0) {
             const double mean = __ddiv_rn(Sy, V), e2 = __ddiv_rn(Syy, V);
@@ -275,9 +296,16 @@ static int run_ewmst(fmk_ctx *ctx, const int64_t *ts, const double *y, int64_t n
     const int64_t ntiles = cdiv(n, EW_TILE);
     Scratch<Ewm> tiles(ctx);
     FMK_TRY(tiles.alloc(ntiles));
-    FMK_LAUNCH(ctx, k_ewm_reduce, (unsigned)ntiles, EW_THREADS, 0, ts, y, n, half_life, tiles.p);
-    FMK_LAUNCH(ctx, k_ewm_tiles, 1, EW_THREADS, 0, tiles.p, ntiles);
-    FMK_LAUNCH(ctx, k_ewm_apply, (unsigned)ntiles, EW_THREADS, 0, ts, y, n, half_life, sigma_floor, (const Ewm *)tiles.p, out);
+    Scratch<double> alpha(ctx);
+    FMK_TRY(alpha.alloc(n));
+    FMK_LAUNCH(ctx, k_ewm_reduce, (unsigned)ntiles, EW_THREADS, 0, ts, y, n, half_life, tiles.p, alpha.p);
+    const int64_t ngroups = cdiv(ntiles, EW_THREADS);
+    Scratch<Ewm> groups(ctx);
+    FMK_TRY(groups.alloc(ngroups));
+    FMK_LAUNCH(ctx, k_ewm_tiles_local, (unsigned)ngroups, EW_THREADS, 0, tiles.p, ntiles, groups.p);
+    FMK_LAUNCH(ctx, k_ewm_tiles_top, 1, EW_THREADS, 0, groups.p, ngroups);
+    FMK_LAUNCH(ctx, k_ewm_tiles_add, (unsigned)ngroups, EW_THREADS, 0, tiles.p, ntiles, (const Ewm *)groups.p);
+    FMK_LAUNCH(ctx, k_ewm_apply, (unsigned)ntiles, EW_THREADS, 0, ts, y, n, half_life, sigma_floor, (const Ewm *)tiles.p, out, alpha.p);
     return FMK_OK;
 }
 

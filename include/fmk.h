@@ -71,6 +71,12 @@ int fmk_trades_upload(fmk_ctx *ctx, const int64_t *ts, const double *price, cons
  * bar/data_model.py:326-344): 4 B/tick over PCIe, widened exactly to float64 on the device. */
 int fmk_trades_upload_f32amt(fmk_ctx *ctx, const int64_t *ts, const double *price, const float *amount, const int8_t *side,
                              int64_t n, fmk_trades **out);
+/* Month-store loader (the reference's /trades/YYYY-MM tables, bar/data_model.py:420-574): allocate one handle for a whole
+ * time range, then write each partition's columns at its offset (any pointer may be NULL to skip that column; amount may be
+ * float32, widened exactly on the device).  No concatenated host frame is needed. */
+int fmk_trades_alloc(fmk_ctx *ctx, int64_t n, int with_ts, int with_side, fmk_trades **out);
+int fmk_trades_write(fmk_ctx *ctx, fmk_trades *t, int64_t offset, int64_t count, const int64_t *ts, const double *price,
+                     const void *amount, int amount_is_f32, const int8_t *side);
 /* Adds a column to a handle uploaded without it (which: 0 = timestamps int64[n], 1 = side int8[n]). */
 int fmk_trades_add_column(fmk_ctx *ctx, fmk_trades *t, int which, const void *host);
 /* Device-side synthetic BTCUSDT-like stream (SURVEY 8d shape) for bench-size runs. */
@@ -176,6 +182,12 @@ typedef enum {
     FMK_COL_FP_BUY_IMB, FMK_COL_FP_SELL_IMB,                                                  /* u8 */
     FMK_COL_COUNT
 } fmk_col;
+/* The per-bar block begins with a self-describing header of FMK_FRAME_HEADER_BYTES: int64[0] = FMK_FRAME_MAGIC, [1] = n_bars,
+ * [2] = n_levels, [3] = bytes of the per-bar block (header included), [4] = bytes of the per-level block, [5] = flags,
+ * [6] = FMK_COL_COUNT, [8 + k] = byte offset of column k inside its block (-1 = absent).  A gathered frame is the per-bar
+ * block followed (at the next 16-byte boundary) by the per-level block. */
+#define FMK_FRAME_HEADER_BYTES 512
+#define FMK_FRAME_MAGIC 0x464D4B4652414D45ll
 int fmk_bar_features_device(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, int flags, const double *theta,
                             int64_t n_theta, double theta_mult, double price_tick_size, double imbalance_factor,
                             fmk_frame **out);

@@ -195,6 +195,13 @@ def test_comm_single_rank_gather(ctx):
         got = comm.gathered_frame(0)
         assert comm.gathered_bytes() == [len(expect)]
         assert np.array_equal(got, expect)
+        # the gathered bytes describe themselves (512-byte header): the receiver rebuilds every column without side information
+        cols = core.frame_views_from_bytes(got)
+        ix = core.dollar_bar_index(tr, 5e4)
+        ref = core.bar_features_device(tr, ix, core.F_ALL, price_tick_size=0.1).download()
+        assert set(cols) == set(ref)
+        for k in ref:
+            assert_exact(cols[k], ref[k], f"gathered frame column {k}")
     finally:
         comm.destroy()
 
@@ -230,18 +237,20 @@ def test_imbalance_and_run_bars_match_the_own_oracle(ctx, kind, thr, monkeypatch
     side[::53] = 0
     tr = core.DeviceTrades.upload(ts, px, qty, side, ctx=ctx)
     ref = oracle.imbalance_bar_indexer(side, thr, kind)
+    # exact chunk start states from the backward maps (imbalance bars, the default) and the speculative chain (run bars; forced
+    # for imbalance bars with FMK_IMBALANCE_NO_EXACT), lane kernel only / walkers only, three chunk sizes
     for ch in (None, "64", "4096"):
-        for walk in ("0", "1000000000"):
-            if ch:
-                monkeypatch.setenv("FMK_CUSUM_CH", ch)
-            else:
-                monkeypatch.delenv("FMK_CUSUM_CH", raising=False)
-            monkeypatch.setenv("FMK_CUSUM_WALK_BELOW", walk)
+        for walk, no_exact in (("0", None), ("1000000000", "1"), ("0", "1")):
+            for var, val in (("FMK_CUSUM_CH", ch), ("FMK_CUSUM_WALK_BELOW", walk), ("FMK_IMBALANCE_NO_EXACT", no_exact)):
+                if val is None:
+                    monkeypatch.delenv(var, raising=False)
+                else:
+                    monkeypatch.setenv(var, val)
             got = core.imbalance_bar_index(tr, thr, use_side=True, kind=kind).download()
-            assert_exact(got[1], ref, f"kind {kind} thr {thr} CH {ch} walk {walk}")
+            assert_exact(got[1], ref, f"kind {kind} thr {thr} CH {ch} walk {walk} no_exact {no_exact}")
             assert np.array_equal(got[0], ts[ref])
-    monkeypatch.delenv("FMK_CUSUM_CH", raising=False)
-    monkeypatch.delenv("FMK_CUSUM_WALK_BELOW", raising=False)
+    for var in ("FMK_CUSUM_CH", "FMK_CUSUM_WALK_BELOW", "FMK_IMBALANCE_NO_EXACT"):
+        monkeypatch.delenv(var, raising=False)
     # tick rule (the stub's signature has no side argument): b_t from the prices
     tick_sides = oracle.comp_trade_side_vector(px)
     f = _imbalance_bar_indexer if kind == 0 else _run_bar_indexer
@@ -258,12 +267,21 @@ def test_imbalance_bars_adversarial_never_coalescing(ctx, monkeypatch):
     side = np.ones(n, np.int8)
     tr = core.DeviceTrades.upload(ts, np.full(n, 100.0), np.ones(n), side, ctx=ctx)
     monkeypatch.setenv("FMK_CUSUM_CH", "96")
-    for walk in ("0", "1000000000"):
+    for walk, no_exact in (("0", "1"), ("1000000000", "1"), ("0", None)):
         monkeypatch.setenv("FMK_CUSUM_WALK_BELOW", walk)
+        if no_exact:
+            monkeypatch.setenv("FMK_IMBALANCE_NO_EXACT", no_exact)
+        else:
+            monkeypatch.delenv("FMK_IMBALANCE_NO_EXACT", raising=False)
         got = core.imbalance_bar_index(tr, 7.0, use_side=True, kind=0).download()[1]
-        assert_exact(got, oracle.imbalance_bar_indexer(side, 7.0, 0), f"all buys walk {walk}")
-    monkeypatch.delenv("FMK_CUSUM_CH")
-    monkeypatch.delenv("FMK_CUSUM_WALK_BELOW")
+        assert_exact(got, oracle.imbalance_bar_indexer(side, 7.0, 0), f"all buys walk {walk} no_exact {no_exact}")
+        if not no_exact:
+            assert ctx.index_stats()["chain_passes"] == 0            # no repair rounds at all: the start states were exact
+    for thr in (1.0, 0.5, 1500.0, 2048.0, 3000.0):                      # m = 1, the map-size limit, and beyond it (chain)
+        got = core.imbalance_bar_index(tr, thr, use_side=True, kind=0).download()[1]
+        assert_exact(got, oracle.imbalance_bar_indexer(side, thr, 0), f"all buys thr {thr}")
+    for var in ("FMK_CUSUM_CH", "FMK_CUSUM_WALK_BELOW", "FMK_IMBALANCE_NO_EXACT"):
+        monkeypatch.delenv(var, raising=False)
 
 
 def test_imbalance_bar_kit(ctx):
