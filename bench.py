@@ -479,7 +479,7 @@ def run_ours(args):
     comm = None
     if world > 1:
         from finmlkit_b200.parallel import Comm
-        comm = Comm.from_env(ctx, max_ctas=env_int("FMK_NCCL_MAX_CTAS", 4))
+        comm = Comm.from_env(ctx, max_ctas=env_int("FMK_NCCL_MAX_CTAS", 16))
     n = args.ticks
     sub_steps, sub_warm = max(1, min(args.steps, args.sub_steps)), 1
     tr = core.DeviceTrades.synth(n, seed=42 + rank, ctx=ctx)   # one independent symbol per rank
@@ -596,6 +596,8 @@ def run_ours(args):
 
     # ---- config 5: dollar bars + FULL feature set + gather of every frame (all N) ----------------------------------------
     if not args.no_sub and not args.no_config5:
+        if comm:
+            comm.gather_reset()          # the headline's small-frame pipeline (3 slots) must not be kept for 4 GB frames
         n5 = int(min(args.config5_ticks, n))
         tr5 = tr if n5 == n else core.DeviceTrades.synth(n5, seed=1042 + rank, ctx=ctx)
 
@@ -832,18 +834,31 @@ def run_e2e(args, core, ctx, comm, tr, n, rank, world, sub):
         from finmlkit_b200.bar.kit import DollarBarKit, TimeBarKit
         n1 = min(n_e, 1_000_000)
         td1 = TradesData(np.array(h_ts[:n1]), np.array(h_px[:n1]), np.array(h_qty[:n1]), side=np.array(h_side[:n1]))
-        sec1, nb1 = best_of(lambda: len(TimeBarKit(td1, pd.Timedelta(minutes=1), ctx=ctx).build_ohlcv()), reps=5)
+        def cold(make):
+            # a cold call: the frame's device copy is dropped first, so the upload is inside the timed call (a second kit
+            # on the same TradesData would find the columns resident -- reported separately as "warm")
+            def f():
+                core.clear_device_cache()
+                return len(make().build_ohlcv())
+            return f
+        sec1, nb1 = best_of(cold(lambda: TimeBarKit(td1, pd.Timedelta(minutes=1), ctx=ctx)), reps=5)
+        sec1w, _ = best_of(lambda: len(TimeBarKit(td1, pd.Timedelta(minutes=1), ctx=ctx).build_ohlcv()), reps=5)
         extra["config1"] = {"workload": f"BASELINE configs[0]: {n1} ticks -> TimeBarKit(trades, 1 min).build_ohlcv() (pandas in, pandas out; "
                                         "upload + kernels + download + frame assembly inside the timed call)",
-                            "ours": {"ticks_per_s": n1 / sec1, "seconds": sec1, "bars": nb1},
+                            "ours": {"ticks_per_s": n1 / sec1, "seconds": sec1, "bars": nb1,
+                                     "warm_ticks_per_s_columns_already_resident": n1 / sec1w},
                             "cpu_baseline": cs["config1"].get("wrapper", cs["config1"]["kernels"]),
                             "cpu_baseline_kernels": cs["config1"]["kernels"], "published": cs["config1"]["published"]}
         nw = int(min(n_e, args.wrapper_ticks))
         try:
             tdw = TradesData(np.array(h_ts[:nw]), np.array(h_px[:nw]), np.array(h_qty[:nw]), side=np.array(h_side[:nw]))
-            secw, nbw = best_of(lambda: len(DollarBarKit(tdw, THRESHOLD, ctx=ctx).build_ohlcv()), reps=2)
-            rec = {"workload": f"DollarBarKit(trades, 1e6).build_ohlcv() on {nw} ticks, pageable pandas columns (bar/kit.py:110-137)",
-                   "ours": {"ticks_per_s": nw / secw, "seconds": secw, "bars": nbw}}
+            secw, nbw = best_of(cold(lambda: DollarBarKit(tdw, THRESHOLD, ctx=ctx)), reps=3)
+            secww, _ = best_of(lambda: len(DollarBarKit(tdw, THRESHOLD, ctx=ctx).build_ohlcv()), reps=2)
+            rec = {"workload": f"DollarBarKit(trades, 1e6).build_ohlcv() on {nw} ticks, pageable pandas columns (bar/kit.py:110-137); "
+                               "cold call: upload (staged multi-threaded H2D of price + amount) + kernels + download + frame assembly",
+                   "ours": {"ticks_per_s": nw / secw, "seconds": secw, "bars": nbw,
+                            "warm_ticks_per_s_columns_already_resident": nw / secww}}
+            core.clear_device_cache()
             del tdw
             tdr = ref.trades_data(np.array(h_ts[:nw]), np.array(h_px[:nw]), np.array(h_qty[:nw]), np.array(h_side[:nw]))
             kit = ref.dollar_kit(tdr)

@@ -100,6 +100,7 @@ SIGNATURES = {
     "fmk_comm_allreduce_f64": (INT, [P, P, INT, INT]),
     "fmk_comm_gather_submit": (INT, [P, P, P, INT, INT]),
     "fmk_comm_gather_finish": (INT, [P]),
+    "fmk_comm_gather_reset": (INT, [P]),
     "fmk_comm_gather_result": (INT, [P, INT, C.POINTER(P), C.POINTER(I64)]),
     "fmk_comm_gather_download": (INT, [P, INT, P, I64]),
     "fmk_triple_barrier": (INT, [P, P, P, P, I64, I64, F64, F64, F64, F64, P, I64, F64, P, P, P, P]),

@@ -7,8 +7,10 @@
 // step k+1:
 //     submit(k):  [ctx stream]  pack the step's segments into staging[k&1] (device-to-device), record `ready`
 //                 [comm stream] wait `ready`; all-gather the counts; copy them to pinned host memory; record `sized`
-//     submit(k+1) / finish():   host waits `sized(k)` (the GPU already has step k+1's kernels queued, so it stays busy),
-//                               sizes the receive buffers, posts the grouped send/recv of step k on the comm stream
+//     submit(k+LAG) / finish(): host waits `sized(k)` (long done by then), sizes the receive buffers, posts the grouped
+//                               send/recv of step k on the comm stream.  LAG = 2 by default: when the transfer is posted every
+//                               rank has packed that frame, so no NCCL kernel sits on SMs spinning for a slower peer (with
+//                               LAG = 1 the receive kernel of rank 0 held its CTAs until the slowest sender arrived)
 //     finish():   the ctx stream waits for the last transfer, so a timer stopped on it covers every gather.
 // libnccl is loaded with dlopen at fmk_comm_init: single-GPU use of libfmk.so needs no NCCL at all.
 #include <dlfcn.h>
@@ -66,6 +68,7 @@ const char *nccl_load() {
 }  // namespace
 
 constexpr int FMK_COMM_MAXSEG = 8;
+constexpr int FMK_COMM_SLOTS = 4;
 
 struct fmk_comm {
     fmk_ctx *ctx;
@@ -73,19 +76,19 @@ struct fmk_comm {
     int rank, world;
     cudaStream_t stream;            // communication stream
     // per pipeline slot
-    char *staging[2];               // packed frame of this rank
-    int64_t staging_cap[2];
-    cudaEvent_t ready[2], sized[2], done[2];
-    int has_done[2];
-    int64_t *counts_dev[2];         // [world] byte counts after the all-gather
-    int64_t *counts_host[2];        // pinned
-    int64_t *mine_host[2];          // pinned: this rank's byte count (source of the all-gather input)
-    int64_t *mine_dev[2];
-    char *recv[2];                  // dst only: frames of all ranks, back to back
-    int64_t recv_cap[2];
-    int64_t recv_off[2][65];        // dst only: offsets of each rank's frame in recv[s]
-    int pending;                    // slot whose counts were exchanged but whose send/recv is not posted yet (-1: none)
-    int pending_dst;
+    char *staging[FMK_COMM_SLOTS];               // packed frame of this rank
+    int64_t staging_cap[FMK_COMM_SLOTS];
+    cudaEvent_t ready[FMK_COMM_SLOTS], sized[FMK_COMM_SLOTS], done[FMK_COMM_SLOTS];
+    int has_done[FMK_COMM_SLOTS];
+    int64_t *counts_dev[FMK_COMM_SLOTS];         // [world] byte counts after the all-gather
+    int64_t *counts_host[FMK_COMM_SLOTS];        // pinned
+    int64_t *mine_host[FMK_COMM_SLOTS];          // pinned: this rank's byte count (source of the all-gather input)
+    int64_t *mine_dev[FMK_COMM_SLOTS];
+    char *recv[FMK_COMM_SLOTS];                  // dst only: frames of all ranks, back to back
+    int64_t recv_cap[FMK_COMM_SLOTS];
+    int64_t recv_off[FMK_COMM_SLOTS][65];        // dst only: offsets of each rank's frame in recv[s]
+    int pend_slot[FMK_COMM_SLOTS], pend_dst[FMK_COMM_SLOTS];   // FIFO of steps whose counts were exchanged but whose send/recv is not posted yet
+    int npending, lag, nslots;
     int last;                       // slot of the last completed gather (-1: none)
     int64_t k;                      // steps submitted
     double *scal_dev;               // small device scratch for barrier / host all-reduce
@@ -123,7 +126,9 @@ int fmk_comm_init(fmk_ctx *ctx, const void *id128, int rank, int world, int max_
     fmk_comm *c = new (std::nothrow) fmk_comm();
     if (!c) return FMK_ERR_ALLOC;
     memset(c, 0, sizeof(*c));
-    c->ctx = ctx; c->rank = rank; c->world = world; c->pending = -1; c->last = -1;
+    c->ctx = ctx; c->rank = rank; c->world = world; c->npending = 0; c->last = -1;
+    c->lag = 2;
+    if (const char *e = getenv("FMK_COMM_LAG")) c->lag = atoi(e) >= 1 && atoi(e) <= FMK_COMM_SLOTS - 1 ? atoi(e) : c->lag;
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
     ncclResult_t r;
@@ -142,7 +147,7 @@ int fmk_comm_init(fmk_ctx *ctx, const void *id128, int rank, int world, int max_
         return fmk_fail(ctx, FMK_ERR_CUDA, b);
     }
     cudaError_t ce = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    for (int s = 0; s < 2 && ce == cudaSuccess; s++) {
+    for (int s = 0; s < FMK_COMM_SLOTS && ce == cudaSuccess; s++) {
         ce = cudaEventCreateWithFlags(&c->ready[s], cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->sized[s], cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->done[s], cudaEventDisableTiming);
@@ -154,6 +159,8 @@ int fmk_comm_init(fmk_ctx *ctx, const void *id128, int rank, int world, int max_
     if (ce == cudaSuccess) ce = cudaMalloc(&c->scal_dev, 64 * sizeof(double));
     if (ce == cudaSuccess) ce = cudaHostAlloc(&c->scal_host, 64 * sizeof(double), cudaHostAllocDefault);
     if (ce != cudaSuccess) return fmk_fail(ctx, FMK_ERR_CUDA, cudaGetErrorString(ce));
+    // kernels whose grid is sized to fill an exact number of waves (the dollar task pass) must not count the SMs NCCL takes
+    if (world > 1) ctx->reserved_sms = max_ctas > 0 ? (max_ctas < ctx->sm_count / 2 ? max_ctas : ctx->sm_count / 2) : 16;
     *out = c;
     return FMK_OK;
 }
@@ -163,7 +170,7 @@ void fmk_comm_destroy(fmk_comm *c) {
     cudaSetDevice(c->ctx->device);
     cudaStreamSynchronize(c->stream);
     if (c->comm) g_nccl.CommDestroy(c->comm);
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < FMK_COMM_SLOTS; s++) {
         cudaFree(c->staging[s]); cudaFree(c->recv[s]); cudaFree(c->counts_dev[s]); cudaFree(c->mine_dev[s]);
         cudaFreeHost(c->counts_host[s]); cudaFreeHost(c->mine_host[s]);
         cudaEventDestroy(c->ready[s]); cudaEventDestroy(c->sized[s]); cudaEventDestroy(c->done[s]);
@@ -210,10 +217,12 @@ static int comm_grow(fmk_ctx *ctx, char **buf, int64_t *cap, int64_t need, cudaS
 }
 
 // post the send / recv of the slot whose byte counts have been exchanged
-static int comm_complete_pending(fmk_comm *c) {
+static int comm_complete_oldest(fmk_comm *c) {
     fmk_ctx *ctx = c->ctx;
-    if (c->pending < 0) return FMK_OK;
-    const int s = c->pending, dst = c->pending_dst;
+    if (c->npending <= 0) return FMK_OK;
+    const int s = c->pend_slot[0], dst = c->pend_dst[0];
+    for (int q = 1; q < c->npending; q++) { c->pend_slot[q - 1] = c->pend_slot[q]; c->pend_dst[q - 1] = c->pend_dst[q]; }
+    c->npending--;
     FMK_CUDA(ctx, cudaEventSynchronize(c->sized[s]));
     const int64_t *cnt = c->counts_host[s];
     if (c->rank == dst) {
@@ -237,7 +246,11 @@ static int comm_complete_pending(fmk_comm *c) {
     FMK_CUDA(ctx, cudaEventRecord(c->done[s], c->stream));
     c->has_done[s] = 1;
     c->last = s;
-    c->pending = -1;
+    return FMK_OK;
+}
+// keep at most `keep` steps waiting for their transfer
+static int comm_complete_pending(fmk_comm *c, int keep) {
+    while (c->npending > keep) FMK_TRY(comm_complete_oldest(c));
     return FMK_OK;
 }
 
@@ -248,13 +261,19 @@ int fmk_comm_gather_submit(fmk_comm *c, const void *const *seg_ptrs, const int64
     FMK_ENTER(ctx);
     if (nseg < 0 || nseg > FMK_COMM_MAXSEG) return fmk_fail(ctx, FMK_ERR_ARG, "too many segments");
     if (dst < 0 || dst >= c->world) return fmk_fail(ctx, FMK_ERR_ARG, "bad destination rank");
-    FMK_TRY(comm_complete_pending(c));
-    const int s = (int)(c->k & 1);
     int64_t total = 0;
     for (int q = 0; q < nseg; q++) {
         if (seg_bytes[q] < 0) return fmk_fail(ctx, FMK_ERR_ARG, "negative segment size");
         total += (seg_bytes[q] + 15) / 16 * 16;
     }
+    if (c->k == 0) {
+        // pipeline depth is fixed by the first frame: lag + 1 staging / receive slots; the destination holds world frames per
+        // slot, so multi-GB frames (footprint CSR of 5e8 ticks: 4 GB per rank) fall back to the two-slot pipeline
+        if (total * (int64_t)c->world > ((int64_t)4 << 30)) c->lag = 1;
+        c->nslots = c->lag + 1;
+    }
+    FMK_TRY(comm_complete_pending(c, c->lag - 1));
+    const int s = (int)(c->k % c->nslots);
     if (c->has_done[s]) {             // the transfer that read this slot two steps ago must be finished before it is rewritten
         FMK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, c->done[s], 0));
     }
@@ -272,8 +291,9 @@ int fmk_comm_gather_submit(fmk_comm *c, const void *const *seg_ptrs, const int64
     FMK_NCCL(ctx, g_nccl.AllGather(c->mine_dev[s], c->counts_dev[s], 1, ncclInt64, c->comm, c->stream));
     FMK_CUDA(ctx, cudaMemcpyAsync(c->counts_host[s], c->counts_dev[s], 8 * (size_t)c->world, cudaMemcpyDeviceToHost, c->stream));
     FMK_CUDA(ctx, cudaEventRecord(c->sized[s], c->stream));
-    c->pending = s;
-    c->pending_dst = dst;
+    c->pend_slot[c->npending] = s;
+    c->pend_dst[c->npending] = dst;
+    c->npending++;
     c->k++;
     return FMK_OK;
 }
@@ -283,9 +303,28 @@ int fmk_comm_gather_submit(fmk_comm *c, const void *const *seg_ptrs, const int64
 int fmk_comm_gather_finish(fmk_comm *c) {
     fmk_ctx *ctx = c->ctx;
     FMK_ENTER(ctx);
-    FMK_TRY(comm_complete_pending(c));
-    for (int s = 0; s < 2; s++)
+    FMK_TRY(comm_complete_pending(c, 0));
+    for (int s = 0; s < FMK_COMM_SLOTS; s++)
         if (c->has_done[s]) FMK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, c->done[s], 0));
+    return FMK_OK;
+}
+
+// Ends a sequence of gather steps: waits for everything outstanding, releases the staging / receive buffers and lets the next
+// fmk_comm_gather_submit size the pipeline afresh (a host that gathers small OHLCV frames first and multi-GB footprint
+// frames later must not keep three receive slots of the large size).
+int fmk_comm_gather_reset(fmk_comm *c) {
+    fmk_ctx *ctx = c->ctx;
+    FMK_ENTER(ctx);
+    FMK_TRY(fmk_comm_gather_finish(c));
+    FMK_CUDA(ctx, cudaStreamSynchronize(c->stream));
+    FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int s = 0; s < FMK_COMM_SLOTS; s++) {
+        cudaFree(c->staging[s]); c->staging[s] = nullptr; c->staging_cap[s] = 0;
+        cudaFree(c->recv[s]); c->recv[s] = nullptr; c->recv_cap[s] = 0;
+        c->has_done[s] = 0;
+    }
+    c->k = 0; c->last = -1; c->lag = 2;
+    if (const char *e = getenv("FMK_COMM_LAG")) c->lag = atoi(e) >= 1 && atoi(e) <= FMK_COMM_SLOTS - 1 ? atoi(e) : c->lag;
     return FMK_OK;
 }
 

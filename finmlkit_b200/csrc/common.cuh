@@ -16,6 +16,7 @@ struct fmk_ctx {
     cudaStream_t stream;
     cudaEvent_t ev0, ev1;
     int sm_count;
+    int reserved_sms;                     // SMs a concurrent communicator may occupy (fmk_comm_init sets it): wave-exact grids plan without them
     int64_t launches;
     char err[512];
     // ctx-owned result columns of fmk_bar_ohlcv_device (kept so the device-resident bench has real outputs)

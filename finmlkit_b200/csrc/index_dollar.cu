@@ -386,7 +386,7 @@ static int64_t dollar_pick_chunk(fmk_ctx *ctx, int64_t n) {
     int bps = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_dollar_tasks, DT_WARPS * 32, 0) != cudaSuccess || bps <= 0)
         return DOLLAR_CH;
-    const int64_t resident = (int64_t)bps * ctx->sm_count * DT_WARPS * 32;
+    const int64_t resident = (int64_t)bps * (ctx->sm_count - ctx->reserved_sms) * DT_WARPS * 32;
     if (n < resident * DOLLAR_CH) return DOLLAR_CH;
     int64_t best = DOLLAR_CH;
     double best_cost = 1e300;

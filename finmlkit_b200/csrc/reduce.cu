@@ -356,8 +356,11 @@ __device__ __forceinline__ unsigned rs_word(unsigned d) {   // lane L of the sca
     return ((w & 15u) << 5) | (w >> 4);
 }
 
+// fused_shift >= 0: the caller already built the first-level histogram while streaming the bar, with that shift (see
+// k_bar_ohlcv_median); it is used when it is the shift this bar needs.  *shift_out receives the first-level shift.
 __device__ bool warp_select_raw(const double *__restrict__ seg, int ncnt, int kk, bool want1, unsigned long long ro,
-                                unsigned long long ra, unsigned *hist, double *r0, double *r1) {
+                                unsigned long long ra, unsigned *hist, double *r0, double *r1, int fused_shift = -1,
+                                int *shift_out = nullptr) {
     const int lane = threadIdx.x & 31;
     const unsigned *segw = reinterpret_cast<const unsigned *>(seg);   // high word of element q: segw[2q + 1]
     unsigned *cidx = hist + RS_WORDS;          // 32 candidate indices
@@ -368,11 +371,15 @@ __device__ bool warp_select_raw(const double *__restrict__ seg, int ncnt, int kk
     for (;;) {
         const int hb = 31 - __clz(diff_hi);
         const int shift = hb >= 9 ? hb - 9 : 0;
-        __syncwarp();                          // earlier readers of the histogram (previous level / previous bar) are done
+        if (mask == 0u && shift_out) *shift_out = shift;
+        const bool have_hist = mask == 0u && fused_shift == shift;      // first level already counted during the streaming pass
+        __syncwarp();                          // earlier readers / writers of the histogram (previous level, streaming pass) are done
+        if (!have_hist) {
 #pragma unroll
-        for (int q = 0; q < RS_WORDS / 32; q++) hist[q * 32 + lane] = 0u;
-        __syncwarp();
-        {
+            for (int q = 0; q < RS_WORDS / 32; q++) hist[q * 32 + lane] = 0u;
+            __syncwarp();
+        }
+        if (!have_hist) {
             int q = lane;
             if (mask == 0u) {                  // first level: every element is in play
                 for (; q + 224 < ncnt; q += 256) {      // eight loads in flight per lane: half as many L2 round trips
@@ -532,6 +539,13 @@ __global__ void __launch_bounds__(OS_WARPS * 32, 5) k_bar_ohlcv_median(const dou
     static_assert(RS_WORDS + 33 <= OS_HIST, "raw-select scratch must fit the generic histogram");
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    // The first-level histogram of the median select is built DURING the streaming pass, with the digit position the previous
+    // bar of this warp needed (sizes of neighbouring bars live in the same binades): when the guess is right -- almost always --
+    // the select starts with its bucket scan instead of another pass over the bar through L2 (the kernel is latency-bound on
+    // exactly those re-reads: ncu long_scoreboard 7.65 warps per issue in round 1).  A wrong guess costs nothing but the wasted
+    // shared-memory atomics: the select then builds the histogram itself, as before.
+    int pred_shift = 15;
+    unsigned *const fh = hist_s[w];
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nb; i += nwarps) {
         const int64_t s = ci[i], e = ci[i + 1];
         if (s == e) {
@@ -539,12 +553,25 @@ __global__ void __launch_bounds__(OS_WARPS * 32, 5) k_bar_ohlcv_median(const dou
             continue;
         }
         const int64_t start = s + 1;
+        const bool fuse = e - start + 1 < 65536;       // packed 16-bit counters
+        __syncwarp();
+        if (fuse) {
+#pragma unroll
+            for (int q = 0; q < RS_WORDS / 32; q++) fh[q * 32 + lane] = 0u;
+        }
+        __syncwarp();
+#define FMK_FUSED_COUNT(x)                                                                    \
+        {                                                                                     \
+            const unsigned d__ = ((unsigned)__double2hiint(x) >> pred_shift) & 1023u;         \
+            atomicAdd(&fh[rs_word(d__)], (d__ & 1u) ? 65536u : 1u);                           \
+        }
         double hi = -INFINITY, lo = INFINITY, sv = 0.0, sd = 0.0;
         unsigned long long ro = 0ull, ra = ~0ull;
         int64_t j = start + lane;
         for (; j + 96 <= e; j += 128) {
             const double p0 = __ldg(p + j), p1 = __ldg(p + j + 32), p2 = __ldg(p + j + 64), p3 = __ldg(p + j + 96);
             const double v0 = __ldg(v + j), v1 = __ldg(v + j + 32), v2 = __ldg(v + j + 64), v3 = __ldg(v + j + 96);
+            if (fuse) { FMK_FUSED_COUNT(v0) FMK_FUSED_COUNT(v1) FMK_FUSED_COUNT(v2) FMK_FUSED_COUNT(v3) }
             // strict compares like the reference (base.py:381-384): a NaN price never replaces the running high / low
             hi = p0 > hi ? p0 : hi; hi = p1 > hi ? p1 : hi; hi = p2 > hi ? p2 : hi; hi = p3 > hi ? p3 : hi;
             lo = p0 < lo ? p0 : lo; lo = p1 < lo ? p1 : lo; lo = p2 < lo ? p2 : lo; lo = p3 < lo ? p3 : lo;
@@ -557,11 +584,13 @@ __global__ void __launch_bounds__(OS_WARPS * 32, 5) k_bar_ohlcv_median(const dou
         }
         for (; j <= e; j += 32) {
             const double pj = __ldg(p + j), vj = __ldg(v + j);
+            if (fuse) FMK_FUSED_COUNT(vj)
             hi = pj > hi ? pj : hi; lo = pj < lo ? pj : lo;
             sv += vj; sd += pj * vj;
             const unsigned long long kj = (unsigned long long)__double_as_longlong(vj);
             ro |= kj; ra &= kj;
         }
+#undef FMK_FUSED_COUNT
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             const double h2 = __shfl_xor_sync(FULL, hi, d), l2 = __shfl_xor_sync(FULL, lo, d);
@@ -582,7 +611,11 @@ __global__ void __launch_bounds__(OS_WARPS * 32, 5) k_bar_ohlcv_median(const dou
         double r0, r1;
         bool done = false;
         if (ro == ra) { r0 = r1 = __longlong_as_double((long long)ro); done = true; }      // all sizes identical
-        else if (!(ro >> 63) && cnt < 65536) done = warp_select_raw(v + start, (int)cnt, (int)mk, !odd, ro, ra, hist_s[w], &r0, &r1);
+        else if (!(ro >> 63) && cnt < 65536) {
+            int used = pred_shift;
+            done = warp_select_raw(v + start, (int)cnt, (int)mk, !odd, ro, ra, hist_s[w], &r0, &r1, pred_shift, &used);
+            pred_shift = used;
+        }
         if (!done) {
             __syncwarp();
             warp_select_two(v + start, cnt, mk, hist_s[w], cand_s[w], &r0, &r1);
@@ -904,16 +937,19 @@ struct OffOut {
 // flushed once: the float32 sums are order-dependent, so every 32-tick step is a read-modify-write of the (level, side)
 // cells it touches, and doing that through global memory cost two L2 round trips per step (17.8 ms at 1e9 ticks,
 // latency-bound at 32 % issue activity).  Wider bars keep the global-memory path.
-constexpr int FP_CAP = 192;
+// The capacity is a launch parameter (dynamic shared memory): it is sized from the average number of levels per bar of the
+// call (a $1M dollar bar of the synthetic stream spans ~300 levels, a 50-BTC volume bar ~440: the fixed 192 of round 1 sent
+// most of those bars down the global-memory path).
 __global__ void __launch_bounds__(256) k_bar_footprint(const double *__restrict__ p, const double *__restrict__ a,
                                                        const int8_t *__restrict__ side,
                                                        const int64_t *__restrict__ ci, int64_t nb,
                                                        const double *__restrict__ lows, double tick,
                                                        const int64_t *__restrict__ off, int32_t *levels, float *bvol,
-                                                       float *svol, int32_t *bt, int32_t *st, int *err) {
-    __shared__ float vol_s[8][2 * FP_CAP];        // [warp][2 * level + side]
-    __shared__ int32_t cnt_s[8][2 * FP_CAP];
+                                                       float *svol, int32_t *bt, int32_t *st, int *err, int FP_CAP) {
+    extern __shared__ float fp_smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float *const vol_w = fp_smem + (size_t)w * 4 * FP_CAP;                 // [2 * level + side]
+    int32_t *const cnt_w = reinterpret_cast<int32_t *>(vol_w + 2 * FP_CAP);
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nb; i += nwarps) {
         const int64_t start = ci[i] + 1, e = ci[i + 1];
@@ -922,7 +958,7 @@ __global__ void __launch_bounds__(256) k_bar_footprint(const double *__restrict_
         const bool in_smem = L <= FP_CAP;
         __syncwarp();
         if (in_smem) {
-            for (int k = lane; k < 2 * (int)L; k += 32) { vol_s[w][k] = 0.0f; cnt_s[w][k] = 0; }
+            for (int k = lane; k < 2 * (int)L; k += 32) { vol_w[k] = 0.0f; cnt_w[k] = 0; }
         } else {
             for (int64_t k = lane; k < L; k += 32) { bvol[o + k] = 0.0f; svol[o + k] = 0.0f; bt[o + k] = 0; st[o + k] = 0; }
         }
@@ -948,7 +984,7 @@ __global__ void __launch_bounds__(256) k_bar_footprint(const double *__restrict_
             float *vp = nullptr;
             int32_t *tp = nullptr;
             if (lead) {
-                if (in_smem) { vp = &vol_s[w][bin]; tp = &cnt_s[w][bin]; }
+                if (in_smem) { vp = &vol_w[bin]; tp = &cnt_w[bin]; }
                 else {
                     const int64_t lv = o + (bin >> 1);
                     vp = (bin & 1) ? svol + lv : bvol + lv;
@@ -974,8 +1010,8 @@ __global__ void __launch_bounds__(256) k_bar_footprint(const double *__restrict_
         }
         if (in_smem) {
             for (int k = lane; k < (int)L; k += 32) {
-                bvol[o + k] = vol_s[w][2 * k]; svol[o + k] = vol_s[w][2 * k + 1];
-                bt[o + k] = cnt_s[w][2 * k]; st[o + k] = cnt_s[w][2 * k + 1];
+                bvol[o + k] = vol_w[2 * k]; svol[o + k] = vol_w[2 * k + 1];
+                bt[o + k] = cnt_w[2 * k]; st[o + k] = cnt_w[2 * k + 1];
             }
         }
     }
@@ -1120,8 +1156,15 @@ static int fp_fill(fmk_ctx *ctx, const fmk_trades *t, const fmk_index *ix, const
     int64_t blocks = cdiv(nb, 8);
     int64_t maxb = (int64_t)ctx->sm_count * 64;
     if (blocks > maxb) blocks = maxb;
-    FMK_LAUNCH(ctx, k_bar_footprint, (unsigned)blocks, 256, 0, t->price, t->amount, t->side, ix->close_idx, nb, dlows, tick,
-               fp->level_offsets, fp->price_levels, fp->buy_vol, fp->sell_vol, fp->buy_ticks, fp->sell_ticks, err_dev);
+    // shared-memory capacity (levels per warp), 16 bytes per level and warp.  Measured on B200 at 1e9 ticks (volume bars of ~440
+    // levels / dollar bars of ~300): 192 -> 18.1 / 18.1 ms, 320 -> 17.7 / 16.4, 448 -> 16.5 / 15.7, 576 -> 18.4 / 18.3,
+    // 832 -> 23.8 / 24.2 ms: beyond 448 the lost occupancy (3 -> 2 blocks per SM) costs more than the shared-memory path saves
+    int cap = 448;
+    if (const char *e = getenv("FMK_FP_CAP")) cap = atoi(e) > 0 ? atoi(e) : cap;      // profiling override
+    const size_t fp_smem_bytes = (size_t)8 * 4 * cap * sizeof(float);
+    FMK_CUDA(ctx, cudaFuncSetAttribute(k_bar_footprint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp_smem_bytes));
+    FMK_LAUNCH(ctx, k_bar_footprint, (unsigned)blocks, 256, fp_smem_bytes, t->price, t->amount, t->side, ix->close_idx, nb, dlows, tick,
+               fp->level_offsets, fp->price_levels, fp->buy_vol, fp->sell_vol, fp->buy_ticks, fp->sell_ticks, err_dev, cap);
     FMK_LAUNCH(ctx, k_footprint_features, (unsigned)cdiv(nb, FF_WARPS * 32), FF_WARPS * 32, 0, fp->level_offsets, nb, fp->price_levels,
                fp->buy_vol, fp->sell_vol, factor, fp->buy_imb, fp->sell_imb, fp->buy_imb_sum, fp->sell_imb_sum, fp->cot,
                fp->run_signed, fp->vp_skew, fp->vp_gini);

@@ -171,6 +171,10 @@ class Comm:
     def gather_finish(self):
         self.ctx.check(self._L.fmk_comm_gather_finish(self.h))
 
+    def gather_reset(self):
+        """finish, release the staging / receive buffers, and let the next submit size the pipeline from its own frame"""
+        self.ctx.check(self._L.fmk_comm_gather_reset(self.h))
+
     def gathered_bytes(self):
         """exact byte count of every rank's frame in the last finished gather"""
         out = []

@@ -218,6 +218,8 @@ int fmk_comm_barrier(fmk_comm *c);
 int fmk_comm_allreduce_f64(fmk_comm *c, double *inout, int n, int op);
 int fmk_comm_gather_submit(fmk_comm *c, const void *const *seg_ptrs, const int64_t *seg_bytes, int nseg, int dst);
 int fmk_comm_gather_finish(fmk_comm *c);
+/* finish + release the staging / receive buffers; the next submit sizes the pipeline from its own frame */
+int fmk_comm_gather_reset(fmk_comm *c);
 int fmk_comm_gather_result(fmk_comm *c, int rank, void **dev_ptr, int64_t *bytes);
 int fmk_comm_gather_download(fmk_comm *c, int rank, void *host, int64_t cap);
 
