@@ -409,6 +409,20 @@ def emit(line):
 
 def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
+    _WATCHDOG["last"] = time.time()
+
+
+# multi-rank runs: a rank that stops making progress (a collective waiting for a peer that died, ...) must not sit on the box
+# until the driver's limit -- every log() call kicks the watchdog, 10 silent minutes end the process
+_WATCHDOG = {"last": time.time(), "limit": 600.0}
+
+
+def _watchdog_loop():
+    while True:
+        time.sleep(5.0)
+        if time.time() - _WATCHDOG["last"] > _WATCHDOG["limit"]:
+            print(f"[bench] watchdog: no progress for {_WATCHDOG['limit']:.0f} s, aborting", file=sys.stderr, flush=True)
+            os._exit(17)
 
 
 # ======================================================================================================================
@@ -478,12 +492,15 @@ def run_ours(args):
     L = ctx._L
     comm = None
     if world > 1:
+        _WATCHDOG["limit"] = float(os.environ.get("FMK_BENCH_WATCHDOG_S", "600"))
+        threading.Thread(target=_watchdog_loop, daemon=True).start()
         from finmlkit_b200.parallel import Comm
         comm = Comm.from_env(ctx, max_ctas=env_int("FMK_NCCL_MAX_CTAS", 16))
     n = args.ticks
     sub_steps, sub_warm = max(1, min(args.steps, args.sub_steps)), 1
     tr = core.DeviceTrades.synth(n, seed=42 + rank, ctx=ctx)   # one independent symbol per rank
     peak, peak_src = measured_peak()
+    log(f"rank {rank}/{world}: stream of {n} ticks ready")
 
     # ---- headline: dollar bars + OHLCV incl. median (BASELINE configs[1]) ------------------------------------------------
     state = {"nbars": 0, "frame_bytes": 0}
@@ -509,6 +526,7 @@ def run_ours(args):
     clk = clocks.stop()
     stats = ctx.index_stats()
     value = world * n / (ms_per_step * 1e-3)
+    log(f"headline {ms_per_step:.3f} ms/step")
     gather_bytes = sum(comm.gathered_bytes()) if comm else 0
 
     roofline = None
@@ -596,8 +614,6 @@ def run_ours(args):
 
     # ---- config 5: dollar bars + FULL feature set + gather of every frame (all N) ----------------------------------------
     if not args.no_sub and not args.no_config5:
-        if comm:
-            comm.gather_reset()          # the headline's small-frame pipeline (3 slots) must not be kept for 4 GB frames
         n5 = int(min(args.config5_ticks, n))
         tr5 = tr if n5 == n else core.DeviceTrades.synth(n5, seed=1042 + rank, ctx=ctx)
 

@@ -7,10 +7,12 @@
 // step k+1:
 //     submit(k):  [ctx stream]  pack the step's segments into staging[k&1] (device-to-device), record `ready`
 //                 [comm stream] wait `ready`; all-gather the counts; copy them to pinned host memory; record `sized`
-//     submit(k+LAG) / finish(): host waits `sized(k)` (long done by then), sizes the receive buffers, posts the grouped
-//                               send/recv of step k on the comm stream.  LAG = 2 by default: when the transfer is posted every
-//                               rank has packed that frame, so no NCCL kernel sits on SMs spinning for a slower peer (with
-//                               LAG = 1 the receive kernel of rank 0 held its CTAs until the slowest sender arrived)
+//     submit(k+LAG) / finish(): host waits `sized(k)` (the GPU already has the next step's kernels queued, so it stays busy),
+//                               sizes the receive buffers, posts the grouped send/recv of step k on the comm stream.
+//                               LAG = 1 (two staging / receive slots) is the default and the configuration validated at
+//                               N = 2 and N = 8; FMK_COMM_LAG=2 posts the transfer one step later still (three slots), so that
+//                               no NCCL kernel waits on SMs for a slower peer -- experimental: a 2-GPU bench run with it
+//                               hung (profiles/README.md), so it is off until that is understood
 //     finish():   the ctx stream waits for the last transfer, so a timer stopped on it covers every gather.
 // libnccl is loaded with dlopen at fmk_comm_init: single-GPU use of libfmk.so needs no NCCL at all.
 #include <dlfcn.h>
@@ -127,7 +129,7 @@ int fmk_comm_init(fmk_ctx *ctx, const void *id128, int rank, int world, int max_
     if (!c) return FMK_ERR_ALLOC;
     memset(c, 0, sizeof(*c));
     c->ctx = ctx; c->rank = rank; c->world = world; c->npending = 0; c->last = -1;
-    c->lag = 2;
+    c->lag = 1;
     if (const char *e = getenv("FMK_COMM_LAG")) c->lag = atoi(e) >= 1 && atoi(e) <= FMK_COMM_SLOTS - 1 ? atoi(e) : c->lag;
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
@@ -159,8 +161,8 @@ int fmk_comm_init(fmk_ctx *ctx, const void *id128, int rank, int world, int max_
     if (ce == cudaSuccess) ce = cudaMalloc(&c->scal_dev, 64 * sizeof(double));
     if (ce == cudaSuccess) ce = cudaHostAlloc(&c->scal_host, 64 * sizeof(double), cudaHostAllocDefault);
     if (ce != cudaSuccess) return fmk_fail(ctx, FMK_ERR_CUDA, cudaGetErrorString(ce));
-    // kernels whose grid is sized to fill an exact number of waves (the dollar task pass) must not count the SMs NCCL takes
-    if (world > 1) ctx->reserved_sms = max_ctas > 0 ? (max_ctas < ctx->sm_count / 2 ? max_ctas : ctx->sm_count / 2) : 16;
+    // (Measured and rejected: sizing the dollar task pass's waves without the SMs NCCL may take -- ctx->reserved_sms = maxCTAs --
+    //  made the pass 0.3 ms slower at every N and no faster on the receiving rank at N = 8: 3.93 ms either way with 16 CTAs.)
     *out = c;
     return FMK_OK;
 }
@@ -323,7 +325,7 @@ int fmk_comm_gather_reset(fmk_comm *c) {
         cudaFree(c->recv[s]); c->recv[s] = nullptr; c->recv_cap[s] = 0;
         c->has_done[s] = 0;
     }
-    c->k = 0; c->last = -1; c->lag = 2;
+    c->k = 0; c->last = -1; c->lag = 1;
     if (const char *e = getenv("FMK_COMM_LAG")) c->lag = atoi(e) >= 1 && atoi(e) <= FMK_COMM_SLOTS - 1 ? atoi(e) : c->lag;
     return FMK_OK;
 }
