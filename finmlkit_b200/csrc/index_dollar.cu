@@ -99,15 +99,21 @@ struct GuessOut {
 constexpr int DT_WARPS = 4;
 constexpr int DT_R = 8;
 
+// PF = L2 prefetch size of the copy (0: none): a task row advances 64 bytes per round, so without it DRAM serves ~85 000
+// interleaved 64-byte streams; with .L2::128B / .L2::256B the row's next rounds are already in L2.
+template <int PF = 0>
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+    if (PF == 256) asm volatile("cp.async.ca.shared.global.L2::256B [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+    else if (PF == 128) asm volatile("cp.async.ca.shared.global.L2::128B [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(DT_WARPS * 32) k_dollar_tasks(const double *__restrict__ p, const double *__restrict__ v,
+template <int PF>
+__global__ void __launch_bounds__(DT_WARPS * 32) k_dollar_tasks_t(const double *__restrict__ p, const double *__restrict__ v,
                                                                 DollarParams P, int64_t nt,
                                                                 const int64_t *__restrict__ K_in,
                                                                 const double *__restrict__ carry,
@@ -123,31 +129,52 @@ __global__ void __launch_bounds__(DT_WARPS * 32) k_dollar_tasks(const double *__
     bool active = k < nt;
     if (active) pos = dollar_task_init(t, P, k, k > 0 ? carry[k] : 0.0, k > 0 ? K_in[k] : 0, k == 0 ? __dmul_rn(p[0], v[0]) : 0.0);
     else { t.B = -1; t.K = 0; t.cnt = 0; t.end_idx = -2; t.nch = DC_NCH; t.start_units = 0; t.phase = 3; }
+    // Every task of the warp advances DT_R ticks per round, so row r of the tile (task kw + r) is always at tick
+    // (kw + r) * CH + adv: the copy addresses need no per-row hand-over (the shuffle version spent 170 of the ~600 warp
+    // instructions of a round on it), only the ballot of the lanes that are still replaying.
     const int sub = lane >> 3, col = lane & 7;     // 8 lanes copy one 64-byte row; 4 rows per instruction
-    auto stage = [&](int buf, int64_t at, bool on) {
+    const int64_t kw = ((int64_t)blockIdx.x * DT_WARPS + w) * 32;
+    const int64_t row0 = (kw + sub) * P.CH + col, rowstep = 4 * P.CH;
+    int skip = 0;
+    if (k == 0) { pos = 0; skip = 1; }             // task 0 starts at tick 1 with c = p0 * v0: its row still starts at tick 0
+    auto stage = [&](int buf, int64_t adv, unsigned act) {
+        const bool inside = (kw + 32) * P.CH + adv + DT_R <= n;      // warp-uniform: no row of this round reaches past n
+        if (inside) {
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const int row = 4 * q + sub;
-            const int64_t rp = __shfl_sync(0xffffffffu, at, row);
-            const int ra = __shfl_sync(0xffffffffu, (int)on, row);
-            const int64_t idx = rp + col;
-            if (ra && idx < n) {
-                cp_async8(&sp[buf][w][row][col], p + idx);
-                cp_async8(&sv[buf][w][row][col], v + idx);
+            for (int q = 0; q < 8; q++) {
+                const int row = 4 * q + sub;
+                const int64_t idx = row0 + q * rowstep + adv;
+                if ((act >> row) & 1u) {
+                    cp_async8<PF>(&sp[buf][w][row][col], p + idx);
+                    cp_async8<PF>(&sv[buf][w][row][col], v + idx);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int row = 4 * q + sub;
+                const int64_t idx = row0 + q * rowstep + adv;
+                if (((act >> row) & 1u) && idx < n) {
+                    cp_async8<PF>(&sp[buf][w][row][col], p + idx);
+                    cp_async8<PF>(&sv[buf][w][row][col], v + idx);
+                }
             }
         }
         cp_async_commit();
     };
     int buf = 0;
-    stage(0, pos, active);
+    int64_t adv = 0;
+    stage(0, 0, __ballot_sync(0xffffffffu, active));
     while (__any_sync(0xffffffffu, active)) {
-        stage(buf ^ 1, pos + DT_R, active);          // prefetch the next round
+        stage(buf ^ 1, adv + DT_R, __ballot_sync(0xffffffffu, active));          // prefetch the next round
+        adv += DT_R;
         cp_async_wait<1>();                           // the current round's copies have landed
         __syncwarp();
         if (active) {
             int m = DT_R;
             if (pos + DT_R > n) m = (int)(n - pos);
-            int tt = 0;
+            int tt = skip;
+            skip = 0;
             if (t.phase == 1) {   // approximate walk to the first boundary of the chunk
 #pragma unroll 1
                 for (; tt < m && t.phase == 1; tt++) {
@@ -157,12 +184,16 @@ __global__ void __launch_bounds__(DT_WARPS * 32) k_dollar_tasks(const double *__
             }
 #ifndef DC_EXPLICIT_CHAINS
             if (t.phase == 2) {   // exact replay: the tight loop
+                // the next tick's product is formed while the current one walks the dependent chain (the shared-memory
+                // load -> DMUL latency was the largest single stall of the loop); column DT_R is the row's padding
+                double d = __dmul_rn(sp[buf][w][lane][tt], sv[buf][w][lane][tt]);
 #pragma unroll 1
                 for (; tt < m; tt++) {
-                    const double d = __dmul_rn(sp[buf][w][lane][tt], sv[buf][w][lane][tt]);
+                    const double dn = __dmul_rn(sp[buf][w][lane][tt + 1], sv[buf][w][lane][tt + 1]);
                     if (dollar_virtual_tick(t, d, P)) {
                         if (dollar_task_emit(t, P, pos + tt, out)) { active = false; break; }
                     }
+                    d = dn;
                 }
             }
 #else
@@ -184,6 +215,12 @@ __global__ void __launch_bounds__(DT_WARPS * 32) k_dollar_tasks(const double *__
         recs[k] = rec;
     }
 }
+
+// The shipped kernel copies with .L2::256B (measured at 1e9 ticks: 3.61 ms without, 3.61 ms with 128B, 3.32 ms with 256B);
+// FMK_DOLLAR_L2PF = 0 / 128 launches the other two (profiling A/B).
+static constexpr auto k_dollar_tasks = &k_dollar_tasks_t<256>;
+static constexpr auto k_dollar_tasks_pf128 = &k_dollar_tasks_t<128>;
+static constexpr auto k_dollar_tasks_pf0 = &k_dollar_tasks_t<0>;
 
 // status block shared between chain / serial kernels and the host
 struct DollarStatus {
@@ -463,8 +500,16 @@ int fmk_dollar_index_impl(fmk_ctx *ctx, const fmk_trades *t, double T, fmk_index
         K_total = hs.K_total;
     }
     if (fast) {
-    FMK_LAUNCH(ctx, k_dollar_tasks, (unsigned)cdiv(nt, DT_WARPS * 32), DT_WARPS * 32, 0, t->price, t->amount, P, nt,
-               (const int64_t *)K_in.p, (const double *)carry.p, idx, recs.p);
+    static const int l2pf = getenv("FMK_DOLLAR_L2PF") ? atoi(getenv("FMK_DOLLAR_L2PF")) : 256;
+    if (l2pf == 0)
+        FMK_LAUNCH(ctx, k_dollar_tasks_pf0, (unsigned)cdiv(nt, DT_WARPS * 32), DT_WARPS * 32, 0, t->price, t->amount, P, nt,
+                   (const int64_t *)K_in.p, (const double *)carry.p, idx, recs.p);
+    else if (l2pf == 128)
+        FMK_LAUNCH(ctx, k_dollar_tasks_pf128, (unsigned)cdiv(nt, DT_WARPS * 32), DT_WARPS * 32, 0, t->price, t->amount, P, nt,
+                   (const int64_t *)K_in.p, (const double *)carry.p, idx, recs.p);
+    else
+        FMK_LAUNCH(ctx, k_dollar_tasks, (unsigned)cdiv(nt, DT_WARPS * 32), DT_WARPS * 32, 0, t->price, t->amount, P, nt,
+                   (const int64_t *)K_in.p, (const double *)carry.p, idx, recs.p);
     Scratch<ChainElem> agg(ctx);
     FMK_TRY(agg.alloc(cdiv(nt, DC_THREADS) + 1));
     // task 0 runs from the exact initial state and decides how the chain is entered
