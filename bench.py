@@ -469,8 +469,13 @@ def timed_steps(ctx, step, steps, warmup, finish=None, comm=None):
     ctx.prof_enable(False)
     prof = ctx.prof_report()
     launches = ctx.launch_count() - l0
+    timed_steps.rank_ms = [ms / steps]
     if comm:
-        ms = float(comm.allreduce([ms], "max")[0])
+        mine = np.zeros(comm.world)
+        mine[comm.rank] = ms
+        every = comm.allreduce(mine, "sum")            # device-timed ms of every rank; the step time is their max
+        timed_steps.rank_ms = [float(x) / steps for x in every]
+        ms = float(every.max())
     kern = {k: v[1] / steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
     return ms / steps, kern, launches, prof
 
@@ -498,7 +503,12 @@ def run_ours(args):
         comm = Comm.from_env(ctx, max_ctas=env_int("FMK_NCCL_MAX_CTAS", 16))
     n = args.ticks
     sub_steps, sub_warm = max(1, min(args.steps, args.sub_steps)), 1
-    tr = core.DeviceTrades.synth(n, seed=42 + rank, ctx=ctx)   # one independent symbol per rank
+    # One independent symbol per rank.  The headline streams are the SAME synthetic symbol on every rank unless
+    # --distinct-streams: the step time depends on the stream (seeds 42..49 alone on one GPU: 9.5-11.1 ms per step, the slowest
+    # needs one exact serial repair per pass -- profiles/r02_stream_sweep_1e9.log), so only identical streams keep the per-GPU
+    # work fixed as N grows, which is what a weak-scaling figure assumes.  config5 always uses 8 different symbols.
+    seed = 42 + (rank if args.distinct_streams else 0)
+    tr = core.DeviceTrades.synth(n, seed=seed, ctx=ctx)
     peak, peak_src = measured_peak()
     log(f"rank {rank}/{world}: stream of {n} ticks ready")
 
@@ -523,6 +533,7 @@ def run_ours(args):
     clocks = ClockSampler(local)
     clocks.start()
     ms_per_step, kern, launches, prof = timed_steps(ctx, step, args.steps, 0, finish, comm)
+    rank_ms = list(timed_steps.rank_ms)
     clk = clocks.stop()
     stats = ctx.index_stats()
     value = world * n / (ms_per_step * 1e-3)
@@ -615,7 +626,7 @@ def run_ours(args):
     # ---- config 5: dollar bars + FULL feature set + gather of every frame (all N) ----------------------------------------
     if not args.no_sub and not args.no_config5:
         n5 = int(min(args.config5_ticks, n))
-        tr5 = tr if n5 == n else core.DeviceTrades.synth(n5, seed=1042 + rank, ctx=ctx)
+        tr5 = tr if (n5 == n and (world == 1 or args.distinct_streams)) else core.DeviceTrades.synth(n5, seed=1042 + rank, ctx=ctx)
 
         def step5():
             ix = core.dollar_bar_index(tr5, THRESHOLD)
@@ -624,13 +635,15 @@ def run_ours(args):
             state["c5_frame"] = fr
             if comm:
                 comm.gather_submit(fr.segments(), dst=0)
-        ms5, k5, _, _ = timed_steps(ctx, step5, sub_steps, sub_warm, finish, comm)
+        # two warm-up steps with a communicator: both pipeline slots size (and map) their multi-GB buffers before the timed region
+        ms5, k5, _, _ = timed_steps(ctx, step5, sub_steps, max(sub_warm, 2) if comm else sub_warm, finish, comm)
+        rank_ms5 = [round(x, 3) for x in timed_steps.rank_ms]
         rec5 = {"workload": f"BASELINE configs[4]: {n5} ticks per GPU, one symbol per GPU -> dollar bars ($1e6) + OHLCV incl. median + directional "
                             f"+ trade-size (theta = the bar's median size, x5) + footprint CSR, "
                             + ("one NCCL gather-v of every frame (per-bar block + footprint CSR block) to rank 0 per step" if comm else "single GPU: no gather"),
                 "ticks_per_s": world * n5 / (ms5 * 1e-3), "ms_per_step": ms5, "steps": sub_steps, "ticks_per_gpu": n5, "n_gpus": world,
                 "bars_per_gpu": state["c5"][0], "footprint_levels_per_gpu": state["c5"][1], "frame_bytes_per_gpu": state["c5"][2],
-                "kernels_ms_per_step_rank0": k5, "roofline": step_roofline("config5", n5, ms5, k5)}
+                "rank_ms_per_step": rank_ms5, "kernels_ms_per_step_rank0": k5, "roofline": step_roofline("config5", n5, ms5, k5)}
         if comm:
             # the gathered bytes on rank 0 equal what each rank produced: crc32 of every rank's own frame vs the received copy
             fr = state["c5_frame"]
@@ -641,8 +654,11 @@ def run_ours(args):
             ok = None
             if rank == 0:
                 ok = all(float(zlib.crc32(comm.gathered_frame(r).tobytes())) == crc[r] for r in range(world))
-            rec5["gather"] = {"bytes_per_step_total": sum(comm.gathered_bytes()), "received_equals_sent_crc32": ok,
-                              "nccl_version": int(L.fmk_comm_nccl_version())}
+            got_bytes = sum(comm.gathered_bytes())
+            rec5["gather"] = {"bytes_per_step_total": got_bytes, "received_equals_sent_crc32": ok,
+                              # every frame but rank 0's own crosses NVLink into ONE GPU: its ingress (900 GB/s nominal) bounds the step
+                              "rank0_ingress_bound_ms": round((got_bytes - comm.gathered_bytes()[0]) / 900e9 * 1e3, 2),
+                              "nccl_version": int(L.fmk_comm_nccl_version()), "payload_path": comm.payload_path}
         state.pop("c5_frame", None)
         sub["config5"] = rec5
         if tr5 is not tr:
@@ -667,6 +683,11 @@ def run_ours(args):
                            "ticks_per_gpu": n, "bars_per_gpu": state["nbars"], "threshold": THRESHOLD,
                            "l2": "inputs (16-24 GB/step) exceed the 126 MB L2; no flush needed" if n * 16 > 4e8 else "inputs fit L2: timing is warm-L2",
                            "parallelism": f"symbols x{world}", "index_stats": stats,
+                           "streams": ("a different synthetic symbol per rank (seed 42 + rank): the step time is the slowest stream's"
+                                       if args.distinct_streams or world == 1 else
+                                       "the same synthetic symbol (seed 42) on every rank: per-GPU work is exactly fixed as N grows; "
+                                       "--distinct-streams gives every rank its own symbol (profiles/r02_stream_sweep_1e9.log)"),
+                           "rank_ms_per_step": [round(x, 4) for x in rank_ms],
                            "gather_bytes_per_step": gather_bytes},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline}
         line.update(sub)
@@ -725,7 +746,7 @@ def run_e2e(args, core, ctx, comm, tr, n, rank, world, sub):
     if n_e == n:
         tr_e = tr
     else:
-        tr_e = core.DeviceTrades.synth(n_e, seed=42 + rank, ctx=ctx)
+        tr_e = core.DeviceTrades.synth(n_e, seed=42 + (rank if args.distinct_streams else 0), ctx=ctx)
     tr_e.download(out=(h_ts, h_px, h_qty, h_side))
 
     def wall(stepf, steps):
@@ -905,6 +926,8 @@ def main():
     ap.add_argument("--sub-steps", type=int, default=5, help="timed steps of the config 3/4/5 sub-records")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--distinct-streams", action="store_true",
+                    help="N > 1: a different synthetic symbol on every rank for the headline too (step time = the slowest stream)")
     ap.add_argument("--no-sub", action="store_true", help="headline only")
     ap.add_argument("--no-config5", action="store_true")
     args = ap.parse_args()

@@ -96,6 +96,7 @@ SIGNATURES = {
     "fmk_comm_rank": (INT, [P]),
     "fmk_comm_world": (INT, [P]),
     "fmk_comm_nccl_version": (INT, []),
+    "fmk_comm_p2p_active": (INT, [P]),
     "fmk_comm_barrier": (INT, [P]),
     "fmk_comm_allreduce_f64": (INT, [P, P, INT, INT]),
     "fmk_comm_gather_submit": (INT, [P, P, P, INT, INT]),

@@ -14,6 +14,13 @@
 //                               no NCCL kernel waits on SMs for a slower peer -- experimental: a 2-GPU bench run with it
 //                               hung (profiles/README.md), so it is off until that is understood
 //     finish():   the ctx stream waits for the last transfer, so a timer stopped on it covers every gather.
+// PAYLOAD PATH (default, one node): the destination exports its receive buffer with CUDA IPC and every other rank PUSHES its
+// frame into it with a peer-to-peer cudaMemcpyAsync over NVLink -- copy engines, no SM.  A tiny all-gather queued behind the
+// copy on every rank's comm stream is the completion fence (it finishes on the destination only after every rank's copy
+// has).  Why: ncclSend/ncclRecv kernels hold up to maxCTAs SMs for the length of the transfer, and the dollar task pass is a
+// single wave of long-lived blocks -- a block that finds its SM taken starts when the NCCL kernel ends, which cost 0.4 ms of
+// a 10 ms step at N = 2 and 1.5 ms at N = 8 (device-timed efficiency 0.87).  The grouped ncclSend/ncclRecv path is kept as
+// the fallback (FMK_COMM_P2P=0, or any rank failing to map the buffer -- decided collectively).
 // libnccl is loaded with dlopen at fmk_comm_init: single-GPU use of libfmk.so needs no NCCL at all.
 #include <dlfcn.h>
 #include <nccl.h>
@@ -89,6 +96,12 @@ struct fmk_comm {
     char *recv[FMK_COMM_SLOTS];                  // dst only: frames of all ranks, back to back
     int64_t recv_cap[FMK_COMM_SLOTS];
     int64_t recv_off[FMK_COMM_SLOTS][65];        // dst only: offsets of each rank's frame in recv[s]
+    // peer-to-peer push of the payload (CUDA IPC): the mapping of the destination's recv[s] on the other ranks
+    int p2p;                                     // 1: push with copy engines; 0: grouped ncclSend / ncclRecv
+    char *peer_recv[FMK_COMM_SLOTS];             // non-destination ranks: destination's recv[s] mapped into this process
+    int64_t agreed_cap[FMK_COMM_SLOTS];          // capacity of the destination's recv[s], tracked identically on every rank
+    int agreed_dst[FMK_COMM_SLOTS];
+    unsigned char *ipc_dev, *ipc_host;           // [world + 1][64]: all-gather buffer for the IPC handle (+ this rank's input)
     int pend_slot[FMK_COMM_SLOTS], pend_dst[FMK_COMM_SLOTS];   // FIFO of steps whose counts were exchanged but whose send/recv is not posted yet
     int npending, lag, nslots;
     int last;                       // slot of the last completed gather (-1: none)
@@ -160,7 +173,12 @@ int fmk_comm_init(fmk_ctx *ctx, const void *id128, int rank, int world, int max_
     }
     if (ce == cudaSuccess) ce = cudaMalloc(&c->scal_dev, 64 * sizeof(double));
     if (ce == cudaSuccess) ce = cudaHostAlloc(&c->scal_host, 64 * sizeof(double), cudaHostAllocDefault);
+    if (ce == cudaSuccess) ce = cudaMalloc(&c->ipc_dev, 64 * (size_t)(world + 1));
+    if (ce == cudaSuccess) ce = cudaHostAlloc(&c->ipc_host, 64 * (size_t)(world + 1), cudaHostAllocDefault);
     if (ce != cudaSuccess) return fmk_fail(ctx, FMK_ERR_CUDA, cudaGetErrorString(ce));
+    c->p2p = world > 1;
+    if (const char *e = getenv("FMK_COMM_P2P")) c->p2p = c->p2p && atoi(e) != 0;
+    for (int s = 0; s < FMK_COMM_SLOTS; s++) c->agreed_dst[s] = -1;
     // (Measured and rejected: sizing the dollar task pass's waves without the SMs NCCL may take -- ctx->reserved_sms = maxCTAs --
     //  made the pass 0.3 ms slower at every N and no faster on the receiving rank at N = 8: 3.93 ms either way with 16 CTAs.)
     *out = c;
@@ -171,7 +189,9 @@ void fmk_comm_destroy(fmk_comm *c) {
     if (!c) return;
     cudaSetDevice(c->ctx->device);
     cudaStreamSynchronize(c->stream);
-    if (c->comm) g_nccl.CommDestroy(c->comm);
+    for (int s = 0; s < FMK_COMM_SLOTS; s++)
+        if (c->peer_recv[s]) { cudaIpcCloseMemHandle(c->peer_recv[s]); c->peer_recv[s] = nullptr; }
+    if (c->comm) g_nccl.CommDestroy(c->comm);    // every rank has unmapped before any rank frees (CommDestroy is collective)
     for (int s = 0; s < FMK_COMM_SLOTS; s++) {
         cudaFree(c->staging[s]); cudaFree(c->recv[s]); cudaFree(c->counts_dev[s]); cudaFree(c->mine_dev[s]);
         cudaFreeHost(c->counts_host[s]); cudaFreeHost(c->mine_host[s]);
@@ -179,11 +199,14 @@ void fmk_comm_destroy(fmk_comm *c) {
     }
     cudaFree(c->scal_dev);
     cudaFreeHost(c->scal_host);
+    cudaFree(c->ipc_dev);
+    cudaFreeHost(c->ipc_host);
     cudaStreamDestroy(c->stream);
     delete c;
 }
 
 int fmk_comm_rank(const fmk_comm *c) { return c->rank; }
+int fmk_comm_p2p_active(const fmk_comm *c) { return c->p2p; }
 int fmk_comm_world(const fmk_comm *c) { return c->world; }
 
 // Host-value all-reduce (op: 0 = max, 1 = min, 2 = sum) of n <= 64 doubles; also the barrier (n = 0 reduces one dummy).
@@ -218,7 +241,64 @@ static int comm_grow(fmk_ctx *ctx, char **buf, int64_t *cap, int64_t need, cudaS
     return FMK_OK;
 }
 
-// post the send / recv of the slot whose byte counts have been exchanged
+// tiny all-gather of one int64 per rank on the comm stream, waited for on the host: barrier + 1 word of agreement
+static int comm_agree(fmk_comm *c, int s, int64_t mine, int64_t *all /* [world] */) {
+    fmk_ctx *ctx = c->ctx;
+    *c->mine_host[s] = mine;
+    FMK_CUDA(ctx, cudaMemcpyAsync(c->mine_dev[s], c->mine_host[s], 8, cudaMemcpyHostToDevice, c->stream));
+    FMK_NCCL(ctx, g_nccl.AllGather(c->mine_dev[s], c->counts_dev[s], 1, ncclInt64, c->comm, c->stream));
+    FMK_CUDA(ctx, cudaMemcpyAsync(all, c->counts_dev[s], 8 * (size_t)c->world, cudaMemcpyDeviceToHost, c->stream));
+    FMK_CUDA(ctx, cudaStreamSynchronize(c->stream));
+    return FMK_OK;
+}
+
+// Collective (every rank takes the same decision from the same byte counts): (re)allocate the destination's receive buffer of
+// slot s with `want` bytes, export it with CUDA IPC and map it on the other ranks.  Order matters: the others unmap, a barrier,
+// the destination frees / allocates / exports, the handle travels in an all-gather, the others map, and a last word of
+// agreement turns the peer-to-peer path off everywhere if any rank could not map.
+static int comm_p2p_regrow(fmk_comm *c, int s, int dst, int64_t want) {
+    fmk_ctx *ctx = c->ctx;
+    int64_t *all = reinterpret_cast<int64_t *>(c->ipc_host);       // scratch for comm_agree ([world] int64 <= 64 * (world + 1) bytes)
+    FMK_CUDA(ctx, cudaStreamSynchronize(c->stream));
+    if (c->peer_recv[s]) { cudaIpcCloseMemHandle(c->peer_recv[s]); c->peer_recv[s] = nullptr; }
+    FMK_TRY(comm_agree(c, s, 0, all));                             // every rank has unmapped the old buffer
+    unsigned char *mine = c->ipc_host + 64 * (size_t)c->world;
+    memset(mine, 0, 64);
+    int64_t ok = 1;
+    if (c->rank == dst) {
+        FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (c->recv[s]) cudaFree(c->recv[s]);
+        c->recv[s] = nullptr; c->recv_cap[s] = 0;
+        FMK_CUDA(ctx, cudaMalloc((void **)&c->recv[s], (size_t)want));
+        c->recv_cap[s] = want;
+        cudaIpcMemHandle_t h;
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle travels as 64 bytes");
+        if (cudaIpcGetMemHandle(&h, c->recv[s]) == cudaSuccess) memcpy(mine, &h, 64);
+        else { ok = 0; cudaGetLastError(); }
+    }
+    FMK_CUDA(ctx, cudaMemcpyAsync(c->ipc_dev + 64 * (size_t)c->world, mine, 64, cudaMemcpyHostToDevice, c->stream));
+    FMK_NCCL(ctx, g_nccl.AllGather(c->ipc_dev + 64 * (size_t)c->world, c->ipc_dev, 64, ncclUint8, c->comm, c->stream));
+    FMK_CUDA(ctx, cudaMemcpyAsync(c->ipc_host, c->ipc_dev, 64 * (size_t)c->world, cudaMemcpyDeviceToHost, c->stream));
+    FMK_CUDA(ctx, cudaStreamSynchronize(c->stream));
+    if (c->rank != dst) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, c->ipc_host + 64 * (size_t)dst, 64);
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) c->peer_recv[s] = (char *)p;
+        else { ok = 0; cudaGetLastError(); }
+    }
+    FMK_TRY(comm_agree(c, s, ok, all));
+    for (int r = 0; r < c->world; r++) ok &= all[r];
+    if (!ok) {                                                     // some rank cannot map: everybody falls back to send / recv
+        if (c->peer_recv[s]) { cudaIpcCloseMemHandle(c->peer_recv[s]); c->peer_recv[s] = nullptr; }
+        c->p2p = 0;
+    }
+    c->agreed_cap[s] = want;
+    c->agreed_dst[s] = dst;
+    return FMK_OK;
+}
+
+// post the transfer of the slot whose byte counts have been exchanged
 static int comm_complete_oldest(fmk_comm *c) {
     fmk_ctx *ctx = c->ctx;
     if (c->npending <= 0) return FMK_OK;
@@ -226,25 +306,37 @@ static int comm_complete_oldest(fmk_comm *c) {
     for (int q = 1; q < c->npending; q++) { c->pend_slot[q - 1] = c->pend_slot[q]; c->pend_dst[q - 1] = c->pend_dst[q]; }
     c->npending--;
     FMK_CUDA(ctx, cudaEventSynchronize(c->sized[s]));
-    const int64_t *cnt = c->counts_host[s];
-    if (c->rank == dst) {
-        int64_t tot = 0;
-        for (int r = 0; r < c->world; r++) { c->recv_off[s][r] = tot; tot += (cnt[r] + 255) / 256 * 256; }
-        c->recv_off[s][c->world] = tot;
-        FMK_TRY(comm_grow(ctx, &c->recv[s], &c->recv_cap[s], tot, c->stream));
+    int64_t cnt[64];
+    for (int r = 0; r < c->world; r++) cnt[r] = c->counts_host[s][r];     // (the pinned block doubles as scratch below)
+    int64_t tot = 0;
+    for (int r = 0; r < c->world; r++) { c->recv_off[s][r] = tot; tot += (cnt[r] + 255) / 256 * 256; }
+    c->recv_off[s][c->world] = tot;
+    if (c->p2p && (tot > c->agreed_cap[s] || dst != c->agreed_dst[s])) {
+        FMK_TRY(comm_p2p_regrow(c, s, dst, tot + tot / 4 + 4096));
+        for (int r = 0; r < c->world; r++) c->counts_host[s][r] = cnt[r];
     }
-    FMK_NCCL(ctx, g_nccl.GroupStart());
-    if (c->rank == dst) {
-        for (int r = 0; r < c->world; r++) {
-            if (r == dst || cnt[r] == 0) continue;
-            FMK_NCCL(ctx, g_nccl.Recv(c->recv[s] + c->recv_off[s][r], (size_t)cnt[r], ncclUint8, r, c->comm, c->stream));
+    if (c->p2p) {
+        if (cnt[c->rank] > 0) {
+            char *to = (c->rank == dst ? c->recv[s] : c->peer_recv[s]) + c->recv_off[s][c->rank];
+            FMK_CUDA(ctx, cudaMemcpyAsync(to, c->staging[s], (size_t)cnt[c->rank], cudaMemcpyDefault, c->stream));
         }
-    } else if (cnt[c->rank] > 0) {
-        FMK_NCCL(ctx, g_nccl.Send(c->staging[s], (size_t)cnt[c->rank], ncclUint8, dst, c->comm, c->stream));
+        // completion fence: queued behind the copy on every rank, so it ends on `dst` only after every rank's push has landed
+        FMK_NCCL(ctx, g_nccl.AllGather(c->mine_dev[s], c->counts_dev[s], 1, ncclInt64, c->comm, c->stream));
+    } else {
+        if (c->rank == dst) FMK_TRY(comm_grow(ctx, &c->recv[s], &c->recv_cap[s], tot, c->stream));
+        FMK_NCCL(ctx, g_nccl.GroupStart());
+        if (c->rank == dst) {
+            for (int r = 0; r < c->world; r++) {
+                if (r == dst || cnt[r] == 0) continue;
+                FMK_NCCL(ctx, g_nccl.Recv(c->recv[s] + c->recv_off[s][r], (size_t)cnt[r], ncclUint8, r, c->comm, c->stream));
+            }
+        } else if (cnt[c->rank] > 0) {
+            FMK_NCCL(ctx, g_nccl.Send(c->staging[s], (size_t)cnt[c->rank], ncclUint8, dst, c->comm, c->stream));
+        }
+        FMK_NCCL(ctx, g_nccl.GroupEnd());
+        if (c->rank == dst && cnt[dst] > 0)   // own frame: device-to-device on the comm stream
+            FMK_CUDA(ctx, cudaMemcpyAsync(c->recv[s] + c->recv_off[s][dst], c->staging[s], (size_t)cnt[dst], cudaMemcpyDeviceToDevice, c->stream));
     }
-    FMK_NCCL(ctx, g_nccl.GroupEnd());
-    if (c->rank == dst && cnt[dst] > 0)   // own frame: device-to-device on the comm stream
-        FMK_CUDA(ctx, cudaMemcpyAsync(c->recv[s] + c->recv_off[s][dst], c->staging[s], (size_t)cnt[dst], cudaMemcpyDeviceToDevice, c->stream));
     FMK_CUDA(ctx, cudaEventRecord(c->done[s], c->stream));
     c->has_done[s] = 1;
     c->last = s;
@@ -311,7 +403,7 @@ int fmk_comm_gather_finish(fmk_comm *c) {
     return FMK_OK;
 }
 
-// Ends a sequence of gather steps: waits for everything outstanding, releases the staging / receive buffers and lets the next
+// Ends a sequence of gather steps (COLLECTIVE: every rank calls it): waits for everything outstanding, releases the staging / receive buffers and lets the next
 // fmk_comm_gather_submit size the pipeline afresh (a host that gathers small OHLCV frames first and multi-GB footprint
 // frames later must not keep three receive slots of the large size).
 int fmk_comm_gather_reset(fmk_comm *c) {
@@ -320,6 +412,16 @@ int fmk_comm_gather_reset(fmk_comm *c) {
     FMK_TRY(fmk_comm_gather_finish(c));
     FMK_CUDA(ctx, cudaStreamSynchronize(c->stream));
     FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    bool mapped = false;
+    for (int s = 0; s < FMK_COMM_SLOTS; s++) {
+        if (c->peer_recv[s]) { cudaIpcCloseMemHandle(c->peer_recv[s]); c->peer_recv[s] = nullptr; }
+        mapped |= c->agreed_dst[s] >= 0;
+        c->agreed_cap[s] = 0; c->agreed_dst[s] = -1;
+    }
+    if (mapped && c->world > 1) {      // collective: nobody frees an exported buffer before every rank has unmapped it
+        int64_t all[64];
+        FMK_TRY(comm_agree(c, 0, 0, all));
+    }
     for (int s = 0; s < FMK_COMM_SLOTS; s++) {
         cudaFree(c->staging[s]); c->staging[s] = nullptr; c->staging_cap[s] = 0;
         cudaFree(c->recv[s]); c->recv[s] = nullptr; c->recv_cap[s] = 0;

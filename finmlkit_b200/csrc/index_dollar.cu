@@ -380,9 +380,14 @@ __global__ void __launch_bounds__(32) k_dollar_serial(const double *__restrict__
     if (c_from_first) c = __dmul_rn(p[0], v[0]);   // logic.py:142 cum_dollar = prices[0] * volumes[0]
     int64_t cnt = 0, pos_out = -2;
     bool overflow = false;
-    for (int64_t base = pos + 1; base < n && pos_out == -2; base += 32) {
+    auto tile = [&](int64_t base) {                    // this lane's product of the 32-tick tile starting at `base`
         const int64_t i = base + lane;
-        const double d = i < n ? __dmul_rn(__ldg(p + i), __ldg(v + i)) : 0.0;
+        return i < n ? __dmul_rn(__ldg(p + i), __ldg(v + i)) : 0.0;
+    };
+    double d_next = tile(pos + 1);
+    for (int64_t base = pos + 1; base < n && pos_out == -2; base += 32) {
+        const double d = d_next;
+        d_next = tile(base + 32);                      // in flight while the chain walks the current tile (the loads were half of the loop's time)
         const int m = (n - base) < 32 ? (int)(n - base) : 32;
         for (int q = 0; q < m; q++) {
             c = __dadd_rn(c, __shfl_sync(0xffffffffu, d, q));

@@ -156,6 +156,11 @@ class Comm:
     def barrier(self):
         self.ctx.check(self._L.fmk_comm_barrier(self.h))
 
+    @property
+    def payload_path(self) -> str:
+        """how frames travel: peer-to-peer pushes into the destination's IPC-mapped buffer (copy engines), or NCCL send/recv"""
+        return "p2p-ipc-copy-engine" if self._L.fmk_comm_p2p_active(self.h) else "nccl-send-recv"
+
     def allreduce(self, values, op="max"):
         a = np.ascontiguousarray(values, dtype=np.float64).reshape(-1).copy()
         self.ctx.check(self._L.fmk_comm_allreduce_f64(self.h, a.ctypes.data_as(C.c_void_p), len(a), {"max": 0, "min": 1, "sum": 2}[op]))
@@ -172,7 +177,8 @@ class Comm:
         self.ctx.check(self._L.fmk_comm_gather_finish(self.h))
 
     def gather_reset(self):
-        """finish, release the staging / receive buffers, and let the next submit size the pipeline from its own frame"""
+        """finish, release the staging / receive buffers, and let the next submit size the pipeline from its own frame
+        (collective: every rank calls it)"""
         self.ctx.check(self._L.fmk_comm_gather_reset(self.h))
 
     def gathered_bytes(self):

@@ -204,8 +204,10 @@ void fmk_frame_free(fmk_ctx *ctx, fmk_frame *f);
  * One process per GPU.  Rank 0 calls fmk_comm_unique_id and hands the 128 bytes to the other ranks (any side channel);
  * every rank then calls fmk_comm_init with its own ctx.  libnccl.so.2 is loaded with dlopen at that point.
  * max_ctas > 0 caps the SMs NCCL may occupy.  A gather step packs up to 8 device segments into this rank's frame and
- * sends exactly that many bytes (ncclAllGather of the byte counts, then grouped ncclSend / ncclRecv); the transfer of
- * step k overlaps the kernels of step k+1.  fmk_comm_gather_finish makes the ctx stream wait for all transfers. */
+ * sends exactly that many bytes: ncclAllGather of the byte counts, then every rank pushes its frame into the destination's
+ * receive buffer (mapped with CUDA IPC) with a peer-to-peer copy over NVLink -- copy engines, no SM -- fenced by a tiny
+ * all-gather; grouped ncclSend / ncclRecv is the fallback (FMK_COMM_P2P=0 or a rank that cannot map the buffer).  The transfer
+ * of step k overlaps the kernels of step k+1.  fmk_comm_gather_finish makes the ctx stream wait for all transfers. */
 typedef struct fmk_comm fmk_comm;
 int fmk_comm_unique_id(void *out128);
 int fmk_comm_init(fmk_ctx *ctx, const void *id128, int rank, int world, int max_ctas, fmk_comm **out);
@@ -213,12 +215,14 @@ void fmk_comm_destroy(fmk_comm *c);
 int fmk_comm_rank(const fmk_comm *c);
 int fmk_comm_world(const fmk_comm *c);
 int fmk_comm_nccl_version(void);
+/* 1: payloads travel as peer-to-peer pushes (CUDA IPC + copy engines); 0: grouped ncclSend / ncclRecv */
+int fmk_comm_p2p_active(const fmk_comm *c);
 int fmk_comm_barrier(fmk_comm *c);
 /* op: 0 = max, 1 = min, 2 = sum over ranks of n <= 64 host doubles (in place) */
 int fmk_comm_allreduce_f64(fmk_comm *c, double *inout, int n, int op);
 int fmk_comm_gather_submit(fmk_comm *c, const void *const *seg_ptrs, const int64_t *seg_bytes, int nseg, int dst);
 int fmk_comm_gather_finish(fmk_comm *c);
-/* finish + release the staging / receive buffers; the next submit sizes the pipeline from its own frame */
+/* finish + release the staging / receive buffers; the next submit sizes the pipeline from its own frame.  COLLECTIVE. */
 int fmk_comm_gather_reset(fmk_comm *c);
 int fmk_comm_gather_result(fmk_comm *c, int rank, void **dev_ptr, int64_t *bytes);
 int fmk_comm_gather_download(fmk_comm *c, int rank, void *host, int64_t cap);

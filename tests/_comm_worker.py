@@ -41,6 +41,8 @@ def main():
         del fr, ix
         if step == 1:                       # also exercise finish() in the middle of the pipeline
             comm.gather_finish()
+        if step == 2 and os.environ.get("FMK_COMM_TEST_RESET"):      # ... and the collective reset (buffers released, remapped)
+            comm.gather_reset()
     comm.gather_finish()
     ctx.sync()
     comm.barrier()
@@ -52,7 +54,7 @@ def main():
             got = comm.gathered_frame(r)
             assert sizes[r] == len(exp), (r, sizes, len(exp))
             assert np.array_equal(got, exp), f"rank {r}: gathered bytes differ from the frame that rank packed"
-        print("GATHER_OK", sizes, flush=True)
+        print("GATHER_OK", comm.payload_path, sizes, flush=True)
     comm.barrier()
     comm.destroy()
     time.sleep(0.1)

@@ -206,25 +206,34 @@ def test_comm_single_rank_gather(ctx):
         comm.destroy()
 
 
-def test_comm_two_ranks_gather_equals_each_ranks_frame(tmp_path):
+@pytest.mark.parametrize("p2p,reset", [("1", ""), ("1", "1"), ("0", "")])
+def test_comm_two_ranks_gather_equals_each_ranks_frame(tmp_path, p2p, reset):
     """world = 2 on two GPUs (skipped on a one-GPU box; run with `gpurun --gpus 2`): rank 0 receives exactly the bytes rank 1
-    packed, for frames of different sizes, with the transfer of step k overlapping step k+1."""
+    packed, for frames of different sizes, with the transfer of step k overlapping step k+1 -- through the peer-to-peer push
+    (CUDA IPC mapping of rank 0's receive buffer, with and without a collective reset in the middle) and through the
+    ncclSend / ncclRecv fallback."""
     from finmlkit_b200 import _lib
     if _lib.lib().fmk_device_count() < 2:
         pytest.skip("needs two GPUs")
     env = dict(os.environ)
     env.update({"WORLD_SIZE": "2", "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": "29617", "FMK_STORE_DIR": str(tmp_path),
-                "FMK_COMM_TEST_DIR": str(tmp_path)})
+                "FMK_COMM_TEST_DIR": str(tmp_path), "FMK_COMM_P2P": p2p, "FMK_COMM_TEST_RESET": reset})
     procs = []
     for r in range(2):
         e = dict(env)
         e.update({"RANK": str(r), "LOCAL_RANK": str(r)})
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_comm_worker.py")], env=e,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
-    outs = [p.communicate(timeout=600)[0] for p in procs]
+    try:
+        outs = [p.communicate(timeout=150)[0] for p in procs]
+    except subprocess.TimeoutExpired:
+        for p in procs:
+            p.kill()
+        pytest.fail("two-rank communicator test hung: " + " | ".join((p.communicate()[0] or "")[-1500:] for p in procs))
     for r, p in enumerate(procs):
         assert p.returncode == 0, f"rank {r}:\n{outs[r][-3000:]}"
     assert "GATHER_OK" in outs[0]
+    assert ("p2p-ipc-copy-engine" if p2p == "1" else "nccl-send-recv") in outs[0], outs[0][-2000:]
 
 
 @pytest.mark.parametrize("kind,thr", [(0, 7.0), (0, 60.0), (0, 2.5), (1, 40.0), (1, 900.0)])
