@@ -26,7 +26,10 @@ def to_bytes(v, u):
     return v * m.get(u, 1)
 for r in rows[2:]:
     name = r[col["Kernel Name"]].split("(")[0]
-    lines.append(f"## {name}\n")
+    if name.startswith("void "): name = name[5:]
+    shown = name
+    name = {"k_dollar_tasks_t": "k_dollar_tasks"}.get(name.split("<")[0], name.split("<")[0] if name.split("<")[0] in ALGO else name)
+    lines.append(f"## {shown}\n")
     lines.append("| metric | value |\n|---|---|")
     for key, label in want:
         if key in col:
