@@ -185,13 +185,16 @@ int fmk_comm_init(fmk_ctx *ctx, const void *id128, int rank, int world, int max_
     return FMK_OK;
 }
 
+static int comm_unmap_all(fmk_comm *c);
+
+// COLLECTIVE when frames were gathered with the peer-to-peer push (every rank unmaps before the destination frees).
 void fmk_comm_destroy(fmk_comm *c) {
     if (!c) return;
     cudaSetDevice(c->ctx->device);
     cudaStreamSynchronize(c->stream);
-    for (int s = 0; s < FMK_COMM_SLOTS; s++)
-        if (c->peer_recv[s]) { cudaIpcCloseMemHandle(c->peer_recv[s]); c->peer_recv[s] = nullptr; }
-    if (c->comm) g_nccl.CommDestroy(c->comm);    // every rank has unmapped before any rank frees (CommDestroy is collective)
+    cudaStreamSynchronize(c->ctx->stream);
+    if (c->comm) comm_unmap_all(c);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
     for (int s = 0; s < FMK_COMM_SLOTS; s++) {
         cudaFree(c->staging[s]); cudaFree(c->recv[s]); cudaFree(c->counts_dev[s]); cudaFree(c->mine_dev[s]);
         cudaFreeHost(c->counts_host[s]); cudaFreeHost(c->mine_host[s]);
@@ -295,6 +298,22 @@ static int comm_p2p_regrow(fmk_comm *c, int s, int dst, int64_t want) {
     }
     c->agreed_cap[s] = want;
     c->agreed_dst[s] = dst;
+    return FMK_OK;
+}
+
+// Collective: every rank unmaps the destination's receive buffers, then a barrier -- an exported buffer must not be freed
+// while another process still has it mapped.  (No-op when nothing was ever exported.)
+static int comm_unmap_all(fmk_comm *c) {
+    bool mapped = false;
+    for (int s = 0; s < FMK_COMM_SLOTS; s++) {
+        if (c->peer_recv[s]) { cudaIpcCloseMemHandle(c->peer_recv[s]); c->peer_recv[s] = nullptr; }
+        mapped |= c->agreed_dst[s] >= 0;
+        c->agreed_cap[s] = 0; c->agreed_dst[s] = -1;
+    }
+    if (mapped && c->world > 1) {
+        int64_t all[64];
+        FMK_TRY(comm_agree(c, 0, 0, all));
+    }
     return FMK_OK;
 }
 
@@ -412,16 +431,7 @@ int fmk_comm_gather_reset(fmk_comm *c) {
     FMK_TRY(fmk_comm_gather_finish(c));
     FMK_CUDA(ctx, cudaStreamSynchronize(c->stream));
     FMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    bool mapped = false;
-    for (int s = 0; s < FMK_COMM_SLOTS; s++) {
-        if (c->peer_recv[s]) { cudaIpcCloseMemHandle(c->peer_recv[s]); c->peer_recv[s] = nullptr; }
-        mapped |= c->agreed_dst[s] >= 0;
-        c->agreed_cap[s] = 0; c->agreed_dst[s] = -1;
-    }
-    if (mapped && c->world > 1) {      // collective: nobody frees an exported buffer before every rank has unmapped it
-        int64_t all[64];
-        FMK_TRY(comm_agree(c, 0, 0, all));
-    }
+    FMK_TRY(comm_unmap_all(c));
     for (int s = 0; s < FMK_COMM_SLOTS; s++) {
         cudaFree(c->staging[s]); c->staging[s] = nullptr; c->staging_cap[s] = 0;
         cudaFree(c->recv[s]); c->recv[s] = nullptr; c->recv_cap[s] = 0;
